@@ -1,0 +1,1142 @@
+// oracle/oracle.hpp — TEST INFRASTRUCTURE ONLY (the parity checker and the timed CPU baseline).
+//
+// A CPU restatement, function by function and floating-point operation by floating-point operation, of the
+// per-pixel render path of antoinehebert/ray-tracer-challenge-rust (Camera::render -> World::color_at and
+// everything beneath it).  The Rust toolchain is absent from this image (no cargo/rustc), so the reference cannot be
+// compiled or run here; the crate has no third-party dependencies (Cargo.toml:9), only `std`, whose f64 operations
+// are IEEE-754 basic ops plus libm pow/tan/sin/cos.  This file follows the reference sources in /root/reference/src
+// (cited as file:line below).  It must be compiled with  -O2 -ffp-contract=off -fno-fast-math  so that gcc emits
+// the same rounding sequence rustc does (rustc never contracts a*b+c into an FMA and never re-associates).
+//
+// Pinning: every known-answer test the reference holds for this path (its inline #[test] functions) is re-stated in
+// oracle/kat.cpp and runs green; the reference's golden images are stripped from the mount
+// (.MISSING_LARGE_BLOBS:1-3) and the reference cannot run here, so whole-frame output below the 1e-5 tolerance of
+// those tests is pinned by code fidelity only.
+//
+// Nothing under ray-tracer-challenge-rust_b200/ (the product) includes, links or calls this file.  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, as the checker or as the
+// timed CPU arm — never as the product path.
+//
+// Two execution modes that produce bit-identical pixels:
+//   faithful : exactly the reference's algorithm, including its costs — Matrix::inverse() recomputed inside every
+//              Shape::intersect (shape.rs:249-253) and Bounds::new() recomputed per ray per group (shape.rs:401).
+//              This is what `cargo run --release` executes; it is the timed "reference CPU path".
+//   cached   : the same arithmetic with those two pure, ray-independent values computed once per scene.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <memory>
+#include <optional>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+
+namespace orc {
+
+// A Rust panic!/expect/assert! becomes this exception; the C API turns it into an error code + message.
+struct Panic : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+#define ORC_ASSERT(c, msg) do { if (!(c)) throw ::orc::Panic(msg); } while (0)
+
+// ---------------------------------------------------------------------------------------------- utils.rs:1-6
+constexpr double EPSILON = 0.00001;
+inline bool is_almost_equal(double a, double b) { return std::fabs(a - b) < EPSILON; }
+
+// f64::min / f64::max ignore a NaN operand (Rust std), like C fmin/fmax.
+inline double fmin_(double a, double b) { return std::fmin(a, b); }
+inline double fmax_(double a, double b) { return std::fmax(a, b); }
+
+// ---------------------------------------------------------------------------------------------- tuple.rs:6-152
+struct Tuple {
+    double x, y, z, w;
+    static Tuple zero() { return {0., 0., 0., 0.}; }
+    static Tuple point(double x, double y, double z) { return {x, y, z, 1.0}; }
+    static Tuple vector(double x, double y, double z) { return {x, y, z, 0.0}; }
+    bool is_point() const { return w == 1.0; }
+    bool is_vector() const { return w == 0.0; }
+    // tuple.rs:43-48  (powf(2.) lowers to x*x; the w term is included, left-to-right sum)
+    double magnitude() const {
+        ORC_ASSERT(is_vector(), "assertion failed: self.is_vector()");
+        return std::sqrt(x * x + y * y + z * z + w * w);
+    }
+    // tuple.rs:50-66
+    Tuple normalize() const {
+        ORC_ASSERT(is_vector(), "assertion failed: self.is_vector()");
+        double m = magnitude();
+        if (m == 0.0) return zero();
+        return {x / m, y / m, z / m, w / m};
+    }
+    // tuple.rs:68-73
+    double dot(const Tuple& o) const {
+        ORC_ASSERT(is_vector(), "assertion failed: self.is_vector()");
+        return x * o.x + y * o.y + z * o.z + w * o.w;
+    }
+    // tuple.rs:75-83
+    Tuple cross(const Tuple& o) const {
+        ORC_ASSERT(is_vector() && o.is_vector(), "assertion failed: self.is_vector() && other.is_vector()");
+        return vector(y * o.z - z * o.y, z * o.x - x * o.z, x * o.y - y * o.x);
+    }
+    Tuple reflect(const Tuple& normal) const;  // tuple.rs:86-90
+    // tuple.rs:93-100 (approximate)
+    bool operator==(const Tuple& o) const {
+        return is_almost_equal(x, o.x) && is_almost_equal(y, o.y) && is_almost_equal(z, o.z) &&
+               is_almost_equal(w, o.w);
+    }
+};
+inline Tuple operator+(const Tuple& a, const Tuple& b) { return {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+inline Tuple operator-(const Tuple& a, const Tuple& b) { return {a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w}; }
+inline Tuple operator-(const Tuple& a) { return {-a.x, -a.y, -a.z, -a.w}; }
+inline Tuple operator*(const Tuple& a, double s) { return {a.x * s, a.y * s, a.z * s, a.w * s}; }
+inline Tuple operator/(const Tuple& a, double s) { return {a.x / s, a.y / s, a.z / s, a.w / s}; }
+// tuple.rs:89:  (*self) - (*normal) * 2. * self.dot(normal)   ==  self - ((normal*2)*dot)
+inline Tuple Tuple::reflect(const Tuple& normal) const {
+    ORC_ASSERT(is_vector(), "assertion failed: self.is_vector()");
+    return (*this) - (normal * 2.) * this->dot(normal);
+}
+
+// ---------------------------------------------------------------------------------------------- color.rs:35-98
+struct Color {
+    double red, green, blue;
+    bool operator==(const Color& o) const {
+        return is_almost_equal(red, o.red) && is_almost_equal(green, o.green) && is_almost_equal(blue, o.blue);
+    }
+};
+inline Color operator+(const Color& a, const Color& b) { return {a.red + b.red, a.green + b.green, a.blue + b.blue}; }
+inline Color operator-(const Color& a, const Color& b) { return {a.red - b.red, a.green - b.green, a.blue - b.blue}; }
+inline Color operator*(const Color& a, double s) { return {a.red * s, a.green * s, a.blue * s}; }
+inline Color operator*(const Color& a, const Color& b) { return {a.red * b.red, a.green * b.green, a.blue * b.blue}; }
+static const Color BLACK{0., 0., 0.}, WHITE{1., 1., 1.}, RED{1., 0., 0.}, GREEN{0., 1., 0.}, BLUE{0., 0., 1.};
+
+// ---------------------------------------------------------------------------------------------- matrix.rs:6-227
+template <int N>
+struct Matrix {
+    double v[N][N];
+    static Matrix zero() {
+        Matrix m;
+        for (int r = 0; r < N; r++)
+            for (int c = 0; c < N; c++) m.v[r][c] = 0.;
+        return m;
+    }
+    static Matrix identity() {
+        Matrix m = zero();
+        for (int i = 0; i < N; i++) m.v[i][i] = 1.;
+        return m;
+    }
+    // matrix.rs:29-39 (hard-coded 4 in the reference; only ever called on Matrix<4>)
+    Matrix transpose() const {
+        Matrix r = zero();
+        for (int row = 0; row < N; row++)
+            for (int col = 0; col < N; col++) r.v[col][row] = v[row][col];
+        return r;
+    }
+    // matrix.rs:41-52: 2x2 closed form; otherwise result = 0.; result += values[0][c] * cofactor(0, c)
+    double determinant() const {
+        double result = 0.;
+        if constexpr (N == 2) {
+            result = v[0][0] * v[1][1] - v[0][1] * v[1][0];
+        } else {
+            for (int column = 0; column < N; column++) result += v[0][column] * cofactor(0, column);
+        }
+        return result;
+    }
+    // matrix.rs:55-112 (submatrix3 / submatrix2)
+    Matrix<(N > 2 ? N - 1 : 2)> submatrix(int row, int col) const {
+        Matrix<(N > 2 ? N - 1 : 2)> r = Matrix<(N > 2 ? N - 1 : 2)>::zero();
+        int rx = 0;
+        for (int x = 0; x < N; x++) {
+            if (x == row) continue;
+            int ry = 0;
+            for (int y = 0; y < N; y++) {
+                if (y == col) continue;
+                r.v[rx][ry] = v[x][y];
+                ry++;
+            }
+            rx++;
+        }
+        return r;
+    }
+    // matrix.rs:114-125
+    double minor(int row, int col) const {
+        static_assert(N == 3 || N == 4 || N == 2, "unsupported");
+        if constexpr (N == 2) {
+            throw Panic("Unsupported SIZE=2 used in Matrix::minor, supported values are: 3, 4.");
+        } else {
+            return submatrix(row, col).determinant();
+        }
+    }
+    // matrix.rs:128-135
+    double cofactor(int row, int col) const {
+        double result = minor(row, col);
+        return ((row + col) % 2 == 0) ? result : -result;
+    }
+    // matrix.rs:138-157: refuses |det| < EPSILON; each element = cofactor / determinant (a true division)
+    std::optional<Matrix> inverse() const {
+        if (is_almost_equal(determinant(), 0.)) return std::nullopt;
+        Matrix result = zero();
+        for (int row = 0; row < N; row++)
+            for (int col = 0; col < N; col++) {
+                double c = cofactor(row, col);
+                result.v[col][row] = c / determinant();
+            }
+        return result;
+    }
+    // matrix.rs:174-185 (approximate)
+    bool operator==(const Matrix& o) const {
+        for (int y = 0; y < N; y++)
+            for (int x = 0; x < N; x++)
+                if (!is_almost_equal(v[x][y], o.v[x][y])) return false;
+        return true;
+    }
+};
+using Matrix4 = Matrix<4>;
+
+// matrix.rs:187-205:  val = 0.; val += self[row][n] * rhs[n][col]
+template <int N>
+inline Matrix<N> operator*(const Matrix<N>& a, const Matrix<N>& b) {
+    Matrix<N> r = Matrix<N>::zero();
+    for (int row = 0; row < N; row++)
+        for (int col = 0; col < N; col++) {
+            double val = 0.;
+            for (int n = 0; n < N; n++) val += a.v[row][n] * b.v[n][col];
+            r.v[row][col] = val;
+        }
+    return r;
+}
+// matrix.rs:207-227: four-term left-to-right sums, w row included
+inline Tuple operator*(const Matrix4& m, const Tuple& t) {
+    Tuple r;
+    r.x = m.v[0][0] * t.x + m.v[0][1] * t.y + m.v[0][2] * t.z + m.v[0][3] * t.w;
+    r.y = m.v[1][0] * t.x + m.v[1][1] * t.y + m.v[1][2] * t.z + m.v[1][3] * t.w;
+    r.z = m.v[2][0] * t.x + m.v[2][1] * t.y + m.v[2][2] * t.z + m.v[2][3] * t.w;
+    r.w = m.v[3][0] * t.x + m.v[3][1] * t.y + m.v[3][2] * t.z + m.v[3][3] * t.w;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------- transformations.rs:4-93
+inline Matrix4 translation(double x, double y, double z) {
+    Matrix4 r = Matrix4::identity();
+    r.v[0][3] = x; r.v[1][3] = y; r.v[2][3] = z;
+    return r;
+}
+inline Matrix4 scaling(double x, double y, double z) {
+    Matrix4 r = Matrix4::identity();
+    r.v[0][0] = x; r.v[1][1] = y; r.v[2][2] = z;
+    return r;
+}
+inline Matrix4 rotation_x(double rad) {
+    Matrix4 r = Matrix4::identity();
+    double c = std::cos(rad); r.v[1][1] = c; r.v[2][2] = c;
+    double s = std::sin(rad); r.v[1][2] = -s; r.v[2][1] = s;
+    return r;
+}
+inline Matrix4 rotation_y(double rad) {
+    Matrix4 r = Matrix4::identity();
+    double c = std::cos(rad); r.v[0][0] = c; r.v[2][2] = c;
+    double s = std::sin(rad); r.v[0][2] = s; r.v[2][0] = -s;
+    return r;
+}
+inline Matrix4 rotation_z(double rad) {
+    Matrix4 r = Matrix4::identity();
+    double c = std::cos(rad); r.v[0][0] = c; r.v[1][1] = c;
+    double s = std::sin(rad); r.v[0][1] = -s; r.v[1][0] = s;
+    return r;
+}
+inline Matrix4 shearing(double xy, double xz, double yx, double yz, double zx, double zy) {
+    Matrix4 r = Matrix4::identity();
+    r.v[0][1] = xy; r.v[0][2] = xz; r.v[1][0] = yx; r.v[1][2] = yz; r.v[2][0] = zx; r.v[2][1] = zy;
+    return r;
+}
+// transformations.rs:80-93
+inline Matrix4 view_transform(const Tuple& from, const Tuple& to, const Tuple& up) {
+    Tuple forward = (to - from).normalize();
+    Tuple upn = up.normalize();
+    Tuple left = forward.cross(upn);
+    Tuple true_up = left.cross(forward);
+    Matrix4 o = Matrix4::zero();
+    o.v[0][0] = left.x; o.v[0][1] = left.y; o.v[0][2] = left.z;
+    o.v[1][0] = true_up.x; o.v[1][1] = true_up.y; o.v[1][2] = true_up.z;
+    o.v[2][0] = -forward.x; o.v[2][1] = -forward.y; o.v[2][2] = -forward.z;
+    o.v[3][3] = 1.;
+    return o * translation(-from.x, -from.y, -from.z);
+}
+
+// ---------------------------------------------------------------------------------------------- ray.rs:5-25
+struct Ray {
+    Tuple origin, direction;
+    Tuple position(double t) const { return origin + direction * t; }
+    Ray transform(const Matrix4& m) const { return {m * origin, m * direction}; }
+};
+
+// ---------------------------------------------------------------------------------------------- light.rs:5-16
+struct Light {
+    Tuple position;
+    Color intensity;
+};
+
+// ---------------------------------------------------------------------------------------------- pattern.rs:3-103
+struct Shape;
+enum class PatternKind { Stripe, Gradient, Ring, Checkers, Test };
+struct Pattern {
+    Matrix4 transform = Matrix4::identity();
+    Matrix4 transform_inverse = Matrix4::identity();
+    PatternKind kind = PatternKind::Test;
+    Color a{0, 0, 0}, b{0, 0, 0};
+    static Pattern make(PatternKind k, Color a, Color b) {
+        Pattern p; p.kind = k; p.a = a; p.b = b;
+        return p;
+    }
+    // pattern.rs:63-66
+    void set_transform(const Matrix4& t) {
+        transform = t;
+        auto inv = t.inverse();
+        ORC_ASSERT(inv.has_value(), "should be invertible");
+        transform_inverse = *inv;
+    }
+    // pattern.rs:68-95  (`%` on f64 is fmod; powf(2.0) is x*x)
+    Color color_at(const Tuple& p) const {
+        switch (kind) {
+            case PatternKind::Stripe: return (std::fmod(std::floor(p.x), 2.0) == 0.0) ? a : b;
+            case PatternKind::Gradient: return a + (b - a) * (p.x - std::floor(p.x));
+            case PatternKind::Ring:
+                return (std::fmod(std::floor(std::sqrt(p.x * p.x + p.z * p.z)), 2.0) == 0.0) ? a : b;
+            case PatternKind::Checkers:
+                return (std::fmod(std::floor(p.x) + std::floor(p.y) + std::floor(p.z), 2.0) == 0.0) ? a : b;
+            case PatternKind::Test: return {p.x, p.y, p.z};
+        }
+        return BLACK;
+    }
+    Color color_at_shape(const Shape& object, const Tuple& world_point) const;  // pattern.rs:98-103
+    // derive(PartialEq): transform, transform_inverse (approximate Matrix eq), kind (+ approximate colours)
+    bool operator==(const Pattern& o) const {
+        if (!(transform == o.transform) || !(transform_inverse == o.transform_inverse) || kind != o.kind) return false;
+        if (kind == PatternKind::Test) return true;
+        return a == o.a && b == o.b;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- material.rs:4-75
+struct Material {
+    Color color = WHITE;
+    double ambient = 0.1, diffuse = 0.9, specular = 0.9, shininess = 200.0, reflective = 0.0;
+    std::optional<Pattern> pattern;
+    double transparency = 0.0, refractive_index = 1.0;
+    // derive(PartialEq): approximate colour, exact f64 fields, Option<Pattern>
+    bool operator==(const Material& o) const {
+        if (!(color == o.color)) return false;
+        if (!(ambient == o.ambient && diffuse == o.diffuse && specular == o.specular && shininess == o.shininess &&
+              reflective == o.reflective))
+            return false;
+        if (pattern.has_value() != o.pattern.has_value()) return false;
+        if (pattern.has_value() && !(*pattern == *o.pattern)) return false;
+        return transparency == o.transparency && refractive_index == o.refractive_index;
+    }
+    Color lighting(const Light& light, const Shape& object, const Tuple& point, const Tuple& eyev,
+                   const Tuple& normalv, bool in_shadow) const;
+};
+
+// ---------------------------------------------------------------------------------------------- shape.rs / bounds.rs
+enum class Kind { Sphere, Plane, Cube, Cylinder, Cone, Group, Triangle };
+
+struct Bounds {
+    Tuple min, max;
+    void add(const Tuple& p) {  // bounds.rs:142-151
+        ORC_ASSERT(p.is_point(), "assertion failed: point.is_point()");
+        min.x = fmin_(min.x, p.x); min.y = fmin_(min.y, p.y); min.z = fmin_(min.z, p.z);
+        max.x = fmax_(max.x, p.x); max.y = fmax_(max.y, p.y); max.z = fmax_(max.z, p.z);
+    }
+};
+
+struct Intersection {
+    double t;
+    const Shape* object;
+};
+using Intersections = std::vector<Intersection>;
+
+// Execution mode + counters (not part of the reference; they do not touch any arithmetic).
+struct Counters {
+    uint64_t primary = 0, shadow = 0, reflect = 0, refract = 0, leaf_tests = 0;
+};
+struct Ctx {
+    bool cached = false;
+    Counters* counters = nullptr;
+};
+inline Ctx& ctx() {
+    static thread_local Ctx c;
+    return c;
+}
+
+struct Shape {
+    Kind kind = Kind::Sphere;
+    double minimum = 0., maximum = 0.;
+    bool capped = false;
+    std::vector<Shape> shapes;          // Group
+    Tuple p1{}, p2{}, p3{}, e1{}, e2{}, normal{};  // Triangle
+    Matrix4 transform = Matrix4::identity();
+    Matrix4 transform_inverse = Matrix4::identity();            // shape.rs:45
+    Matrix4 transform_inverse_transpose = Matrix4::identity();  // shape.rs:46
+    bool transformed = false;
+    Material material;
+    // cached-mode values (pure functions of the scene; see file header)
+    Matrix4 cached_fresh_inverse = Matrix4::identity();
+    Bounds cached_bounds{};
+    bool cache_valid = false;
+
+    // shape.rs:52-193
+    static Shape sphere() { Shape s; s.kind = Kind::Sphere; return s; }
+    static Shape glass_sphere() {
+        Shape s = sphere();
+        s.material.transparency = 1.0;
+        s.material.refractive_index = 1.5;
+        return s;
+    }
+    static Shape plane() { Shape s; s.kind = Kind::Plane; return s; }
+    static Shape cube() { Shape s; s.kind = Kind::Cube; return s; }
+    static Shape cylinder(double mn, double mx, bool capped) {
+        Shape s; s.kind = Kind::Cylinder; s.minimum = mn; s.maximum = mx; s.capped = capped;
+        return s;
+    }
+    static Shape infinite_cylinder() {
+        return cylinder(-std::numeric_limits<double>::infinity(), std::numeric_limits<double>::infinity(), false);
+    }
+    static Shape cone(double mn, double mx, bool capped) {
+        Shape s; s.kind = Kind::Cone; s.minimum = mn; s.maximum = mx; s.capped = capped;
+        return s;
+    }
+    static Shape infinite_cone() {
+        return cone(-std::numeric_limits<double>::infinity(), std::numeric_limits<double>::infinity(), false);
+    }
+    static Shape group() { Shape s; s.kind = Kind::Group; return s; }
+    // shape.rs:171-193
+    static Shape triangle(const Tuple& p1, const Tuple& p2, const Tuple& p3) {
+        ORC_ASSERT(p1.is_point() && p2.is_point() && p3.is_point(),
+                   "assertion failed: p1.is_point() && p2.is_point() && p3.is_point()");
+        Shape s; s.kind = Kind::Triangle;
+        s.p1 = p1; s.p2 = p2; s.p3 = p3;
+        s.e1 = p2 - p1;
+        s.e2 = p3 - p1;
+        s.normal = s.e2.cross(s.e1).normalize();
+        return s;
+    }
+
+    // shape.rs:196-218
+    void set_transform(const Matrix4& t) {
+        if (transformed) throw Panic("Can't call set_transform more than once.");
+        transformed = true;
+        set_transform_internal(t);
+    }
+    void set_transform_internal(const Matrix4& t) {
+        if (kind == Kind::Group) {
+            for (auto& s : shapes) s.set_transform_internal(t);
+        } else {
+            transform = t * transform;
+            auto inv = transform.inverse();
+            ORC_ASSERT(inv.has_value(), "should be invertible");
+            transform_inverse = *inv;
+            transform_inverse_transpose = transform_inverse.transpose();
+        }
+        cache_valid = false;
+    }
+    // shape.rs:220-229
+    void set_material(const Material& m) {
+        if (kind == Kind::Group) {
+            for (auto& s : shapes) s.set_material(m);
+        } else {
+            material = m;
+        }
+    }
+    void push_shape(Shape s) {  // shape.rs:528-535
+        if (kind != Kind::Group) throw Panic("push_shape was called on something that isn't a group");
+        shapes.push_back(std::move(s));
+        cache_valid = false;
+    }
+
+    // Fill the cached-mode values for this subtree (bottom-up so group bounds see cached children).
+    void build_cache() {
+        for (auto& s : shapes) s.build_cache();
+        auto inv = transform.inverse();
+        ORC_ASSERT(inv.has_value(), "shape transform should be invertible");
+        cached_fresh_inverse = *inv;
+        cache_valid = false;
+        if (kind == Kind::Group) cached_bounds = bounds_of(*this);
+        cache_valid = true;
+    }
+
+    // bounds.rs:11-140
+    static Bounds bounds_of(const Shape& shape) {
+        const double inf = std::numeric_limits<double>::infinity();
+        Bounds b{};
+        switch (shape.kind) {
+            case Kind::Sphere:
+            case Kind::Cube: b.min = Tuple::point(-1., -1., -1.); b.max = Tuple::point(1., 1., 1.); break;
+            case Kind::Plane: b.min = Tuple::point(-1., -1., 0.); b.max = Tuple::point(1., 1., 0.); break;
+            case Kind::Cylinder:
+            case Kind::Cone:
+                if (shape.capped) {
+                    b.min = Tuple::point(-1., shape.minimum, -1.);
+                    b.max = Tuple::point(1., shape.maximum, 1.);
+                } else {
+                    b.min = Tuple::point(-1., -inf, -1.);
+                    b.max = Tuple::point(1., inf, 1.);
+                }
+                break;
+            case Kind::Group: {
+                if (ctx().cached && shape.cache_valid) return shape.cached_bounds;
+                Bounds out{Tuple::point(0., 0., 0.), Tuple::point(0., 0., 0.)};
+                for (const auto& child : shape.shapes) {
+                    Bounds pb = bounds_of(child);
+                    const Matrix4& tr = child.transform;
+                    Tuple c1 = tr * Tuple::point(pb.min.x, pb.min.y, pb.min.z);
+                    Tuple c2 = tr * Tuple::point(pb.min.x, pb.min.y, pb.max.z);
+                    Tuple c3 = tr * Tuple::point(pb.min.x, pb.max.y, pb.min.z);
+                    Tuple c4 = tr * Tuple::point(pb.min.x, pb.max.y, pb.max.z);
+                    Tuple c5 = tr * Tuple::point(pb.max.x, pb.min.y, pb.min.z);
+                    Tuple c6 = tr * Tuple::point(pb.max.x, pb.min.y, pb.max.z);
+                    Tuple c7 = tr * Tuple::point(pb.max.x, pb.max.y, pb.min.z);
+                    Tuple c8 = tr * pb.max;
+                    out.add(c1); out.add(c2); out.add(c3); out.add(c4);
+                    out.add(c5); out.add(c6); out.add(c7); out.add(c8);
+                }
+                b = out;
+                break;
+            }
+            case Kind::Triangle: {
+                Bounds tmp{Tuple::point(0., 0., 0.), Tuple::point(0., 0., 0.)};
+                tmp.add(shape.p1); tmp.add(shape.p2); tmp.add(shape.p3);
+                b = tmp;
+                break;
+            }
+        }
+        return b;
+    }
+
+    // shape.rs:587-606
+    static std::pair<double, double> check_axis(double mn, double mx, double origin, double direction) {
+        double tmin_numerator = mn - origin;
+        double tmax_numerator = mx - origin;
+        double tmin, tmax;
+        if (std::fabs(direction) >= EPSILON) {
+            tmin = tmin_numerator / direction;
+            tmax = tmax_numerator / direction;
+        } else {
+            tmin = tmin_numerator * std::numeric_limits<double>::infinity();
+            tmax = tmax_numerator * std::numeric_limits<double>::infinity();
+        }
+        if (tmin > tmax) std::swap(tmin, tmax);
+        return {tmin, tmax};
+    }
+    // shape.rs:579-585
+    static bool check_cap(const Ray& ray, double t) {
+        double x = ray.origin.x + t * ray.direction.x;
+        double y = ray.origin.y + t * ray.direction.y;
+        double z = ray.origin.z + t * ray.direction.z;
+        return x * x + z * z <= std::fabs(y);
+    }
+    // shape.rs:537-573
+    void intersect_caps(Intersections& out, const Ray& local_ray) const {
+        if (!capped) return;
+        if (is_almost_equal(local_ray.direction.y, 0.0)) return;
+        double t = (minimum - local_ray.origin.y) / local_ray.direction.y;
+        if (check_cap(local_ray, t)) out.push_back({t, this});
+        t = (maximum - local_ray.origin.y) / local_ray.direction.y;
+        if (check_cap(local_ray, t)) out.push_back({t, this});
+    }
+
+    // shape.rs:248-463
+    Intersections intersect(const Ray& world_ray) const {
+        Matrix4 inv;
+        if (ctx().cached && cache_valid) {
+            inv = cached_fresh_inverse;
+        } else {
+            auto o = transform.inverse();
+            ORC_ASSERT(o.has_value(), "shape transform should be invertible");
+            inv = *o;
+        }
+        Ray local_ray = world_ray.transform(inv);
+        Intersections result;
+        if (kind != Kind::Group && ctx().counters) ctx().counters->leaf_tests++;
+        switch (kind) {
+            case Kind::Sphere: {  // shape.rs:258-273
+                Tuple sphere_to_ray = local_ray.origin - Tuple::point(0., 0., 0.);
+                double a = local_ray.direction.dot(local_ray.direction);
+                double b = 2. * local_ray.direction.dot(sphere_to_ray);
+                double c = sphere_to_ray.dot(sphere_to_ray) - 1.;
+                double discriminant = b * b - 4. * a * c;
+                if (discriminant >= 0.) {
+                    double sq = std::sqrt(discriminant);
+                    result.push_back({(-b - sq) / (2. * a), this});
+                    result.push_back({(-b + sq) / (2. * a), this});
+                }
+                break;
+            }
+            case Kind::Plane: {  // shape.rs:274-282
+                if (std::fabs(local_ray.direction.y) >= EPSILON)
+                    result.push_back({-local_ray.origin.y / local_ray.direction.y, this});
+                break;
+            }
+            case Kind::Cube: {  // shape.rs:283-319
+                auto [xtmin, xtmax] = check_axis(-1.0, 1.0, local_ray.origin.x, local_ray.direction.x);
+                auto [ytmin, ytmax] = check_axis(-1.0, 1.0, local_ray.origin.y, local_ray.direction.y);
+                auto [ztmin, ztmax] = check_axis(-1.0, 1.0, local_ray.origin.z, local_ray.direction.z);
+                double tmin = fmax_(fmax_(xtmin, ytmin), ztmin);
+                double tmax = fmin_(fmin_(xtmax, ytmax), ztmax);
+                if (tmax >= tmin) {
+                    result.push_back({tmin, this});
+                    result.push_back({tmax, this});
+                }
+                break;
+            }
+            case Kind::Cylinder: {  // shape.rs:320-355
+                const Tuple& o = local_ray.origin;
+                const Tuple& d = local_ray.direction;
+                double a = d.x * d.x + d.z * d.z;
+                if (!is_almost_equal(a, 0.0)) {
+                    double b = 2.0 * o.x * d.x + 2.0 * o.z * d.z;
+                    double c = o.x * o.x + o.z * o.z - 1.0;
+                    double discriminant = b * b - 4.0 * a * c;
+                    if (discriminant >= 0.0) {
+                        double sq = std::sqrt(discriminant);
+                        double t0 = (-b - sq) / (2. * a);
+                        double t1 = (-b + sq) / (2. * a);
+                        if (t0 > t1) std::swap(t0, t1);
+                        double y0 = o.y + t0 * d.y;
+                        if (minimum < y0 && y0 < maximum) result.push_back({t0, this});
+                        double y1 = o.y + t1 * d.y;
+                        if (minimum < y1 && y1 < maximum) result.push_back({t1, this});
+                    }
+                }
+                intersect_caps(result, local_ray);
+                break;
+            }
+            case Kind::Cone: {  // shape.rs:356-398
+                const Tuple& o = local_ray.origin;
+                const Tuple& d = local_ray.direction;
+                double a = d.x * d.x - d.y * d.y + d.z * d.z;
+                double b = 2.0 * o.x * d.x - 2.0 * o.y * d.y + 2.0 * o.z * d.z;
+                double c = o.x * o.x - o.y * o.y + o.z * o.z;
+                if (is_almost_equal(a, 0.0)) {
+                    if (!is_almost_equal(b, 0.0)) {
+                        double t = -c / (2.0 * b);
+                        result.push_back({t, this});
+                    }
+                } else {
+                    double discriminant = b * b - 4.0 * a * c;
+                    if (discriminant >= 0.0) {
+                        double sq = std::sqrt(discriminant);
+                        double t0 = (-b - sq) / (2. * a);
+                        double t1 = (-b + sq) / (2. * a);
+                        if (t0 > t1) std::swap(t0, t1);
+                        double y0 = o.y + t0 * d.y;
+                        if (minimum < y0 && y0 < maximum) result.push_back({t0, this});
+                        double y1 = o.y + t1 * d.y;
+                        if (minimum < y1 && y1 < maximum) result.push_back({t1, this});
+                    }
+                }
+                intersect_caps(result, local_ray);
+                break;
+            }
+            case Kind::Group: {  // shape.rs:399-436
+                Bounds bounds = bounds_of(*this);
+                auto [xtmin, xtmax] = check_axis(bounds.min.x, bounds.max.x, local_ray.origin.x, local_ray.direction.x);
+                auto [ytmin, ytmax] = check_axis(bounds.min.y, bounds.max.y, local_ray.origin.y, local_ray.direction.y);
+                auto [ztmin, ztmax] = check_axis(bounds.min.z, bounds.max.z, local_ray.origin.z, local_ray.direction.z);
+                double tmin = fmax_(fmax_(xtmin, ytmin), ztmin);
+                double tmax = fmin_(fmin_(xtmax, ytmax), ztmax);
+                if (tmax > tmin) {
+                    Intersections shape_results;
+                    for (const auto& child : shapes) {
+                        Intersections xs = child.intersect(world_ray);  // world_ray: transforms were pushed down
+                        shape_results.insert(shape_results.end(), xs.begin(), xs.end());
+                    }
+                    sort_by_t(shape_results);
+                    result.insert(result.end(), shape_results.begin(), shape_results.end());
+                }
+                break;
+            }
+            case Kind::Triangle: {  // shape.rs:438-459 (Moller-Trumbore)
+                Tuple dir_cross_e2 = local_ray.direction.cross(e2);
+                double det = e1.dot(dir_cross_e2);
+                if (!(std::fabs(det) < EPSILON)) {
+                    double f = 1.0 / det;
+                    Tuple p1_to_origin = local_ray.origin - p1;
+                    double u = f * p1_to_origin.dot(dir_cross_e2);
+                    if (!(u < 0.0 || u > 1.0)) {
+                        Tuple origin_cross_e1 = p1_to_origin.cross(e1);
+                        double v = f * local_ray.direction.dot(origin_cross_e1);
+                        if (!(v < 0.0 || (u + v) > 1.0)) {
+                            double t = f * e2.dot(origin_cross_e1);
+                            result.push_back({t, this});
+                        }
+                    }
+                }
+                break;
+            }
+        }
+        return result;
+    }
+
+    // slice::sort_by(|a,b| a.t.partial_cmp(&b.t).unwrap_or(Equal)) — a stable sort; NaN compares Equal.
+    static void sort_by_t(Intersections& xs) {
+        std::stable_sort(xs.begin(), xs.end(), [](const Intersection& a, const Intersection& b) { return a.t < b.t; });
+    }
+
+    // shape.rs:466-519 (+ world_to_object :608-621, normal_to_world :623-635)
+    Tuple normal_at(const Tuple& world_point) const {
+        Tuple lp = transform_inverse * world_point;
+        Tuple ln;
+        switch (kind) {
+            case Kind::Sphere: ln = lp - Tuple::point(0.0, 0.0, 0.0); break;
+            case Kind::Plane: ln = Tuple::vector(0.0, 1.0, 0.0); break;
+            case Kind::Cube: {
+                double xa = std::fabs(lp.x), ya = std::fabs(lp.y), za = std::fabs(lp.z);
+                double maxc = fmax_(fmax_(xa, ya), za);
+                if (maxc == xa) ln = Tuple::vector(lp.x, 0.0, 0.0);
+                else if (maxc == ya) ln = Tuple::vector(0.0, lp.y, 0.0);
+                else ln = Tuple::vector(0.0, 0.0, lp.z);
+                break;
+            }
+            case Kind::Cylinder: {
+                double dist = lp.x * lp.x + lp.z * lp.z;
+                if (dist < 1.0 && lp.y >= maximum - EPSILON) ln = Tuple::vector(0.0, 1.0, 0.0);
+                else if (dist < 1.0 && lp.y <= minimum + EPSILON) ln = Tuple::vector(0.0, -1.0, 0.0);
+                else ln = Tuple::vector(lp.x, 0.0, lp.z);
+                break;
+            }
+            case Kind::Cone: {
+                double y = std::sqrt(lp.x * lp.x + lp.z * lp.z);
+                if (lp.y > 0.0) y = -y;
+                ln = Tuple::vector(lp.x, y, lp.z);
+                break;
+            }
+            case Kind::Group: throw Panic("internal error: entered unreachable code");
+            case Kind::Triangle: ln = normal; break;
+        }
+        ORC_ASSERT(ln.is_vector(), "assertion failed: local_normal.is_vector()");
+        Tuple wn = transform_inverse_transpose * ln;  // normal_to_world
+        wn.w = 0.0;
+        wn = wn.normalize();
+        wn.w = 0.;
+        return wn.normalize();
+    }
+
+    // shape.rs:638-646 — VALUE equality (approximate transform, derived kind + material equality)
+    bool operator==(const Shape& o) const {
+        if (kind != o.kind) return false;
+        switch (kind) {
+            case Kind::Cylinder:
+            case Kind::Cone:
+                if (!(minimum == o.minimum && maximum == o.maximum && capped == o.capped)) return false;
+                break;
+            case Kind::Group:
+                if (shapes.size() != o.shapes.size()) return false;
+                for (size_t i = 0; i < shapes.size(); i++)
+                    if (!(shapes[i] == o.shapes[i])) return false;
+                break;
+            case Kind::Triangle:
+                if (!(p1 == o.p1 && p2 == o.p2 && p3 == o.p3 && e1 == o.e1 && e2 == o.e2 && normal == o.normal))
+                    return false;
+                break;
+            default: break;
+        }
+        return transform == o.transform && material == o.material;
+    }
+};
+
+// pattern.rs:98-103
+inline Color Pattern::color_at_shape(const Shape& object, const Tuple& world_point) const {
+    Tuple object_point = object.transform_inverse * world_point;
+    Tuple pattern_point = transform_inverse * object_point;
+    return color_at(pattern_point);
+}
+
+// material.rs:32-75
+inline Color Material::lighting(const Light& light, const Shape& object, const Tuple& point, const Tuple& eyev,
+                                const Tuple& normalv, bool in_shadow) const {
+    Color c = pattern.has_value() ? pattern->color_at_shape(object, point) : color;
+    Color effective_color = c * light.intensity;
+    Tuple lightv = (light.position - point).normalize();
+    Color ambient_c = effective_color * ambient;
+    Color diffuse_c = BLACK, specular_c = BLACK;
+    if (!in_shadow) {
+        double light_dot_normal = lightv.dot(normalv);
+        if (light_dot_normal >= 0.) {
+            diffuse_c = effective_color * diffuse * light_dot_normal;
+            Tuple reflectv = (-lightv).reflect(normalv);
+            double reflect_dot_eye = reflectv.dot(eyev);
+            if (reflect_dot_eye > 0.) {
+                double factor = std::pow(reflect_dot_eye, shininess);
+                specular_c = light.intensity * specular * factor;
+            }
+        }
+    }
+    return ambient_c + diffuse_c + specular_c;
+}
+
+// ---------------------------------------------------------------------------------------------- intersection.rs:17-128
+struct Computations {
+    double t;
+    const Shape* object;
+    Tuple point, over_point, under_point, eyev;
+    bool inside;
+    Tuple normalv, reflectv;
+    double n1, n2;
+    // intersection.rs:107-128  (powi(2) = x*x, powi(5) = x*((x*x)*(x*x)))
+    double schlick() const {
+        double cos = eyev.dot(normalv);
+        if (n1 > n2) {
+            double n = n1 / n2;
+            double sin2_t = (n * n) * (1.0 - cos * cos);
+            if (sin2_t > 1.0) return 1.0;
+            double cos_t = std::sqrt(1.0 - sin2_t);
+            cos = cos_t;
+        }
+        double q = (n1 - n2) / (n1 + n2);
+        double r0 = q * q;
+        double m = 1.0 - cos;
+        double m2 = m * m;
+        return r0 + (1.0 - r0) * (m * (m2 * m2));
+    }
+};
+
+// derive(PartialEq) on Intersection: exact t, VALUE equality of the shapes (intersection.rs:6-10)
+inline bool intersection_eq(const Intersection& a, const Intersection& b) {
+    return a.t == b.t && (a.object == b.object || *a.object == *b.object);
+}
+
+// intersection.rs:79-83: first of the minimal t >= 0 in slice order
+inline const Intersection* hit(const Intersections& xs) {
+    const Intersection* best = nullptr;
+    for (const auto& x : xs) {
+        if (!(x.t >= 0.)) continue;
+        if (!best || x.t < best->t) best = &x;
+    }
+    return best;
+}
+
+// intersection.rs:17-77
+inline Computations prepare_computations(const Intersection& self, const Ray& ray, const Intersections& xs) {
+    Tuple point = ray.position(self.t);
+    Tuple eyev = -ray.direction;
+    Tuple normalv = self.object->normal_at(point);
+    bool inside = normalv.dot(eyev) < 0.0;
+    if (inside) normalv = -normalv;
+    Tuple reflectv = ray.direction.reflect(normalv);
+
+    std::vector<const Shape*> containers;
+    double n1 = 1.0, n2 = 1.0;
+    for (const auto& i : xs) {
+        bool is_self = intersection_eq(i, self);
+        if (is_self) {
+            if (!containers.empty()) n1 = containers.back()->material.refractive_index;
+        }
+        size_t pos = containers.size();
+        for (size_t k = 0; k < containers.size(); k++)
+            if (containers[k] == i.object || *containers[k] == *i.object) { pos = k; break; }
+        if (pos < containers.size()) containers.erase(containers.begin() + pos);
+        else containers.push_back(i.object);
+        if (is_self) {
+            if (!containers.empty()) n2 = containers.back()->material.refractive_index;
+            break;
+        }
+    }
+    Computations c;
+    c.t = self.t; c.object = self.object; c.point = point;
+    c.over_point = point + normalv * EPSILON;
+    c.under_point = point - normalv * EPSILON;
+    c.eyev = eyev; c.inside = inside; c.normalv = normalv; c.reflectv = reflectv; c.n1 = n1; c.n2 = n2;
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------- world.rs:11-163
+constexpr size_t RECURSION_LIMIT = 5;
+
+struct World {
+    std::vector<Shape> objects;
+    Light light{Tuple::point(0, 0, 0), WHITE};
+
+    static World default_world() {  // world.rs:26-41
+        World w;
+        w.light = Light{Tuple::point(-10.0, 10.0, -10.0), WHITE};
+        Shape s1 = Shape::sphere();
+        s1.material.color = Color{0.8, 1.0, 0.6};
+        s1.material.diffuse = 0.7;
+        s1.material.specular = 0.2;
+        Shape s2 = Shape::sphere();
+        s2.set_transform(scaling(0.5, 0.5, 0.5));
+        w.objects.push_back(s1);
+        w.objects.push_back(s2);
+        return w;
+    }
+    void build_cache() { for (auto& o : objects) o.build_cache(); }
+
+    // world.rs:43-54
+    Intersections intersect(const Ray& ray) const {
+        Intersections result;
+        for (const auto& object : objects) {
+            Intersections xs = object.intersect(ray);
+            result.insert(result.end(), xs.begin(), xs.end());
+        }
+        Shape::sort_by_t(result);
+        return result;
+    }
+    // world.rs:56-78   (remaining is usize: `remaining - 1` on 0 panics in debug, wraps in release)
+    Color shade_hit(const Computations& comps, size_t remaining) const {
+        const Shape* object = comps.object;
+        const Material& material = object->material;
+        if (ctx().counters) ctx().counters->shadow++;
+        Color surface = material.lighting(light, *object, comps.point, comps.eyev, comps.normalv,
+                                          is_shadowed(comps.over_point));
+        Color reflected = reflected_color(comps, remaining - 1);
+        Color refracted = refracted_color(comps, remaining - 1);
+        if (material.reflective > 0.0 && material.transparency > 0.0) {
+            double reflectance = comps.schlick();
+            return surface + reflected * reflectance + refracted * (1.0 - reflectance);
+        }
+        return surface + reflected + refracted;
+    }
+    Color color_at(const Ray& ray) const { return internal_color_at(ray, RECURSION_LIMIT); }  // world.rs:80-82
+    // world.rs:84-98
+    Color internal_color_at(const Ray& ray, size_t remaining) const {
+        if (remaining < 1) return BLACK;
+        Intersections xs = intersect(ray);
+        const Intersection* h = hit(xs);
+        if (!h) return BLACK;
+        return shade_hit(prepare_computations(*h, ray, xs), remaining - 1);
+    }
+    // world.rs:100-114
+    bool is_shadowed(const Tuple& point) const {
+        Tuple vector = light.position - point;
+        double distance = vector.magnitude();
+        Tuple direction = vector.normalize();
+        Ray ray{point, direction};
+        Intersections xs = intersect(ray);
+        const Intersection* h = hit(xs);
+        return h ? (h->t < distance) : false;
+    }
+    // world.rs:116-129
+    Color reflected_color(const Computations& comps, size_t remaining) const {
+        if (remaining < 1) return BLACK;
+        const Shape* object = comps.object;
+        if (object->material.reflective == 0.0) return BLACK;
+        if (ctx().counters) ctx().counters->reflect++;
+        Ray reflect_ray{comps.over_point, comps.reflectv};
+        Color color = internal_color_at(reflect_ray, remaining - 1);
+        return color * object->material.reflective;
+    }
+    // world.rs:131-163  (powf(2.0) = x*x)
+    Color refracted_color(const Computations& comps, size_t remaining) const {
+        if (remaining == 0) return BLACK;
+        const Shape* object = comps.object;
+        if (object->material.transparency == 0.0) return BLACK;
+        double n_ratio = comps.n1 / comps.n2;
+        double cos_i = comps.eyev.dot(comps.normalv);
+        double sin2_t = (n_ratio * n_ratio) * (1.0 - cos_i * cos_i);
+        if (sin2_t > 1.0) return BLACK;
+        double cos_t = std::sqrt(1.0 - sin2_t);
+        Tuple direction = comps.normalv * (n_ratio * cos_i - cos_t) - comps.eyev * n_ratio;
+        if (ctx().counters) ctx().counters->refract++;
+        Ray refract_ray{comps.under_point, direction};
+        Color color = internal_color_at(refract_ray, remaining - 1) * object->material.transparency;
+        return color;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- canvas.rs:5-63
+struct Canvas {
+    size_t width = 0, height = 0;
+    std::vector<Color> pixels;
+    Canvas() = default;
+    Canvas(size_t w, size_t h) : width(w), height(h), pixels(w * h, BLACK) {}
+    Color get_pixel(size_t x, size_t y) const { return pixels.at(x + y * width); }
+    void set_pixel(size_t x, size_t y, Color c) { pixels.at(x + y * width) = c; }
+    // canvas.rs:61-63:  ((color.clamp(0., 1.) * 255.).round() as i32)
+    static int quantise(double c) {
+        double k = c;  // f64::clamp keeps NaN
+        if (k < 0.) k = 0.;
+        else if (k > 1.) k = 1.;
+        double r = std::round(k * 255.);  // half away from zero
+        if (std::isnan(r)) return 0;      // `as i32` saturates; NaN -> 0
+        return (int)r;
+    }
+    // canvas.rs:28-58
+    std::string to_ppm() const {
+        std::string out;
+        out.reserve(width * height * 12 + 32);
+        out += "P3\n";
+        out += std::to_string(width) + " " + std::to_string(height) + "\n";
+        out += "255\n";
+        for (size_t y = 0; y < height; y++) {
+            size_t len = 0;
+            for (size_t x = 0; x < width; x++) {
+                Color c = get_pixel(x, y);
+                const double ch[3] = {c.red, c.green, c.blue};
+                for (double v : ch) {
+                    std::string s = std::to_string(quantise(v));
+                    if (len + s.size() + 1 > 70) { out += "\n"; len = 0; }
+                    if (len > 0) { out += " "; len += 1; }
+                    out += s;
+                    len += s.size();
+                }
+            }
+            out += "\n";
+        }
+        return out;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- camera.rs:5-79
+struct Camera {
+    size_t hsize, vsize;
+    double field_of_view;
+    Matrix4 transform = Matrix4::identity();
+    Matrix4 transform_inverse = Matrix4::identity();
+    double pixel_size = 0., half_width = 0., half_height = 0.;
+    Camera(size_t h, size_t v, double fov) : hsize(h), vsize(v), field_of_view(fov) {  // camera.rs:16-41
+        double half_view = std::tan(field_of_view / 2.0);
+        double aspect = (double)hsize / (double)vsize;
+        if (aspect >= 1.0) {
+            half_width = half_view;
+            half_height = half_view / aspect;
+        } else {
+            half_width = half_view * aspect;
+            half_height = half_view;
+        }
+        pixel_size = (half_width * 2.0) / (double)hsize;
+    }
+    void set_transform(const Matrix4& t) {  // camera.rs:43-46
+        transform = t;
+        auto inv = t.inverse();
+        ORC_ASSERT(inv.has_value(), "should be invertible");
+        transform_inverse = *inv;
+    }
+    Ray ray_for_pixel(size_t px, size_t py) const {  // camera.rs:48-65
+        double xoffset = ((double)px + 0.5) * pixel_size;
+        double yoffset = ((double)py + 0.5) * pixel_size;
+        double world_x = half_width - xoffset;
+        double world_y = half_height - yoffset;
+        Tuple pixel = transform_inverse * Tuple::point(world_x, world_y, -1.0);
+        Tuple origin = transform_inverse * Tuple::point(0.0, 0.0, 0.0);
+        Tuple direction = (pixel - origin).normalize();
+        return {origin, direction};
+    }
+    // camera.rs:67-79 — the serial pixel loop (faithful, 1 thread)
+    Canvas render(const World& world) const {
+        Canvas image(hsize, vsize);
+        for (size_t y = 0; y < vsize; y++)
+            for (size_t x = 0; x < hsize; x++) {
+                Ray ray = ray_for_pixel(x, y);
+                if (ctx().counters) ctx().counters->primary++;
+                image.set_pixel(x, y, world.color_at(ray));
+            }
+        return image;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- obj_file.rs:5-128
+struct Parser {
+    std::vector<Tuple> vertices;
+    size_t ignored_lines = 0;
+    Shape default_group = Shape::group();
+    // The reference keeps named groups in a std HashMap (iteration order is randomised per process); this oracle
+    // keeps first-insertion order.  Re-declaring a name replaces the group (HashMap::insert), dropping its triangles.
+    std::vector<std::pair<std::string, Shape>> named_groups;
+
+    static Parser from_obj_file(const std::string& filename) {
+        std::ifstream f(filename, std::ios::binary);
+        if (!f) throw Panic("something went wrong reading " + filename + ".");
+        std::stringstream ss;
+        ss << f.rdbuf();
+        return from_obj_str(ss.str());
+    }
+    static double parse_f64(const std::string& tok, const char* what, const std::string& line) {
+        char* end = nullptr;
+        double v = std::strtod(tok.c_str(), &end);
+        if (tok.empty() || end != tok.c_str() + tok.size())
+            throw Panic(std::string("vertex ") + what + " should be an f64 in \"" + line + "\"");
+        return v;
+    }
+    static size_t parse_usize(const std::string& tok, const char* what, const std::string& line) {
+        size_t i = 0, v = 0;
+        if (i < tok.size() && tok[i] == '+') i++;
+        bool any = false;
+        for (; i < tok.size(); i++) {
+            if (tok[i] < '0' || tok[i] > '9') { any = false; break; }
+            v = v * 10 + (size_t)(tok[i] - '0');
+            any = true;
+        }
+        if (!any) throw Panic(std::string("face ") + what + " should be a usize in \"" + line + "\"");
+        return v;
+    }
+    Tuple vertex(size_t one_based) const {  // obj_file.rs:116-118
+        if (one_based == 0 || one_based - 1 >= vertices.size()) throw Panic("index out of bounds");
+        return vertices[one_based - 1];
+    }
+    Shape* find_group(const std::string& name) {
+        for (auto& g : named_groups)
+            if (g.first == name) return &g.second;
+        return nullptr;
+    }
+    // obj_file.rs:29-114
+    static Parser from_obj_str(const std::string& text) {
+        Parser result;
+        std::optional<std::string> current_group;
+        size_t pos = 0;
+        while (pos < text.size()) {
+            size_t nl = text.find('\n', pos);
+            std::string s = text.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos);
+            pos = (nl == std::string::npos) ? text.size() : nl + 1;
+            if (!s.empty() && s.back() == '\r') s.pop_back();
+            std::vector<std::string> tokens;
+            {
+                std::istringstream ls(s);
+                std::string tk;
+                while (ls >> tk) tokens.push_back(tk);
+            }
+            if (tokens.empty()) continue;
+            const std::string& token = tokens[0];
+            if (token == "v") {
+                if (tokens.size() < 4) throw Panic("vertex token to have a x/y/z in \"" + s + "\"");
+                double x = parse_f64(tokens[1], "x", s), y = parse_f64(tokens[2], "y", s), z = parse_f64(tokens[3], "z", s);
+                result.vertices.push_back(Tuple::point(x, y, z));
+            } else if (token == "f") {
+                if (tokens.size() < 3) throw Panic("face should have a v1/v2 in \"" + s + "\"");
+                size_t v1 = parse_usize(tokens[1], "v1", s);
+                size_t v2 = parse_usize(tokens[2], "v2", s);
+                for (size_t k = 3; k < tokens.size(); k++) {
+                    size_t v3 = parse_usize(tokens[k], "v3", s);
+                    Shape tri = Shape::triangle(result.vertex(v1), result.vertex(v2), result.vertex(v3));
+                    if (current_group) result.find_group(*current_group)->push_shape(std::move(tri));
+                    else result.default_group.push_shape(std::move(tri));
+                    v2 = v3;
+                }
+            } else if (token == "g") {
+                if (tokens.size() < 2) throw Panic("group should have a name in \"" + s + "\"");
+                if (Shape* g = result.find_group(tokens[1])) *g = Shape::group();
+                else result.named_groups.emplace_back(tokens[1], Shape::group());
+                current_group = tokens[1];
+            } else {
+                result.ignored_lines += 1;
+            }
+        }
+        return result;
+    }
+    // obj_file.rs:120-128
+    Shape obj_to_group() {
+        Shape g = Shape::group();
+        g.push_shape(std::move(default_group));
+        for (auto& ng : named_groups) g.push_shape(std::move(ng.second));
+        return g;
+    }
+};
+
+}  // namespace orc
