@@ -1,0 +1,252 @@
+/* include/rtc.h — C ABI of librtc_b200.so, the B200 (sm_100a) render path for the Ray-Tracer-Challenge renderer
+ * antoinehebert/ray-tracer-challenge-rust.
+ *
+ * The reference has no FFI or plugin layer; its seam for this path is the pure function
+ *     pub fn render(&self, world: &World) -> Canvas            (src/camera.rs:67-79)
+ * whose body is `for y {for x { world.color_at(&self.ray_for_pixel(x, y)) }}`.  This header is what a thin Rust
+ * `rtc-sys` crate would bind (INTEGRATION.md shows the `extern "C"` block and the patched Camera::render): plain
+ * pointers and sizes, no C++ or torch types.  All `file:line` citations are relative to /root/reference/.
+ *
+ * Two layers:
+ *   1. CORE BOUNDARY  (rtc_scene_*, rtc_render*, rtc_color_at) — replaces camera.rs:67-79 + world.rs:80-82.  The caller
+ *      hands over the World exactly as its own host code computed it (transforms with their cached inverses,
+ *      triangle edges and normals, materials with pattern inverses), so no value that reaches a pixel is recomputed
+ *      with a different rounding on this side of the boundary.
+ *   2. HOST MIRROR    (rtc_shape_*, rtc_world_*, rtc_camera_*, rtc_canvas_*, rtc_obj_*, rtc_mat_*) — the reference's own
+ *      host API (Shape/World/Camera/Canvas/Parser/transformations) restated in C++ behind C entry points, because no
+ *      Rust toolchain exists in this image.  It is what tests/ and bench.py drive; rtc_camera_render() marshals its
+ *      World into layer 1 exactly as the Rust Camera::render patch would.
+ *
+ * Errors: the reference panics (expect/panic!/assert!); here every fallible call returns 0 on success or a negative
+ * code and leaves a thread-local message for rtc_last_error().  Nothing aborts.  There is NO CPU fallback: without a
+ * usable CUDA device every rendering call fails with RTC_ERR_CUDA.
+ */
+#ifndef RTC_H
+#define RTC_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTC_OK 0
+#define RTC_ERR_INVALID (-1)  /* bad argument / malformed description */
+#define RTC_ERR_PANIC (-2)    /* the reference would have panicked (message says where: file:line) */
+#define RTC_ERR_CUDA (-3)     /* CUDA runtime failure or no device */
+#define RTC_ERR_UNSUPPORTED (-4)
+
+/* ShapeKind (src/shape.rs:14-39) */
+enum { RTC_SPHERE = 0, RTC_PLANE = 1, RTC_CUBE = 2, RTC_CYLINDER = 3, RTC_CONE = 4, RTC_GROUP = 5, RTC_TRIANGLE = 6 };
+/* PatternKind (src/pattern.rs:4-12) */
+enum { RTC_PATTERN_NONE = -1, RTC_PATTERN_STRIPE = 0, RTC_PATTERN_GRADIENT = 1, RTC_PATTERN_RING = 2,
+       RTC_PATTERN_CHECKERS = 3, RTC_PATTERN_TEST = 4 };
+
+/* Material (src/material.rs:4-14) with its Option<Pattern> (src/pattern.rs:14-19) flattened in.  Matrices are
+ * row-major 4x4.  pattern_inverse is Pattern.transform_inverse as the caller cached it (pattern.rs:63-66). */
+typedef struct rtc_material {
+    double color[3];
+    double ambient, diffuse, specular, shininess, reflective, transparency, refractive_index;
+    int32_t pattern_kind; /* RTC_PATTERN_* */
+    int32_t _pad;
+    double pattern_a[3], pattern_b[3];
+    double pattern_transform[16], pattern_inverse[16];
+} rtc_material;
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * 1. CORE BOUNDARY
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* Shape.transform and Shape.transform_inverse (src/shape.rs:44-45), row-major. */
+typedef struct rtc_transform_desc {
+    double transform[16];
+    double inverse[16];
+} rtc_transform_desc;
+
+/* ShapeKind::Triangle payload (src/shape.rs:31-38) as Shape::triangle computed it (src/shape.rs:171-193). */
+typedef struct rtc_triangle_desc {
+    double p1[3], p2[3], p3[3], e1[3], e2[3], normal[3];
+} rtc_triangle_desc;
+
+/* One Shape.  World.objects is sent as a pre-order walk: a group is followed by its `child_count` children, each
+ * followed by its own subtree (src/shape.rs:28-30). */
+typedef struct rtc_shape_desc {
+    int32_t kind;        /* RTC_SPHERE .. RTC_TRIANGLE */
+    int32_t material;    /* leaves: index into materials[] */
+    int32_t transform;   /* index into transforms[] (groups: their own, always identity in the reference) */
+    int32_t capped;      /* cylinder / cone */
+    double minimum, maximum;
+    int32_t child_count; /* groups only */
+    int32_t triangle;    /* triangles: index into triangles[] */
+} rtc_shape_desc;
+
+/* World (src/world.rs:13-16) + Light (src/light.rs:5-8). */
+typedef struct rtc_scene_desc {
+    const rtc_shape_desc* shapes;
+    uint32_t shape_count;
+    uint32_t root_count; /* World.objects.len() */
+    const rtc_transform_desc* transforms;
+    uint32_t transform_count;
+    const rtc_material* materials;
+    uint32_t material_count;
+    const rtc_triangle_desc* triangles;
+    uint32_t triangle_count;
+    double light_position[3];
+    double light_intensity[3];
+} rtc_scene_desc;
+
+/* Camera (src/camera.rs:5-12): the values Camera::new / set_transform computed (camera.rs:16-46). */
+typedef struct rtc_camera_desc {
+    uint32_t hsize, vsize;
+    double inverse[16]; /* transform_inverse */
+    double half_width, half_height, pixel_size;
+} rtc_camera_desc;
+
+/* Which rows of the frame a call renders.  Rows are grouped in bands of `band_rows`; the call renders bands
+ * band_first, band_first + band_stride, ... (row-cyclic sharding over GPUs: band_first = rank, band_stride = world
+ * size).  The output is COMPACT: local band k holds frame rows [ (band_first + k*band_stride) * band_rows, ... ).
+ * {band_rows = vsize, band_first = 0, band_stride = 1} (or a NULL pointer) is the whole frame. */
+typedef struct rtc_rows {
+    uint32_t band_rows, band_first, band_stride;
+} rtc_rows;
+
+/* Work counters of one render (exact; the numerators of Mrays/s). */
+typedef struct rtc_stats {
+    uint64_t primary_rays; /* pixels rendered (camera.rs:72) */
+    uint64_t shadow_rays;  /* is_shadowed calls = shade_hit calls (world.rs:65) */
+    uint64_t reflect_rays; /* world.rs:125 */
+    uint64_t refract_rays; /* world.rs:155 */
+    uint64_t kernel_launches;
+    double device_ms;      /* CUDA-event time of the render kernel(s) on the launch stream */
+} rtc_stats;
+
+typedef struct rtc_scene rtc_scene;
+
+/* Validates the description, computes the group gate boxes exactly as Bounds::new would per ray (src/bounds.rs:11-140),
+ * flattens the tree into device tables, builds the per-mesh BVH and uploads everything once to `device`.
+ * Fails with RTC_ERR_PANIC where the reference would panic while rendering this world (e.g. an uncapped cylinder inside
+ * a group: bounds.rs:143), RTC_ERR_UNSUPPORTED for non-affine transforms. */
+int rtc_scene_create(const rtc_scene_desc* desc, int device, rtc_scene** out);
+void rtc_scene_destroy(rtc_scene* scene);
+/* Flattened-scene facts for reports: n[0]=leaves, [1]=gates, [2]=meshes, [3]=mesh triangles, [4]=bvh nodes,
+ * [5]=device bytes. */
+int rtc_scene_info(const rtc_scene* scene, uint64_t n[6]);
+
+/* Camera::render (src/camera.rs:67-79) with HOST output buffers (either may be NULL):
+ *   rgba8_out  : rows*hsize*4 bytes, each channel quantised as canvas.rs:61-63 does at PPM time, alpha = 255
+ *   rgb_f64_out: rows*hsize*3 doubles, the Canvas colours themselves (canvas.rs:24-26)
+ * Includes the device->host copies.  `rows` NULL = whole frame. */
+int rtc_render(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows, uint8_t* rgba8_out,
+               double* rgb_f64_out, rtc_stats* stats);
+
+/* Same, DEVICE output buffers on the scene's device, asynchronous on `cuda_stream` (a cudaStream_t, 0 = default
+ * stream).  `stats` (nullable) is filled only if `sync_stats` is non-zero, which synchronises the stream. */
+int rtc_render_device(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows,
+                      void* d_rgba8_out, void* d_rgb_f64_out, void* cuda_stream, int sync_stats, rtc_stats* stats);
+
+/* Number of frame rows a (camera, rows) selection renders = the row count of the compact output buffers. */
+uint32_t rtc_rows_count(const rtc_camera_desc* camera, const rtc_rows* rows);
+
+/* World::color_at (src/world.rs:80-82) for `n` explicit rays (origin xyz, direction xyz; host pointers) -> rgb f64. */
+int rtc_color_at(const rtc_scene* scene, const double* rays, uint64_t n, double* rgb_out);
+
+/* Self-measured FP64 issue peaks of the device (independent DADD+DMUL chains, and DFMA chains), in Gflop/s with an FMA
+ * counted as 2.  Used as the FP64 roofline denominator (the path must run without FMA contraction). */
+int rtc_measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops);
+
+const char* rtc_last_error(void);
+int rtc_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * 2. HOST MIRROR of the reference API (C++ inside; the Rust host in the reference)
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct rtc_shape rtc_shape;   /* Shape   src/shape.rs:42-49 */
+typedef struct rtc_world rtc_world;   /* World   src/world.rs:13-16 */
+typedef struct rtc_camera rtc_camera; /* Camera  src/camera.rs:5-12 */
+typedef struct rtc_canvas rtc_canvas; /* Canvas  src/canvas.rs:5-9 */
+typedef struct rtc_marshalled rtc_marshalled; /* a World flattened into the arrays of an rtc_scene_desc */
+
+/* transformations.rs:4-93, matrix.rs:29-39,138-157,187-227 — row-major 4x4 in/out */
+void rtc_translation(double x, double y, double z, double* out16);
+void rtc_scaling(double x, double y, double z, double* out16);
+void rtc_rotation_x(double rad, double* out16);
+void rtc_rotation_y(double rad, double* out16);
+void rtc_rotation_z(double rad, double* out16);
+void rtc_shearing(double xy, double xz, double yx, double yz, double zx, double zy, double* out16);
+int rtc_view_transform(const double* from3, const double* to3, const double* up3, double* out16);
+void rtc_matrix_mul(const double* a16, const double* b16, double* out16);
+void rtc_matrix_transpose(const double* a16, double* out16);
+int rtc_matrix_inverse(const double* a16, double* out16); /* RTC_ERR_PANIC when |det| < 1e-5 (matrix.rs:140) */
+void rtc_matrix_mul_tuple(const double* a16, const double* t4, double* out4);
+
+/* material.rs:17-29 defaults; pattern.rs:63-66 */
+void rtc_material_default(rtc_material* m);
+int rtc_material_set_pattern_transform(rtc_material* m, const double* t16);
+
+/* shape.rs:52-245.  kind: RTC_SPHERE..RTC_GROUP (triangles via rtc_shape_triangle). */
+rtc_shape* rtc_shape_new(int kind, double minimum, double maximum, int capped);
+rtc_shape* rtc_shape_triangle(const double* p1, const double* p2, const double* p3);
+void rtc_shape_free(rtc_shape* s);
+int rtc_shape_set_transform(rtc_shape* s, const double* m16);      /* shape.rs:196-218: push-down, once per node */
+int rtc_shape_set_material(rtc_shape* s, const rtc_material* m);   /* shape.rs:220-229: push-down */
+int rtc_shape_push_shape(rtc_shape* group, rtc_shape* child);      /* shape.rs:528-535; consumes `child` */
+uint64_t rtc_shape_leaf_count(const rtc_shape* s);
+
+/* obj_file.rs:23-128: returns Parser::obj_to_group().  Named groups keep first-insertion order (the reference iterates
+ * a HashMap, i.e. a random order per process). */
+rtc_shape* rtc_obj_parse_file(const char* path, uint64_t* ignored_lines);
+rtc_shape* rtc_obj_parse_str(const char* text, uint64_t len, uint64_t* ignored_lines);
+/* group{ default_group{ triangles } } for vertex/face arrays (faces 1-based, 3 per triangle) */
+rtc_shape* rtc_mesh_from_arrays(const double* verts, uint64_t nverts, const int32_t* faces, uint64_t nfaces);
+
+/* world.rs:18-24, 26-41 */
+rtc_world* rtc_world_new(const double* light_position3, const double* light_intensity3);
+rtc_world* rtc_world_default(void);
+void rtc_world_free(rtc_world* w);
+int rtc_world_push(rtc_world* w, rtc_shape* s); /* World.objects.push; consumes `s` */
+/* World::color_at for n rays on the GPU (uploads the world on first use; cached until the world changes). */
+int rtc_world_color_at(rtc_world* w, const double* rays, uint64_t n, double* rgb_out);
+/* The layer-1 scene handle this world marshals into (created on first use on `device`); owned by the world. */
+int rtc_world_scene(rtc_world* w, int device, rtc_scene** out);
+
+/* The layer-1 description of this world: what rtc_world_scene passes to rtc_scene_create, and what the Rust-side
+ * Camera::render patch builds from its &World.  The rtc_scene_desc borrows from the rtc_marshalled. */
+int rtc_world_marshal(rtc_world* w, rtc_marshalled** out);
+const rtc_scene_desc* rtc_marshalled_desc(const rtc_marshalled* m);
+void rtc_marshalled_free(rtc_marshalled* m);
+/* Host-only views of what rtc_world_scene would send / build (no device needed; used by reports and CPU tests):
+ *   describe     n = {shapes, roots, transforms, materials, triangles} of the marshalled rtc_scene_desc
+ *   flatten_info n = {leaves, gates, meshes, mesh triangles, bvh nodes, bvh max depth, program nodes, distinct
+ *                transforms}; gates_out (nullable) receives the gate boxes, 6 doubles each (lo xyz, hi xyz). */
+int rtc_world_describe(rtc_world* w, uint64_t n[5]);
+int rtc_world_flatten_info(rtc_world* w, uint64_t n[8], double* gates_out, uint64_t gates_cap);
+
+/* camera.rs:16-46 */
+rtc_camera* rtc_camera_new(uint64_t hsize, uint64_t vsize, double field_of_view);
+void rtc_camera_free(rtc_camera* c);
+int rtc_camera_set_transform(rtc_camera* c, const double* m16);
+void rtc_camera_desc_get(const rtc_camera* c, rtc_camera_desc* out);
+/* camera.rs:67-79: Camera::render(&World) -> Canvas, on the GPU.  The canvas holds the f64 colours and the quantised
+ * RGBA8 frame.  `want_f64` = 0 skips the 24-byte-per-pixel colour copy (get_pixel then fails) and keeps the RGBA8 frame
+ * that to_ppm needs. */
+int rtc_camera_render(const rtc_camera* c, rtc_world* w, int want_f64, rtc_canvas** out, rtc_stats* stats);
+
+/* canvas.rs:12-58 */
+rtc_canvas* rtc_canvas_new(uint64_t width, uint64_t height);
+void rtc_canvas_free(rtc_canvas* c);
+uint64_t rtc_canvas_width(const rtc_canvas* c);
+uint64_t rtc_canvas_height(const rtc_canvas* c);
+int rtc_canvas_get_pixel(const rtc_canvas* c, uint64_t x, uint64_t y, double* rgb3);
+int rtc_canvas_set_pixel(rtc_canvas* c, uint64_t x, uint64_t y, const double* rgb3);
+const double* rtc_canvas_pixels_f64(const rtc_canvas* c); /* NULL if rendered with want_f64 = 0 */
+const uint8_t* rtc_canvas_pixels_rgba8(const rtc_canvas* c);
+/* canvas.rs:28-58: P3 text, 70-column wrap.  Returns a malloc'd buffer (free with rtc_free). */
+char* rtc_canvas_to_ppm(const rtc_canvas* c, uint64_t* len);
+/* the same encoder over a caller-owned RGBA8 frame (e.g. a frame gathered from several GPUs) */
+char* rtc_ppm_from_rgba8(const uint8_t* rgba8, uint64_t width, uint64_t height, uint64_t* len);
+void rtc_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTC_H */

@@ -1,0 +1,187 @@
+"""rtc_b200 — B200-native per-pixel render path for antoinehebert/ray-tracer-challenge-rust.
+
+The product is librtc_b200.so (CUDA sm_100a behind the C ABI of include/rtc.h); this package is its Python host: the
+reference's `World / Camera / Canvas / to_ppm` API (camera.rs, world.rs, canvas.rs) bound with ctypes.  There is no CPU
+rendering path: without the built library the import fails, and without a CUDA device every render call raises
+RtcError(RTC_ERR_CUDA).
+
+The directory name contains hyphens, so import it with importlib (tests/conftest.py and bench.py do):
+    rtc = importlib.import_module("ray-tracer-challenge-rust_b200")
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import scenes  # noqa: F401
+from ._capi import BuilderApi, CameraDesc, Rows, Stats, as_f64, dptr
+from ._lib import (LIB_PATH, RTC_ERR_CUDA, RTC_ERR_INVALID, RTC_ERR_PANIC, RTC_ERR_UNSUPPORTED, RTC_OK, RtcError,
+                   api)
+from .scene_api import (BLACK, BLUE, GREEN, RED, WHITE, CameraHandle, Light, Material, Matrix, Pattern, Shape, Shapes,
+                        Transformations, WorldHandle)
+
+__all__ = ["api", "World", "Camera", "Canvas", "Light", "Material", "Pattern", "Shapes", "Transformations", "Matrix",
+           "Rows", "Stats", "RtcError", "scenes", "device_count", "measure_fp64_peak", "ppm_from_rgba8"]
+
+
+def device_count():
+    return api().device_count()
+
+
+def measure_fp64_peak(device=0):
+    """Self-measured FP64 issue peaks in Gflop/s: (DMUL+DADD chains without FMA, DFMA chains counted as 2)."""
+    a, b = C.c_double(0), C.c_double(0)
+    api().check(api().measure_fp64_peak(device, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def ppm_from_rgba8(rgba8, width, height):
+    """Canvas::to_ppm (canvas.rs:28-58) over an RGBA8 frame -> bytes."""
+    a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+    if a.size != width * height * 4:
+        raise ValueError("rgba8 has the wrong size")
+    n = C.c_uint64(0)
+    p = api().ppm_from_rgba8(a.ctypes.data_as(C.c_void_p), width, height, C.byref(n))
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        api().free(p)
+
+
+class Canvas:
+    """Canvas (canvas.rs:5-63)."""
+
+    def __init__(self, width=None, height=None, _handle=None):
+        self.api = api()
+        self.h = _handle if _handle is not None else self.api.canvas_new(int(width), int(height))
+        self.width, self.height = self.api.canvas_width(self.h), self.api.canvas_height(self.h)
+
+    def get_pixel(self, x, y):
+        out = np.empty(3)
+        self.api.check(self.api.canvas_get_pixel(self.h, x, y, dptr(out)))
+        return out
+
+    def set_pixel(self, x, y, color):
+        c = as_f64(color, 3)
+        self.api.check(self.api.canvas_set_pixel(self.h, x, y, dptr(c)))
+
+    def pixels_f64(self):
+        """(height, width, 3) float64 copy of the Canvas colours, or None (rendered with want_f64=False)."""
+        p = self.api.canvas_pixels_f64(self.h)
+        if not p:
+            return None
+        return np.ctypeslib.as_array(p, shape=(self.height, self.width, 3)).copy()
+
+    def pixels_rgba8(self):
+        p = self.api.canvas_pixels_rgba8(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.height, self.width, 4)).copy()
+
+    def to_ppm(self):
+        n = C.c_uint64(0)
+        p = self.api.canvas_to_ppm(self.h, C.byref(n))
+        try:
+            return C.string_at(p, n.value)
+        finally:
+            self.api.free(p)
+
+    def __del__(self):
+        if getattr(self, "h", None) is not None:
+            self.api.canvas_free(self.h)
+            self.h = None
+
+
+class World(WorldHandle):
+    """World (world.rs:13-98) on the GPU."""
+
+    def __init__(self, light=None, _handle=None):
+        super().__init__(api(), light, _handle)
+
+    @staticmethod
+    def default_world():  # world.rs:26-41
+        return World(_handle=api().world_default())
+
+    def color_at(self, rays):
+        """World::color_at (world.rs:80-82) for an (n, 6) array of rays (origin xyz, direction xyz) -> (n, 3)."""
+        r = as_f64(rays).reshape(-1, 6)
+        out = np.empty((r.shape[0], 3))
+        self.api.check(self.api.world_color_at(self.h, dptr(r), r.shape[0], dptr(out)))
+        return out
+
+    def scene(self, device=0):
+        """The layer-1 rtc_scene handle (flattened + uploaded on first use; owned by the world)."""
+        s = C.c_void_p()
+        self.api.check(self.api.world_scene(self.h, device, C.byref(s)))
+        return s
+
+    def scene_info(self, device=0):
+        n = (C.c_uint64 * 6)()
+        self.api.check(self.api.scene_info(self.scene(device), n))
+        return dict(zip(("leaves", "gates", "meshes", "mesh_triangles", "bvh_nodes", "device_bytes"), list(n)))
+
+    def flatten_info(self, want_gates=False):
+        """Host-only flattening facts (no device needed)."""
+        n = (C.c_uint64 * 8)()
+        self.api.check(self.api.world_flatten_info(self.h, n, None, 0))
+        info = dict(zip(("leaves", "gates", "meshes", "mesh_triangles", "bvh_nodes", "bvh_max_depth", "program_nodes",
+                         "transforms"), list(n)))
+        if want_gates:
+            g = np.empty((info["gates"], 6))
+            self.api.check(self.api.world_flatten_info(self.h, n, dptr(g), info["gates"]))
+            info["gate_boxes"] = g
+        return info
+
+
+class Camera(CameraHandle):
+    """Camera (camera.rs:5-79); render() is the drop-in for camera.rs:67-79."""
+
+    def __init__(self, hsize, vsize, field_of_view):
+        super().__init__(api(), hsize, vsize, field_of_view)
+
+    def desc(self):
+        d = CameraDesc()
+        self.api.camera_desc_get(self.h, C.byref(d))
+        return d
+
+    def render(self, world, want_f64=True, stats=None):
+        """Camera::render(&World) -> Canvas.  `stats` (a Stats) receives ray counts and the kernel's device time."""
+        out = C.c_void_p()
+        st = stats if stats is not None else None
+        self.api.check(self.api.camera_render(self.h, world.h, int(bool(want_f64)), C.byref(out),
+                                              C.byref(st) if st is not None else None))
+        return Canvas(_handle=out)
+
+    def render_into(self, world, rgba8=None, rgb_f64=None, rows=None, stats=None, device=0):
+        """rtc_render with caller-owned HOST arrays (numpy; pinned torch tensors work through .numpy()):
+        rgba8 (local_rows, hsize, 4) uint8 and/or rgb_f64 (local_rows, hsize, 3) float64."""
+        d = self.desc()
+        p8 = rgba8.ctypes.data_as(C.c_void_p) if rgba8 is not None else None
+        p64 = rgb_f64.ctypes.data_as(C.c_void_p) if rgb_f64 is not None else None
+        self.api.check(self.api.render(world.scene(device), C.byref(d), C.byref(rows) if rows is not None else None,
+                                       p8, p64, C.byref(stats) if stats is not None else None))
+
+    def render_device(self, world, d_rgba8=None, d_rgb_f64=None, rows=None, stream=0, stats=None, device=0):
+        """rtc_render_device: DEVICE pointers (ints, e.g. torch tensor .data_ptr()), asynchronous on `stream` (a
+        cudaStream_t as int).  With `stats` the call synchronises the stream and fills it."""
+        d = self.desc()
+        self.api.check(self.api.render_device(world.scene(device), C.byref(d),
+                                              C.byref(rows) if rows is not None else None,
+                                              C.c_void_p(d_rgba8) if d_rgba8 else None,
+                                              C.c_void_p(d_rgb_f64) if d_rgb_f64 else None,
+                                              C.c_void_p(stream) if stream else None,
+                                              1 if stats is not None else 0,
+                                              C.byref(stats) if stats is not None else None))
+
+    def rows_count(self, rows=None):
+        d = self.desc()
+        return self.api.rows_count(C.byref(d), C.byref(rows) if rows is not None else None)
+
+
+def build_scene(name, hsize=None, vsize=None):
+    """A named BASELINE config as (World, Camera) on the product library."""
+    w, c = scenes.build(api(), name, hsize, vsize)
+    world = World(_handle=w.h)
+    w.h = None
+    world.light = w.light
+    cam = Camera.__new__(Camera)
+    cam.api, cam.hsize, cam.vsize, cam.field_of_view, cam.h = c.api, c.hsize, c.vsize, c.field_of_view, c.h
+    c.h = None
+    return world, cam

@@ -1,0 +1,73 @@
+"""Loads librtc_b200.so (built in-tree by build.py) and declares the rest of include/rtc.h."""
+import ctypes as C
+import os
+
+from ._capi import BuilderApi, CameraDesc, Material, Rows, Stats, c_double_p, c_u64_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librtc_b200.so")
+
+RTC_OK, RTC_ERR_INVALID, RTC_ERR_PANIC, RTC_ERR_CUDA, RTC_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+
+
+class RtcError(RuntimeError):
+    """A non-zero status from librtc_b200.so.  code == RTC_ERR_PANIC marks what the reference would panic on."""
+
+    def __init__(self, code, message):
+        super().__init__(f"rtc error {code}: {message}")
+        self.code, self.message = code, message
+
+
+class RtcApi(BuilderApi):
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: build it with `python ray-tracer-challenge-rust_b200/build.py` "
+                              "(there is no CPU fallback)")
+        super().__init__(C.CDLL(path), "rtc_")
+        self.path = path
+        f, vp = self._fn, C.c_void_p
+        u8p = C.POINTER(C.c_uint8)
+        f("device_count", C.c_int)
+        f("scene_create", C.c_int, vp, C.c_int, C.POINTER(vp))
+        f("scene_destroy", None, vp)
+        f("scene_info", C.c_int, vp, c_u64_p)
+        f("render", C.c_int, vp, C.POINTER(CameraDesc), C.POINTER(Rows), vp, vp, C.POINTER(Stats))
+        f("render_device", C.c_int, vp, C.POINTER(CameraDesc), C.POINTER(Rows), vp, vp, vp, C.c_int, C.POINTER(Stats))
+        f("rows_count", C.c_uint32, C.POINTER(CameraDesc), C.POINTER(Rows))
+        f("color_at", C.c_int, vp, c_double_p, C.c_uint64, c_double_p)
+        f("measure_fp64_peak", C.c_int, C.c_int, c_double_p, c_double_p)
+        f("world_color_at", C.c_int, vp, c_double_p, C.c_uint64, c_double_p)
+        f("world_scene", C.c_int, vp, C.c_int, C.POINTER(vp))
+        f("world_describe", C.c_int, vp, c_u64_p)
+        f("world_flatten_info", C.c_int, vp, c_u64_p, c_double_p, C.c_uint64)
+        f("world_marshal", C.c_int, vp, C.POINTER(vp))
+        f("marshalled_desc", vp, vp)
+        f("marshalled_free", None, vp)
+        f("camera_desc_get", None, vp, C.POINTER(CameraDesc))
+        f("camera_render", C.c_int, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(Stats))
+        f("canvas_new", vp, C.c_uint64, C.c_uint64)
+        f("canvas_free", None, vp)
+        f("canvas_width", C.c_uint64, vp)
+        f("canvas_height", C.c_uint64, vp)
+        f("canvas_get_pixel", C.c_int, vp, C.c_uint64, C.c_uint64, c_double_p)
+        f("canvas_set_pixel", C.c_int, vp, C.c_uint64, C.c_uint64, c_double_p)
+        f("canvas_pixels_f64", c_double_p, vp)
+        f("canvas_pixels_rgba8", u8p, vp)
+        f("canvas_to_ppm", vp, vp, c_u64_p)
+        f("ppm_from_rgba8", vp, vp, C.c_uint64, C.c_uint64, c_u64_p)
+        f("free", None, vp)
+
+    def check(self, rc):
+        if rc != RTC_OK:
+            raise RtcError(rc, self.error())
+
+
+_api = None
+
+
+def api():
+    """The process-wide binding (loads the library on first use; raises ImportError if it was never built)."""
+    global _api
+    if _api is None:
+        _api = RtcApi()
+    return _api

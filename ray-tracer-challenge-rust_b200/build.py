@@ -1,0 +1,72 @@
+"""Builds librtc_b200.so (the C-ABI library of include/rtc.h) in-tree for sm_100a.
+
+    python ray-tracer-challenge-rust_b200/build.py [--force]
+
+Host translation units are compiled by g++ with -ffp-contract=off (their matrices, gate boxes and triangle normals
+reach pixels and must round exactly as the reference's Rust does); the CUDA translation unit by nvcc for
+compute_100a/sm_100a with -fmad=false (same reason, see csrc/rt_core.cuh) and -lineinfo for ncu source pages.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "librtc_b200.so")
+ROOT = os.path.dirname(HERE)
+
+HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fno-unsafe-math-optimizations", "-fPIC",
+              "-Wall", "-Wextra", "-Wno-unused-parameter"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _sources():
+    out = []
+    for d, _, files in os.walk(CSRC):
+        out += [os.path.join(d, f) for f in files]
+    out += [os.path.join(ROOT, "include", "rtc.h"), os.path.abspath(__file__)]
+    return out
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def _run(cmd, log):
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log.write("$ " + " ".join(cmd) + "\n" + p.stdout + "\n")
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout)
+        raise RuntimeError("build step failed: " + " ".join(cmd))
+
+
+def build(force=False, verbose=False):
+    """Compile if sources are newer than the library; returns the library path."""
+    if not force and not _stale():
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    nvcc = _nvcc()
+    with open(os.path.join(BUILD, "build.log"), "w") as log:
+        _run(["g++", *HOST_FLAGS, "-c", os.path.join(CSRC, "capi.cpp"), "-o", os.path.join(BUILD, "capi.o")], log)
+        _run([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "render.cu"), "-o", os.path.join(BUILD, "render.o")], log)
+        _run([nvcc, "-shared", "-o", LIB, os.path.join(BUILD, "capi.o"), os.path.join(BUILD, "render.o")], log)
+    if verbose:
+        print(open(os.path.join(BUILD, "build.log")).read())
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

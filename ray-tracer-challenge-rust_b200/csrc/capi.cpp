@@ -1,0 +1,548 @@
+// capi.cpp — the extern "C" surface of librtc_b200.so (include/rtc.h): the CORE boundary that replaces
+// Camera::render (camera.rs:67-79) and World::color_at (world.rs:80-82), and the HOST MIRROR of the reference's scene
+// API.  There is no CPU rendering path in this library: every render / color_at call needs a CUDA device and fails with
+// RTC_ERR_CUDA otherwise.
+#include <cstdio>
+#include <fstream>
+#include <mutex>
+#include <sstream>
+
+#include "../../include/rtc.h"
+#include "flatten.hpp"
+#include "host_model.hpp"
+#include "render.cuh"
+
+using namespace rtc;
+
+namespace {
+thread_local std::string g_err;
+int set_err(int code, const std::string& m) {
+    g_err = m;
+    return code;
+}
+DCamera to_dcamera(const rtc_camera_desc& c) {
+    DCamera d;
+    d.hsize = c.hsize;
+    d.vsize = c.vsize;
+    std::memcpy(d.inv, c.inverse, sizeof(d.inv));
+    d.half_width = c.half_width;
+    d.half_height = c.half_height;
+    d.pixel_size = c.pixel_size;
+    return d;
+}
+// rows == NULL: the whole frame
+int to_drows(const rtc_camera_desc& cam, const rtc_rows* rows, DRows* out) {
+    if (!rows) {
+        out->band_rows = cam.vsize ? cam.vsize : 1;
+        out->band_first = 0;
+        out->band_stride = 1;
+        out->local_rows = cam.vsize;
+        return RTC_OK;
+    }
+    if (rows->band_rows == 0 || rows->band_stride == 0) return set_err(RTC_ERR_INVALID, "band_rows and band_stride must be > 0");
+    out->band_rows = rows->band_rows;
+    out->band_first = rows->band_first;
+    out->band_stride = rows->band_stride;
+    // rows owned by bands band_first, band_first + stride, ... below vsize
+    uint64_t local = 0;
+    for (uint64_t b = rows->band_first;; b += rows->band_stride) {
+        uint64_t r0 = b * rows->band_rows;
+        if (r0 >= cam.vsize) break;
+        uint64_t r1 = r0 + rows->band_rows;
+        if (r1 > cam.vsize) r1 = cam.vsize;
+        local += r1 - r0;
+    }
+    out->local_rows = (uint32_t)local;
+    return RTC_OK;
+}
+void fill_stats(const LaunchStats& ls, rtc_stats* st) {
+    if (!st) return;
+    st->primary_rays = ls.primary;
+    st->shadow_rays = ls.shadow;
+    st->reflect_rays = ls.reflect;
+    st->refract_rays = ls.refract;
+    st->kernel_launches = ls.launches;
+    st->device_ms = ls.device_ms;
+}
+bool affine_camera(const rtc_camera_desc& c) {
+    const double* b = c.inverse;
+    return b[12] == 0.0 && b[13] == 0.0 && b[14] == 0.0 && b[15] == 1.0;
+}
+}  // namespace
+
+struct rtc_scene {
+    DeviceScene* dev = nullptr;
+    uint64_t info[6] = {0, 0, 0, 0, 0, 0};
+};
+struct rtc_shape {
+    std::unique_ptr<HShape> s;
+};
+struct rtc_world {
+    HWorld w;
+    rtc_scene* scene = nullptr;  // marshalled + uploaded on first use; dropped when the world changes
+    std::mutex mu;
+};
+struct rtc_camera {
+    HCamera c;
+};
+struct rtc_marshalled {
+    Marshalled m;
+};
+struct rtc_canvas {
+    uint64_t width = 0, height = 0;
+    double* rgb = nullptr;     // Canvas.pixels (canvas.rs:8), 3 f64 per pixel; may be absent for want_f64 = 0 renders
+    uint8_t* rgba8 = nullptr;  // the same pixels quantised as canvas.rs:61-63
+    bool rgb_pinned = false, rgba_pinned = false;
+};
+
+extern "C" {
+
+const char* rtc_last_error(void) { return g_err.c_str(); }
+int rtc_device_count(void) {
+    std::string e;
+    int n = cuda_device_count(&e);
+    if (n == 0 && !e.empty()) g_err = e;
+    return n;
+}
+
+/* ---------------------------------------------------------------------------------------------- 1. CORE BOUNDARY */
+int rtc_scene_create(const rtc_scene_desc* desc, int device, rtc_scene** out) {
+    if (!desc || !out) return set_err(RTC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    FlatScene flat;
+    std::string e;
+    int rc = flatten_scene(*desc, flat, &e);
+    if (rc != RTC_OK) return set_err(rc, e);
+    DeviceScene* dev = nullptr;
+    rc = device_scene_create(flat, device, &dev, &e);
+    if (rc != 0) return set_err(RTC_ERR_CUDA, e);
+    rtc_scene* s = new rtc_scene();
+    s->dev = dev;
+    s->info[0] = flat.leaf_count;
+    s->info[1] = flat.gates.size();
+    s->info[2] = flat.meshes.size();
+    s->info[3] = flat.tris.size();
+    s->info[4] = flat.bvh.size();
+    s->info[5] = device_scene_bytes(dev);
+    *out = s;
+    return RTC_OK;
+}
+void rtc_scene_destroy(rtc_scene* scene) {
+    if (!scene) return;
+    device_scene_destroy(scene->dev);
+    delete scene;
+}
+int rtc_scene_info(const rtc_scene* scene, uint64_t n[6]) {
+    if (!scene || !n) return set_err(RTC_ERR_INVALID, "null argument");
+    std::memcpy(n, scene->info, sizeof(scene->info));
+    return RTC_OK;
+}
+
+int rtc_render(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows, uint8_t* rgba8_out,
+               double* rgb_f64_out, rtc_stats* stats) {
+    if (!scene || !camera) return set_err(RTC_ERR_INVALID, "null argument");
+    if (!affine_camera(*camera)) return set_err(RTC_ERR_UNSUPPORTED, "non-affine camera transform");
+    DRows dr;
+    int rc = to_drows(*camera, rows, &dr);
+    if (rc != RTC_OK) return rc;
+    LaunchStats ls;
+    std::string e;
+    rc = render_host(scene->dev, to_dcamera(*camera), dr, rgba8_out, rgb_f64_out, stats ? &ls : nullptr, &e);
+    if (rc != 0) return set_err(RTC_ERR_CUDA, e);
+    fill_stats(ls, stats);
+    return RTC_OK;
+}
+
+int rtc_render_device(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows, void* d_rgba8_out,
+                      void* d_rgb_f64_out, void* cuda_stream, int sync_stats, rtc_stats* stats) {
+    if (!scene || !camera) return set_err(RTC_ERR_INVALID, "null argument");
+    if (!affine_camera(*camera)) return set_err(RTC_ERR_UNSUPPORTED, "non-affine camera transform");
+    DRows dr;
+    int rc = to_drows(*camera, rows, &dr);
+    if (rc != RTC_OK) return rc;
+    LaunchStats ls;
+    std::string e;
+    const bool want = sync_stats && stats;
+    rc = render_device(scene->dev, to_dcamera(*camera), dr, d_rgba8_out, d_rgb_f64_out, cuda_stream, want ? &ls : nullptr, &e);
+    if (rc != 0) return set_err(RTC_ERR_CUDA, e);
+    if (want) fill_stats(ls, stats);
+    return RTC_OK;
+}
+
+uint32_t rtc_rows_count(const rtc_camera_desc* camera, const rtc_rows* rows) {
+    if (!camera) return 0;
+    DRows dr;
+    if (to_drows(*camera, rows, &dr) != RTC_OK) return 0;
+    return dr.local_rows;
+}
+
+int rtc_color_at(const rtc_scene* scene, const double* rays, uint64_t n, double* rgb_out) {
+    if (!scene || (n && (!rays || !rgb_out))) return set_err(RTC_ERR_INVALID, "null argument");
+    std::string e;
+    if (color_at_host(scene->dev, rays, n, rgb_out, &e) != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+
+int rtc_measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops) {
+    std::string e;
+    if (measure_fp64_peak(device, nofma_gflops, fma_gflops, &e) != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ 2. HOST MIRROR */
+void rtc_translation(double x, double y, double z, double* o) { std::memcpy(o, translation(x, y, z).m, 128); }
+void rtc_scaling(double x, double y, double z, double* o) { std::memcpy(o, scaling(x, y, z).m, 128); }
+void rtc_rotation_x(double r, double* o) { std::memcpy(o, rotation_x(r).m, 128); }
+void rtc_rotation_y(double r, double* o) { std::memcpy(o, rotation_y(r).m, 128); }
+void rtc_rotation_z(double r, double* o) { std::memcpy(o, rotation_z(r).m, 128); }
+void rtc_shearing(double xy, double xz, double yx, double yz, double zx, double zy, double* o) {
+    std::memcpy(o, shearing(xy, xz, yx, yz, zx, zy).m, 128);
+}
+int rtc_view_transform(const double* from, const double* to, const double* up, double* o) {
+    if (!from || !to || !up || !o) return set_err(RTC_ERR_INVALID, "null argument");
+    Mat4 m = view_transform(point(from[0], from[1], from[2]), point(to[0], to[1], to[2]), vector(up[0], up[1], up[2]));
+    std::memcpy(o, m.m, 128);
+    return RTC_OK;
+}
+void rtc_matrix_mul(const double* a, const double* b, double* o) {
+    Mat4 r = mul(Mat4::from(a), Mat4::from(b));
+    std::memcpy(o, r.m, 128);
+}
+void rtc_matrix_transpose(const double* a, double* o) {
+    Mat4 r = transpose(Mat4::from(a));
+    std::memcpy(o, r.m, 128);
+}
+int rtc_matrix_inverse(const double* a, double* o) {
+    Mat4 r;
+    if (!inverse(Mat4::from(a), &r)) return set_err(RTC_ERR_PANIC, "matrix is not invertible: |det| < 1e-5 (src/matrix.rs:140)");
+    std::memcpy(o, r.m, 128);
+    return RTC_OK;
+}
+void rtc_matrix_mul_tuple(const double* a, const double* t, double* o) {
+    Vec4 r = mul(Mat4::from(a), Vec4{t[0], t[1], t[2], t[3]});
+    o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+}
+
+void rtc_material_default(rtc_material* m) { material_default(m); }
+int rtc_material_set_pattern_transform(rtc_material* m, const double* t) {
+    Mat4 inv;
+    if (!inverse(Mat4::from(t), &inv)) return set_err(RTC_ERR_PANIC, "should be invertible (src/pattern.rs:65)");
+    std::memcpy(m->pattern_transform, t, 128);
+    std::memcpy(m->pattern_inverse, inv.m, 128);
+    return RTC_OK;
+}
+
+rtc_shape* rtc_shape_new(int kind, double minimum, double maximum, int capped) {
+    if (kind < RTC_SPHERE || kind > RTC_GROUP) {
+        g_err = "unknown shape kind";
+        return nullptr;
+    }
+    return new rtc_shape{shape_new(kind, minimum, maximum, capped != 0)};
+}
+rtc_shape* rtc_shape_triangle(const double* p1, const double* p2, const double* p3) {
+    if (!p1 || !p2 || !p3) {
+        g_err = "null argument";
+        return nullptr;
+    }
+    return new rtc_shape{shape_triangle(p1, p2, p3)};
+}
+void rtc_shape_free(rtc_shape* s) { delete s; }
+int rtc_shape_set_transform(rtc_shape* s, const double* m) {
+    if (!s || !s->s || !m) return set_err(RTC_ERR_INVALID, "null argument");
+    try {
+        shape_set_transform(s->s.get(), Mat4::from(m));
+        return RTC_OK;
+    } catch (const HostPanic& e) { return set_err(RTC_ERR_PANIC, e.what()); }
+}
+int rtc_shape_set_material(rtc_shape* s, const rtc_material* m) {
+    if (!s || !s->s || !m) return set_err(RTC_ERR_INVALID, "null argument");
+    shape_set_material(s->s.get(), *m);
+    return RTC_OK;
+}
+int rtc_shape_push_shape(rtc_shape* group, rtc_shape* child) {
+    if (!group || !group->s || !child || !child->s) return set_err(RTC_ERR_INVALID, "null argument");
+    try {
+        shape_push(group->s.get(), std::move(child->s));
+        delete child;
+        return RTC_OK;
+    } catch (const HostPanic& e) { return set_err(RTC_ERR_PANIC, e.what()); }
+}
+uint64_t rtc_shape_leaf_count(const rtc_shape* s) { return (s && s->s) ? shape_leaf_count(s->s.get()) : 0; }
+
+rtc_shape* rtc_obj_parse_str(const char* text, uint64_t len, uint64_t* ignored_lines) {
+    if (!text && len) {
+        g_err = "null argument";
+        return nullptr;
+    }
+    try {
+        ObjResult r = obj_parse(text, (size_t)len);
+        if (ignored_lines) *ignored_lines = r.ignored_lines;
+        return new rtc_shape{std::move(r.group)};
+    } catch (const HostPanic& e) {
+        set_err(RTC_ERR_PANIC, e.what());
+        return nullptr;
+    }
+}
+rtc_shape* rtc_obj_parse_file(const char* path, uint64_t* ignored_lines) {
+    std::ifstream f(path ? path : "", std::ios::binary);
+    if (!f) {
+        set_err(RTC_ERR_PANIC, std::string("something went wrong reading ") + (path ? path : "(null)") + ". (src/obj_file.rs:25)");
+        return nullptr;
+    }
+    std::stringstream ss;
+    ss << f.rdbuf();
+    std::string text = ss.str();
+    return rtc_obj_parse_str(text.data(), text.size(), ignored_lines);
+}
+rtc_shape* rtc_mesh_from_arrays(const double* verts, uint64_t nverts, const int32_t* faces, uint64_t nfaces) {
+    if ((nverts && !verts) || (nfaces && !faces)) {
+        g_err = "null argument";
+        return nullptr;
+    }
+    auto def = shape_new(RTC_GROUP, 0., 0., false);
+    for (uint64_t f = 0; f < nfaces; f++) {
+        const double* p[3];
+        for (int k = 0; k < 3; k++) {
+            int64_t i = faces[f * 3 + k];
+            if (i < 1 || (uint64_t)i > nverts) {
+                set_err(RTC_ERR_PANIC, "index out of bounds (src/obj_file.rs:117)");
+                return nullptr;
+            }
+            p[k] = verts + (i - 1) * 3;
+        }
+        shape_push(def.get(), shape_triangle(p[0], p[1], p[2]));
+    }
+    auto g = shape_new(RTC_GROUP, 0., 0., false);
+    shape_push(g.get(), std::move(def));
+    return new rtc_shape{std::move(g)};
+}
+
+rtc_world* rtc_world_new(const double* light_position3, const double* light_intensity3) {
+    if (!light_position3 || !light_intensity3) {
+        g_err = "null argument";
+        return nullptr;
+    }
+    rtc_world* w = new rtc_world();
+    for (int k = 0; k < 3; k++) {
+        w->w.light_position[k] = light_position3[k];
+        w->w.light_intensity[k] = light_intensity3[k];
+    }
+    return w;
+}
+rtc_world* rtc_world_default(void) {
+    rtc_world* w = new rtc_world();
+    auto d = world_default();
+    w->w = std::move(*d);
+    return w;
+}
+void rtc_world_free(rtc_world* w) {
+    if (!w) return;
+    rtc_scene_destroy(w->scene);
+    delete w;
+}
+int rtc_world_push(rtc_world* w, rtc_shape* s) {
+    if (!w || !s || !s->s) return set_err(RTC_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(w->mu);
+    w->w.objects.push_back(std::move(s->s));
+    delete s;
+    rtc_scene_destroy(w->scene);
+    w->scene = nullptr;
+    return RTC_OK;
+}
+int rtc_world_scene(rtc_world* w, int device, rtc_scene** out) {
+    if (!w || !out) return set_err(RTC_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(w->mu);
+    if (w->scene && device_scene_device(w->scene->dev) != device) {
+        rtc_scene_destroy(w->scene);
+        w->scene = nullptr;
+    }
+    if (!w->scene) {
+        Marshalled m;
+        marshal_world(w->w, m);
+        int rc = rtc_scene_create(&m.desc, device, &w->scene);
+        if (rc != RTC_OK) return rc;
+    }
+    *out = w->scene;
+    return RTC_OK;
+}
+// The layer-1 description of a world — exactly what rtc_world_scene hands to rtc_scene_create, and what the Rust-side
+// Camera::render patch builds from its &World.  The description borrows from the returned object.
+int rtc_world_marshal(rtc_world* w, rtc_marshalled** out) {
+    if (!w || !out) return set_err(RTC_ERR_INVALID, "null argument");
+    rtc_marshalled* m = new rtc_marshalled();
+    marshal_world(w->w, m->m);
+    *out = m;
+    return RTC_OK;
+}
+const rtc_scene_desc* rtc_marshalled_desc(const rtc_marshalled* m) { return m ? &m->m.desc : nullptr; }
+void rtc_marshalled_free(rtc_marshalled* m) { delete m; }
+// The marshalled description of a world (what the Rust Camera::render patch would build), for tests of the flattener
+// that need no device: returns counts {shapes, roots, transforms, materials, triangles}.
+int rtc_world_describe(rtc_world* w, uint64_t n[5]) {
+    if (!w || !n) return set_err(RTC_ERR_INVALID, "null argument");
+    Marshalled m;
+    marshal_world(w->w, m);
+    n[0] = m.shapes.size();
+    n[1] = w->w.objects.size();
+    n[2] = m.transforms.size();
+    n[3] = m.materials.size();
+    n[4] = m.triangles.size();
+    return RTC_OK;
+}
+// Host-only half of rtc_scene_create (validation, gate boxes, flattening, BVH) without the upload, for reports and CPU
+// tests: n = {leaves, gates, meshes, mesh triangles, bvh nodes, bvh max depth, program nodes, distinct transforms}.
+// Optionally copies the gate boxes (6 doubles each: lo xyz, hi xyz) into gates_out (capacity gates_cap boxes).
+int rtc_world_flatten_info(rtc_world* w, uint64_t n[8], double* gates_out, uint64_t gates_cap) {
+    if (!w || !n) return set_err(RTC_ERR_INVALID, "null argument");
+    Marshalled m;
+    marshal_world(w->w, m);
+    FlatScene flat;
+    std::string e;
+    int rc = flatten_scene(m.desc, flat, &e);
+    if (rc != RTC_OK) return set_err(rc, e);
+    n[0] = flat.leaf_count;
+    n[1] = flat.gates.size();
+    n[2] = flat.meshes.size();
+    n[3] = flat.tris.size();
+    n[4] = flat.bvh.size();
+    n[5] = (uint64_t)flat.bvh_max_depth;
+    n[6] = flat.program.size();
+    n[7] = flat.xforms.size();
+    if (gates_out)
+        for (uint64_t i = 0; i < flat.gates.size() && i < gates_cap; i++) {
+            std::memcpy(gates_out + 6 * i, flat.gates[i].lo, 24);
+            std::memcpy(gates_out + 6 * i + 3, flat.gates[i].hi, 24);
+        }
+    return RTC_OK;
+}
+int rtc_world_color_at(rtc_world* w, const double* rays, uint64_t n, double* rgb_out) {
+    rtc_scene* s = nullptr;
+    int rc = rtc_world_scene(w, 0, &s);
+    if (rc != RTC_OK) return rc;
+    return rtc_color_at(s, rays, n, rgb_out);
+}
+
+rtc_camera* rtc_camera_new(uint64_t hsize, uint64_t vsize, double fov) {
+    rtc_camera* c = new rtc_camera();
+    c->c = *camera_new(hsize, vsize, fov);
+    return c;
+}
+void rtc_camera_free(rtc_camera* c) { delete c; }
+int rtc_camera_set_transform(rtc_camera* c, const double* m) {
+    if (!c || !m) return set_err(RTC_ERR_INVALID, "null argument");
+    try {
+        camera_set_transform(&c->c, Mat4::from(m));
+        return RTC_OK;
+    } catch (const HostPanic& e) { return set_err(RTC_ERR_PANIC, e.what()); }
+}
+void rtc_camera_desc_get(const rtc_camera* c, rtc_camera_desc* out) {
+    out->hsize = (uint32_t)c->c.hsize;
+    out->vsize = (uint32_t)c->c.vsize;
+    std::memcpy(out->inverse, c->c.inverse.m, 128);
+    out->half_width = c->c.half_width;
+    out->half_height = c->c.half_height;
+    out->pixel_size = c->c.pixel_size;
+}
+
+static rtc_canvas* canvas_alloc(uint64_t width, uint64_t height, bool want_f64, bool pinned) {
+    rtc_canvas* cv = new rtc_canvas();
+    cv->width = width;
+    cv->height = height;
+    const size_t px = (size_t)width * height;
+    if (pinned) {
+        cv->rgba8 = (uint8_t*)pinned_alloc(px * 4);
+        cv->rgba_pinned = cv->rgba8 != nullptr;
+    }
+    if (!cv->rgba8) cv->rgba8 = (uint8_t*)std::malloc(px * 4 ? px * 4 : 1);
+    if (want_f64) {
+        if (pinned) {
+            cv->rgb = (double*)pinned_alloc(px * 24);
+            cv->rgb_pinned = cv->rgb != nullptr;
+        }
+        if (!cv->rgb) cv->rgb = (double*)std::malloc(px * 24 ? px * 24 : 1);
+    }
+    return cv;
+}
+
+int rtc_camera_render(const rtc_camera* c, rtc_world* w, int want_f64, rtc_canvas** out, rtc_stats* stats) {
+    if (!c || !w || !out) return set_err(RTC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    rtc_scene* s = nullptr;
+    int rc = rtc_world_scene(w, 0, &s);
+    if (rc != RTC_OK) return rc;
+    rtc_camera_desc cd;
+    rtc_camera_desc_get(c, &cd);
+    rtc_canvas* cv = canvas_alloc(c->c.hsize, c->c.vsize, want_f64 != 0, true);
+    rc = rtc_render(s, &cd, nullptr, cv->rgba8, cv->rgb, stats);
+    if (rc != RTC_OK) {
+        rtc_canvas_free(cv);
+        return rc;
+    }
+    *out = cv;
+    return RTC_OK;
+}
+
+rtc_canvas* rtc_canvas_new(uint64_t width, uint64_t height) {  // canvas.rs:12-18: all BLACK
+    rtc_canvas* cv = canvas_alloc(width, height, true, false);
+    const size_t px = (size_t)width * height;
+    for (size_t i = 0; i < px * 3; i++) cv->rgb[i] = 0.;
+    for (size_t i = 0; i < px; i++) {
+        cv->rgba8[4 * i] = cv->rgba8[4 * i + 1] = cv->rgba8[4 * i + 2] = 0;
+        cv->rgba8[4 * i + 3] = 255;
+    }
+    return cv;
+}
+void rtc_canvas_free(rtc_canvas* c) {
+    if (!c) return;
+    if (c->rgb) c->rgb_pinned ? pinned_free(c->rgb) : std::free(c->rgb);
+    if (c->rgba8) c->rgba_pinned ? pinned_free(c->rgba8) : std::free(c->rgba8);
+    delete c;
+}
+uint64_t rtc_canvas_width(const rtc_canvas* c) { return c ? c->width : 0; }
+uint64_t rtc_canvas_height(const rtc_canvas* c) { return c ? c->height : 0; }
+int rtc_canvas_get_pixel(const rtc_canvas* c, uint64_t x, uint64_t y, double* rgb3) {
+    if (!c || !rgb3) return set_err(RTC_ERR_INVALID, "null argument");
+    if (x >= c->width || y >= c->height) return set_err(RTC_ERR_PANIC, "index out of bounds (src/canvas.rs:21)");
+    if (!c->rgb) return set_err(RTC_ERR_INVALID, "canvas was rendered with want_f64 = 0");
+    std::memcpy(rgb3, c->rgb + 3 * (x + y * c->width), 24);
+    return RTC_OK;
+}
+int rtc_canvas_set_pixel(rtc_canvas* c, uint64_t x, uint64_t y, const double* rgb3) {
+    if (!c || !rgb3) return set_err(RTC_ERR_INVALID, "null argument");
+    if (x >= c->width || y >= c->height) return set_err(RTC_ERR_PANIC, "index out of bounds (src/canvas.rs:25)");
+    const size_t i = x + y * c->width;
+    if (c->rgb) std::memcpy(c->rgb + 3 * i, rgb3, 24);
+    for (int k = 0; k < 3; k++) c->rgba8[4 * i + k] = quantise_channel(rgb3[k]);
+    c->rgba8[4 * i + 3] = 255;
+    return RTC_OK;
+}
+const double* rtc_canvas_pixels_f64(const rtc_canvas* c) { return c ? c->rgb : nullptr; }
+const uint8_t* rtc_canvas_pixels_rgba8(const rtc_canvas* c) { return c ? c->rgba8 : nullptr; }
+char* rtc_canvas_to_ppm(const rtc_canvas* c, uint64_t* len) {
+    if (!c || !len) {
+        g_err = "null argument";
+        return nullptr;
+    }
+    std::string s = ppm_from_rgba8(c->rgba8, c->width, c->height);
+    char* out = (char*)std::malloc(s.size() + 1);
+    std::memcpy(out, s.data(), s.size());
+    out[s.size()] = 0;
+    *len = s.size();
+    return out;
+}
+// canvas.rs:28-58 for a caller-owned RGBA8 frame (e.g. the gathered multi-GPU frame)
+char* rtc_ppm_from_rgba8(const uint8_t* rgba8, uint64_t width, uint64_t height, uint64_t* len) {
+    if (!rgba8 || !len) {
+        g_err = "null argument";
+        return nullptr;
+    }
+    std::string s = ppm_from_rgba8(rgba8, width, height);
+    char* out = (char*)std::malloc(s.size() + 1);
+    std::memcpy(out, s.data(), s.size());
+    out[s.size()] = 0;
+    *len = s.size();
+    return out;
+}
+void rtc_free(void* p) { std::free(p); }
+
+}  // extern "C"

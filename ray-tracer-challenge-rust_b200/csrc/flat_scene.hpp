@@ -1,0 +1,25 @@
+// flat_scene.hpp — the flattened World as host vectors (output of flatten.hpp, input of the device upload).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "device_scene.h"
+
+namespace rtc {
+
+struct FlatScene {
+    std::vector<DProgramNode> program;
+    std::vector<DXform> xforms;
+    std::vector<DPrim> prims;
+    std::vector<DGate> gates;
+    std::vector<DMesh> meshes;
+    std::vector<DBvhNode> bvh;
+    std::vector<DTri> tris;
+    std::vector<DTriAttr> tri_attr;
+    std::vector<DMaterial> materials;
+    double light_pos[3] = {0, 0, 0}, light_int[3] = {0, 0, 0};
+    uint64_t leaf_count = 0;
+    int bvh_max_depth = 0;
+};
+
+}  // namespace rtc

@@ -1,0 +1,310 @@
+// flatten.hpp — host side of rtc_scene_create: World (as an rtc_scene_desc pre-order walk) -> flat device tables.
+//
+//   * validates the description (indices, affine matrices, identity group transforms);
+//   * computes every Group's gate box exactly as Bounds::new does per ray in the reference (bounds.rs:11-151,
+//     shape.rs:401) — origin-seeded, 8 transformed corners per child, f64::min/max folds — once per scene;
+//   * flattens the tree in DFS order into the GATE / PRIM / MESH program of device_scene.h, numbering leaves in the
+//     order World::intersect would push them (the tie-break order of the reference's stable sorts);
+//   * turns each run of sibling triangles that share one transform into a MESH with a padded object-space BVH
+//     (bvh.hpp) and precomputes each triangle's world normal (shape.rs:509-518 is point-independent).
+//
+// Compiled with -ffp-contract=off: gate boxes and triangle normals reach pixels.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rtc.h"
+#include "bvh.hpp"
+#include "device_scene.h"
+#include "flat_scene.hpp"
+#include "host_math.hpp"
+
+namespace rtc {
+
+struct FlattenError {
+    int code;
+    std::string message;
+};
+
+namespace detail {
+
+struct XKey {
+    unsigned char b[96];
+    bool operator<(const XKey& o) const { return std::memcmp(b, o.b, sizeof(b)) < 0; }
+};
+
+struct Box4 {
+    Vec4 min, max;
+};
+
+class Flattener {
+  public:
+    Flattener(const rtc_scene_desc& d, FlatScene& out) : d_(d), out_(out) {}
+
+    void run() {
+        check(d_.shape_count == 0 || d_.shapes, "shapes is NULL");
+        check(d_.transform_count == 0 || d_.transforms, "transforms is NULL");
+        check(d_.material_count == 0 || d_.materials, "materials is NULL");
+        check(d_.triangle_count == 0 || d_.triangles, "triangles is NULL");
+        // subtree extents of the pre-order walk
+        end_.assign(d_.shape_count, 0);
+        uint32_t pos = 0;
+        for (uint32_t r = 0; r < d_.root_count; r++) pos = scan(pos, 0);
+        check(pos == d_.shape_count, "shape_count does not match the pre-order walk of root_count objects");
+        for (uint32_t i = 0; i < d_.transform_count; i++) check_affine(d_.transforms[i]);
+        for (uint32_t i = 0; i < d_.material_count; i++) out_.materials.push_back(material(d_.materials[i]));
+        for (int k = 0; k < 3; k++) {
+            out_.light_pos[k] = d_.light_position[k];
+            out_.light_int[k] = d_.light_intensity[k];
+        }
+        emit_children(0, d_.shape_count);  // World.objects in order (world.rs:46-50)
+        out_.leaf_count = next_leaf_;
+    }
+
+  private:
+    const rtc_scene_desc& d_;
+    FlatScene& out_;
+    std::vector<uint32_t> end_;  // end_[i] = index just past shape i's subtree
+    std::map<XKey, int32_t> xform_ids_;
+    uint32_t next_leaf_ = 0;
+
+    [[noreturn]] static void fail(int code, const std::string& m) { throw FlattenError{code, m}; }
+    static void check(bool c, const char* m) {
+        if (!c) fail(RTC_ERR_INVALID, m);
+    }
+
+    uint32_t scan(uint32_t i, int depth) {
+        check(i < d_.shape_count, "pre-order walk runs past shape_count");
+        check(depth < 64, "group nesting deeper than 64");
+        const rtc_shape_desc& s = d_.shapes[i];
+        check(s.kind >= RTC_SPHERE && s.kind <= RTC_TRIANGLE, "unknown shape kind");
+        check(s.transform >= 0 && (uint32_t)s.transform < d_.transform_count, "transform index out of range");
+        uint32_t next = i + 1;
+        if (s.kind == RTC_GROUP) {
+            check(s.child_count >= 0, "negative child_count");
+            for (int32_t c = 0; c < s.child_count; c++) next = scan(next, depth + 1);
+        } else {
+            check(s.material >= 0 && (uint32_t)s.material < d_.material_count, "material index out of range");
+            if (s.kind == RTC_TRIANGLE)
+                check(s.triangle >= 0 && (uint32_t)s.triangle < d_.triangle_count, "triangle index out of range");
+        }
+        end_[i] = next;
+        return next;
+    }
+
+    static bool is_pm_zero(double v) { return v == 0.0; }
+    void check_affine(const rtc_transform_desc& t) {
+        const double* a = t.transform;
+        const double* b = t.inverse;
+        bool ok = is_pm_zero(a[12]) && is_pm_zero(a[13]) && is_pm_zero(a[14]) && a[15] == 1.0 && is_pm_zero(b[12]) &&
+                  is_pm_zero(b[13]) && is_pm_zero(b[14]) && b[15] == 1.0;
+        if (!ok) fail(RTC_ERR_UNSUPPORTED, "non-affine shape transform (bottom row must be 0 0 0 1)");
+    }
+
+    DMaterial material(const rtc_material& m) {
+        DMaterial o;
+        std::memset(&o, 0, sizeof(o));
+        for (int k = 0; k < 3; k++) {
+            o.color[k] = m.color[k];
+            o.pa[k] = m.pattern_a[k];
+            o.pb[k] = m.pattern_b[k];
+        }
+        o.ambient = m.ambient; o.diffuse = m.diffuse; o.specular = m.specular; o.shininess = m.shininess;
+        o.reflective = m.reflective; o.transparency = m.transparency; o.refractive_index = m.refractive_index;
+        check(m.pattern_kind >= RTC_PATTERN_NONE && m.pattern_kind <= RTC_PATTERN_TEST, "unknown pattern kind");
+        o.pattern_kind = m.pattern_kind;
+        if (m.pattern_kind >= 0) {
+            const double* b = m.pattern_inverse;
+            if (!(is_pm_zero(b[12]) && is_pm_zero(b[13]) && is_pm_zero(b[14]) && b[15] == 1.0))
+                fail(RTC_ERR_UNSUPPORTED, "non-affine pattern transform");
+            std::memcpy(o.pinv, b, sizeof(double) * 12);
+        } else {
+            Mat4 id = Mat4::identity();
+            std::memcpy(o.pinv, id.m, sizeof(double) * 12);
+        }
+        return o;
+    }
+
+    int32_t xform_id(int32_t transform_index) {
+        XKey k;
+        std::memcpy(k.b, d_.transforms[transform_index].inverse, sizeof(k.b));
+        auto it = xform_ids_.find(k);
+        if (it != xform_ids_.end()) return it->second;
+        DXform x;
+        std::memcpy(x.m, d_.transforms[transform_index].inverse, sizeof(x.m));
+        int32_t id = (int32_t)out_.xforms.size();
+        out_.xforms.push_back(x);
+        xform_ids_.emplace(k, id);
+        return id;
+    }
+
+    // ---- bounds.rs:11-151 -------------------------------------------------------------------------------------------
+    static void add(Box4& b, const Vec4& p) {  // bounds.rs:142-151
+        if (!(p.w == 1.0)) fail(RTC_ERR_PANIC, "assertion failed: point.is_point() (src/bounds.rs:143) — a group holds a "
+                                               "shape with an unbounded box (uncapped cylinder/cone)");
+        b.min.x = std::fmin(b.min.x, p.x); b.min.y = std::fmin(b.min.y, p.y); b.min.z = std::fmin(b.min.z, p.z);
+        b.max.x = std::fmax(b.max.x, p.x); b.max.y = std::fmax(b.max.y, p.y); b.max.z = std::fmax(b.max.z, p.z);
+    }
+    Box4 bounds_of(uint32_t i) {
+        const rtc_shape_desc& s = d_.shapes[i];
+        const double inf = std::numeric_limits<double>::infinity();
+        switch (s.kind) {
+            case RTC_SPHERE:
+            case RTC_CUBE: return {point(-1., -1., -1.), point(1., 1., 1.)};
+            case RTC_PLANE: return {point(-1., -1., 0.), point(1., 1., 0.)};  // sic, bounds.rs:21-24
+            case RTC_CYLINDER:
+            case RTC_CONE:
+                if (s.capped) return {point(-1., s.minimum, -1.), point(1., s.maximum, 1.)};
+                return {point(-1., -inf, -1.), point(1., inf, 1.)};
+            case RTC_TRIANGLE: {  // bounds.rs:126-137: seeded with the origin
+                const rtc_triangle_desc& t = d_.triangles[s.triangle];
+                Box4 b{point(0., 0., 0.), point(0., 0., 0.)};
+                add(b, point(t.p1[0], t.p1[1], t.p1[2]));
+                add(b, point(t.p2[0], t.p2[1], t.p2[2]));
+                add(b, point(t.p3[0], t.p3[1], t.p3[2]));
+                return b;
+            }
+            default: {  // group, bounds.rs:50-125
+                Box4 out{point(0., 0., 0.), point(0., 0., 0.)};
+                for (uint32_t c = i + 1; c < end_[i]; c = end_[c]) {
+                    Box4 pb = bounds_of(c);
+                    Mat4 tr = Mat4::from(d_.transforms[d_.shapes[c].transform].transform);
+                    add(out, mul(tr, point(pb.min.x, pb.min.y, pb.min.z)));
+                    add(out, mul(tr, point(pb.min.x, pb.min.y, pb.max.z)));
+                    add(out, mul(tr, point(pb.min.x, pb.max.y, pb.min.z)));
+                    add(out, mul(tr, point(pb.min.x, pb.max.y, pb.max.z)));
+                    add(out, mul(tr, point(pb.max.x, pb.min.y, pb.min.z)));
+                    add(out, mul(tr, point(pb.max.x, pb.min.y, pb.max.z)));
+                    add(out, mul(tr, point(pb.max.x, pb.max.y, pb.min.z)));
+                    add(out, mul(tr, pb.max));
+                }
+                return out;
+            }
+        }
+    }
+
+    // ---- emission ---------------------------------------------------------------------------------------------------
+    bool same_inverse(uint32_t a, uint32_t b) const {
+        return std::memcmp(d_.transforms[d_.shapes[a].transform].inverse, d_.transforms[d_.shapes[b].transform].inverse,
+                           sizeof(double) * 16) == 0;
+    }
+
+    void emit_children(uint32_t begin, uint32_t end) {
+        uint32_t i = begin;
+        while (i < end) {
+            const rtc_shape_desc& s = d_.shapes[i];
+            if (s.kind == RTC_GROUP) {
+                emit_group(i);
+                i = end_[i];
+            } else if (s.kind == RTC_TRIANGLE) {
+                uint32_t j = i + 1;
+                while (j < end && d_.shapes[j].kind == RTC_TRIANGLE && same_inverse(i, j)) j++;
+                emit_mesh(i, j);
+                i = j;
+            } else {
+                DPrim p;
+                std::memset(&p, 0, sizeof(p));
+                p.kind = s.kind;
+                p.material = s.material;
+                p.xform = xform_id(s.transform);
+                p.capped = s.capped ? 1 : 0;
+                p.minimum = s.minimum;
+                p.maximum = s.maximum;
+                p.leaf = (int32_t)next_leaf_++;
+                out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, 0});
+                out_.prims.push_back(p);
+                i++;
+            }
+        }
+    }
+
+    void emit_group(uint32_t i) {
+        // the reference intersects a group in the space of its own transform, which set_transform never changes from
+        // the identity (shape.rs:203-217); anything else has no reference behaviour to match
+        const double* t = d_.transforms[d_.shapes[i].transform].transform;
+        Mat4 id = Mat4::identity();
+        for (int k = 0; k < 16; k++)
+            if (!(t[k] == id.m[k])) fail(RTC_ERR_UNSUPPORTED, "a group's own transform must be the identity (shape.rs:203-217)");
+        Box4 b = bounds_of(i);
+        DGate g;
+        g.lo[0] = b.min.x; g.lo[1] = b.min.y; g.lo[2] = b.min.z;
+        g.hi[0] = b.max.x; g.hi[1] = b.max.y; g.hi[2] = b.max.z;
+        size_t at = out_.program.size();
+        out_.program.push_back(DProgramNode{NODE_GATE, (int32_t)out_.gates.size(), 0, 0});
+        out_.gates.push_back(g);
+        emit_children(i + 1, end_[i]);
+        out_.program[at].skip = (int32_t)out_.program.size();
+    }
+
+    void emit_mesh(uint32_t begin, uint32_t end) {
+        const int32_t xf = xform_id(d_.shapes[begin].transform);
+        const rtc_transform_desc& td = d_.transforms[d_.shapes[begin].transform];
+        const Mat4 inv_t = transpose(Mat4::from(td.inverse));  // shape.rs:216
+        const uint32_t n = end - begin;
+        std::vector<BvhTri> bt(n);
+        for (uint32_t k = 0; k < n; k++) {
+            const rtc_triangle_desc& t = d_.triangles[d_.shapes[begin + k].triangle];
+            for (int a = 0; a < 3; a++) {
+                bt[k].p[0][a] = t.p1[a];
+                bt[k].p[1][a] = t.p2[a];
+                bt[k].p[2][a] = t.p3[a];
+            }
+        }
+        DMesh m;
+        m.xform = xf;
+        m.tri_base = (int32_t)out_.tris.size();
+        m.tri_count = (int32_t)n;
+        std::vector<uint32_t> order;
+        int depth = 0;
+        m.root = build_bvh(bt, out_.bvh, m.tri_base, order, &depth);
+        if (depth > out_.bvh_max_depth) out_.bvh_max_depth = depth;
+        const uint32_t leaf0 = next_leaf_;
+        next_leaf_ += n;
+        for (uint32_t slot = 0; slot < n; slot++) {
+            const uint32_t k = order[slot];
+            const rtc_shape_desc& s = d_.shapes[begin + k];
+            const rtc_triangle_desc& t = d_.triangles[s.triangle];
+            DTri dt;
+            std::memset(&dt, 0, sizeof(dt));
+            for (int a = 0; a < 3; a++) {
+                dt.p1[a] = t.p1[a];
+                dt.e1[a] = t.e1[a];
+                dt.e2[a] = t.e2[a];
+            }
+            dt.leaf = (int32_t)(leaf0 + k);
+            out_.tris.push_back(dt);
+            // normal_at for a triangle (shape.rs:509-518): invT * normal, w = 0, normalize, w = 0, normalize
+            Vec4 wn = mul(inv_t, vector(t.normal[0], t.normal[1], t.normal[2]));
+            wn.w = 0.;
+            wn = normalize(wn);
+            wn.w = 0.;
+            wn = normalize(wn);
+            DTriAttr ta;
+            ta.normal[0] = wn.x; ta.normal[1] = wn.y; ta.normal[2] = wn.z;
+            ta.material = s.material;
+            ta.xform = xf;
+            out_.tri_attr.push_back(ta);
+        }
+        out_.program.push_back(DProgramNode{NODE_MESH, (int32_t)out_.meshes.size(), 0, 0});
+        out_.meshes.push_back(m);
+    }
+};
+
+}  // namespace detail
+
+// Returns RTC_OK or a negative code with *err set.
+inline int flatten_scene(const rtc_scene_desc& desc, FlatScene& out, std::string* err) {
+    try {
+        detail::Flattener f(desc, out);
+        f.run();
+        return RTC_OK;
+    } catch (const FlattenError& e) {
+        if (err) *err = e.message;
+        return e.code;
+    }
+}
+
+}  // namespace rtc

@@ -1,0 +1,393 @@
+// render.cu — the CUDA side of librtc_b200.so (sm_100a, compiled with -fmad=false; see rt_core.cuh for why).
+//
+// Camera::render's `for y { for x { ... } }` (camera.rs:70-76) is ONE kernel launch: a persistent grid (a fixed number
+// of CTAs per SM) whose warps pull 8x4-pixel tiles from an atomic work queue, run World::color_at per lane, quantise
+// as canvas.rs:61-63 does and store one uchar4 (and optionally the f64 Canvas colour) per pixel.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "flat_scene.hpp"
+#include "render.cuh"
+#include "rt_core.cuh"
+
+namespace rtc {
+
+namespace {
+
+constexpr int kBlockThreads = 128;
+constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
+constexpr int kBlocksPerSm = 4;
+
+struct DQueue {
+    unsigned long long primary, shadow, reflect, refract;
+    unsigned int next_tile;
+    unsigned int pad;
+};
+
+__global__ void __launch_bounds__(kBlockThreads) render_kernel(const __grid_constant__ DScene s,
+                                                               const __grid_constant__ DCamera cam,
+                                                               const __grid_constant__ DRows rows,
+                                                               uint32_t* __restrict__ out8, double* __restrict__ out64,
+                                                               DQueue* __restrict__ q) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t tiles_x = (cam.hsize + kTileW - 1) / kTileW;
+    const uint32_t tiles_y = (rows.local_rows + kTileH - 1) / kTileH;
+    const uint32_t ntiles = tiles_x * tiles_y;
+    RayCounters rc;
+    uint32_t primary = 0;
+    for (;;) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(&q->next_tile, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
+        const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+        const uint32_t px = tx * kTileW + (lane & (kTileW - 1));
+        const uint32_t lrow = ty * kTileH + (lane / kTileW);  // row inside this call's compact output
+        if (px < cam.hsize && lrow < rows.local_rows) {
+            const uint32_t band = lrow / rows.band_rows;
+            const uint32_t py = (rows.band_first + band * rows.band_stride) * rows.band_rows + (lrow % rows.band_rows);
+            const Ray ray = ray_for_pixel(cam, px, py);
+            primary++;
+            const V3 c = color_at(s, ray, rc);
+            const size_t o = (size_t)lrow * cam.hsize + px;
+            if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
+            if (out64) {
+                out64[3 * o + 0] = c.x;
+                out64[3 * o + 1] = c.y;
+                out64[3 * o + 2] = c.z;
+            }
+        }
+    }
+    // ray counters: warp reduce, one atomic per warp and counter
+    unsigned long long v[4] = {primary, rc.shadow, rc.reflect, rc.refract};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned x = (unsigned)v[k];
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        v[k] = x;
+    }
+    if (lane == 0) {
+        if (v[0]) atomicAdd(&q->primary, v[0]);
+        if (v[1]) atomicAdd(&q->shadow, v[1]);
+        if (v[2]) atomicAdd(&q->reflect, v[2]);
+        if (v[3]) atomicAdd(&q->refract, v[3]);
+    }
+}
+
+__global__ void __launch_bounds__(kBlockThreads) color_at_kernel(const __grid_constant__ DScene s,
+                                                                 const double* __restrict__ rays, uint64_t n,
+                                                                 double* __restrict__ rgb) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r{v3(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]), v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};
+    RayCounters rc;
+    V3 c = color_at(s, r, rc);
+    rgb[3 * i + 0] = c.x;
+    rgb[3 * i + 1] = c.y;
+    rgb[3 * i + 2] = c.z;
+}
+
+// FP64 issue-rate probes: 8 independent dependency chains per thread
+template <bool kFma>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double b, double c) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (kFma) a[k] = __fma_rn(a[k], b, c);
+            else a[k] = __dadd_rn(__dmul_rn(a[k], b), c);
+        }
+    }
+    double sum = 0.;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += a[k];
+    if (sum == 123.456) out[0] = sum;  // keep the chains alive
+}
+
+std::string cuda_err(const char* what, cudaError_t e) {
+    return std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+}
+#define RTC_CUDA(call)                                         \
+    do {                                                       \
+        cudaError_t e_ = (call);                               \
+        if (e_ != cudaSuccess) {                               \
+            if (err) *err = cuda_err(#call, e_);               \
+            return -3;                                         \
+        }                                                      \
+    } while (0)
+
+template <class T>
+size_t slab_bytes(const std::vector<T>& v) {
+    return (v.size() * sizeof(T) + 255) & ~size_t(255);
+}
+
+}  // namespace
+
+struct DeviceScene {
+    int device = 0;
+    int sm_count = 0;
+    void* slab = nullptr;
+    size_t slab_size = 0;
+    DScene view{};
+    DQueue* queue = nullptr;
+    // grow-only output scratch for render_host
+    void* out8 = nullptr;
+    size_t out8_size = 0;
+    void* out64 = nullptr;
+    size_t out64_size = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+};
+
+int cuda_device_count(std::string* err) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        if (err) *err = cuda_err("cudaGetDeviceCount", e);
+        return 0;
+    }
+    return n;
+}
+
+int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::string* err) {
+    int ndev = 0;
+    RTC_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        if (err) *err = "no such CUDA device";
+        return -3;
+    }
+    RTC_CUDA(cudaSetDevice(device));
+    DeviceScene* s = new DeviceScene();
+    s->device = device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete s;
+        if (err) *err = cuda_err("cudaGetDeviceProperties", e);
+        return -3;
+    }
+    s->sm_count = prop.multiProcessorCount;
+    const size_t sizes[9] = {slab_bytes(f.program), slab_bytes(f.xforms),   slab_bytes(f.prims),
+                             slab_bytes(f.gates),   slab_bytes(f.meshes),   slab_bytes(f.bvh),
+                             slab_bytes(f.tris),    slab_bytes(f.tri_attr), slab_bytes(f.materials)};
+    size_t total = 256;
+    for (size_t b : sizes) total += b;
+    std::vector<unsigned char> host(total, 0);
+    size_t off[9], at = 0;
+    const void* src[9] = {f.program.data(), f.xforms.data(),   f.prims.data(),    f.gates.data(), f.meshes.data(),
+                          f.bvh.data(),     f.tris.data(),     f.tri_attr.data(), f.materials.data()};
+    const size_t raw[9] = {f.program.size() * sizeof(DProgramNode), f.xforms.size() * sizeof(DXform),
+                           f.prims.size() * sizeof(DPrim),          f.gates.size() * sizeof(DGate),
+                           f.meshes.size() * sizeof(DMesh),         f.bvh.size() * sizeof(DBvhNode),
+                           f.tris.size() * sizeof(DTri),            f.tri_attr.size() * sizeof(DTriAttr),
+                           f.materials.size() * sizeof(DMaterial)};
+    for (int k = 0; k < 9; k++) {
+        off[k] = at;
+        if (raw[k]) std::memcpy(host.data() + at, src[k], raw[k]);
+        at += sizes[k];
+    }
+    auto cleanup = [&]() {
+        if (s->slab) cudaFree(s->slab);
+        if (s->queue) cudaFree(s->queue);
+        if (s->stream) cudaStreamDestroy(s->stream);
+        if (s->ev0) cudaEventDestroy(s->ev0);
+        if (s->ev1) cudaEventDestroy(s->ev1);
+        delete s;
+    };
+#define RTC_CUDA_C(call)                                       \
+    do {                                                       \
+        cudaError_t e_ = (call);                               \
+        if (e_ != cudaSuccess) {                               \
+            if (err) *err = cuda_err(#call, e_);               \
+            cleanup();                                         \
+            return -3;                                         \
+        }                                                      \
+    } while (0)
+    RTC_CUDA_C(cudaMalloc(&s->slab, total));
+    s->slab_size = total;
+    RTC_CUDA_C(cudaMemcpy(s->slab, host.data(), total, cudaMemcpyHostToDevice));
+    RTC_CUDA_C(cudaMalloc((void**)&s->queue, sizeof(DQueue)));
+    RTC_CUDA_C(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    RTC_CUDA_C(cudaEventCreate(&s->ev0));
+    RTC_CUDA_C(cudaEventCreate(&s->ev1));
+#undef RTC_CUDA_C
+    unsigned char* base = (unsigned char*)s->slab;
+    s->view.program = (const DProgramNode*)(base + off[0]);
+    s->view.xforms = (const DXform*)(base + off[1]);
+    s->view.prims = (const DPrim*)(base + off[2]);
+    s->view.gates = (const DGate*)(base + off[3]);
+    s->view.meshes = (const DMesh*)(base + off[4]);
+    s->view.bvh = (const DBvhNode*)(base + off[5]);
+    s->view.tris = (const DTri*)(base + off[6]);
+    s->view.tri_attr = (const DTriAttr*)(base + off[7]);
+    s->view.materials = (const DMaterial*)(base + off[8]);
+    s->view.program_count = (int32_t)f.program.size();
+    for (int k = 0; k < 3; k++) {
+        s->view.light_pos[k] = f.light_pos[k];
+        s->view.light_int[k] = f.light_int[k];
+    }
+    *out = s;
+    return 0;
+}
+
+void device_scene_destroy(DeviceScene* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->out8) cudaFree(s->out8);
+    if (s->out64) cudaFree(s->out64);
+    if (s->slab) cudaFree(s->slab);
+    if (s->queue) cudaFree(s->queue);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+uint64_t device_scene_bytes(const DeviceScene* s) { return s->slab_size; }
+int device_scene_device(const DeviceScene* s) { return s->device; }
+
+static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d8, void* d64, cudaStream_t st,
+                  LaunchStats* stats, std::string* err) {
+    if (rows.local_rows == 0 || cam.hsize == 0) {
+        if (stats) *stats = LaunchStats{};
+        return 0;
+    }
+    RTC_CUDA(cudaMemsetAsync(s->queue, 0, sizeof(DQueue), st));
+    const uint64_t tiles = (uint64_t)((cam.hsize + kTileW - 1) / kTileW) * ((rows.local_rows + kTileH - 1) / kTileH);
+    const uint64_t warps_per_block = kBlockThreads / 32;
+    uint64_t blocks = (tiles + warps_per_block - 1) / warps_per_block;
+    const uint64_t cap = (uint64_t)s->sm_count * kBlocksPerSm;
+    if (blocks > cap) blocks = cap;
+    if (stats) RTC_CUDA(cudaEventRecord(s->ev0, st));
+    render_kernel<<<(unsigned)blocks, kBlockThreads, 0, st>>>(s->view, cam, rows, (uint32_t*)d8, (double*)d64, s->queue);
+    RTC_CUDA(cudaGetLastError());
+    if (stats) {
+        RTC_CUDA(cudaEventRecord(s->ev1, st));
+        DQueue h;
+        RTC_CUDA(cudaMemcpyAsync(&h, s->queue, sizeof(h), cudaMemcpyDeviceToHost, st));
+        RTC_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        RTC_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        stats->primary = h.primary;
+        stats->shadow = h.shadow;
+        stats->reflect = h.reflect;
+        stats->refract = h.refract;
+        stats->launches = 1;
+        stats->device_ms = ms;
+    }
+    return 0;
+}
+
+int render_device(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d_rgba8, void* d_rgb_f64, void* stream,
+                  LaunchStats* stats, std::string* err) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    RTC_CUDA(cudaSetDevice(s->device));
+    return launch(s, cam, rows, d_rgba8, d_rgb_f64, (cudaStream_t)stream, stats, err);
+}
+
+int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* rgba8, double* rgb_f64,
+                LaunchStats* stats, std::string* err) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    RTC_CUDA(cudaSetDevice(s->device));
+    const size_t px = (size_t)rows.local_rows * cam.hsize;
+    if (rgba8 && s->out8_size < px * 4) {
+        if (s->out8) cudaFree(s->out8);
+        s->out8 = nullptr;
+        s->out8_size = 0;
+        RTC_CUDA(cudaMalloc(&s->out8, px * 4));
+        s->out8_size = px * 4;
+    }
+    if (rgb_f64 && s->out64_size < px * 24) {
+        if (s->out64) cudaFree(s->out64);
+        s->out64 = nullptr;
+        s->out64_size = 0;
+        RTC_CUDA(cudaMalloc(&s->out64, px * 24));
+        s->out64_size = px * 24;
+    }
+    int rc = launch(s, cam, rows, rgba8 ? s->out8 : nullptr, rgb_f64 ? s->out64 : nullptr, s->stream, stats, err);
+    if (rc) return rc;
+    if (rgba8 && px) RTC_CUDA(cudaMemcpyAsync(rgba8, s->out8, px * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (rgb_f64 && px) RTC_CUDA(cudaMemcpyAsync(rgb_f64, s->out64, px * 24, cudaMemcpyDeviceToHost, s->stream));
+    RTC_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int color_at_host(DeviceScene* s, const double* rays, uint64_t n, double* rgb, std::string* err) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (n == 0) return 0;
+    RTC_CUDA(cudaSetDevice(s->device));
+    double *d_rays = nullptr, *d_rgb = nullptr;
+    RTC_CUDA(cudaMalloc((void**)&d_rays, n * 48));
+    cudaError_t e = cudaMalloc((void**)&d_rgb, n * 24);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * 48, cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) {
+        color_at_kernel<<<(unsigned)((n + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, s->stream>>>(
+            s->view, d_rays, n, d_rgb);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rgb, d_rgb, n * 24, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_rays);
+    if (d_rgb) cudaFree(d_rgb);
+    if (e != cudaSuccess) {
+        if (err) *err = cuda_err("rtc_color_at", e);
+        return -3;
+    }
+    return 0;
+}
+
+int measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops, std::string* err) {
+    RTC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RTC_CUDA(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    RTC_CUDA(cudaMalloc((void**)&d, 64));
+    cudaEvent_t a, b;
+    RTC_CUDA(cudaEventCreate(&a));
+    RTC_CUDA(cudaEventCreate(&b));
+    const int iters = 4096, threads = 256, blocks = prop.multiProcessorCount * 8;
+    const double flops = 2.0 * 8.0 * iters * (double)threads * blocks;  // mul + add (or one FMA = 2) per chain step
+    double best[2] = {0., 0.};
+    for (int mode = 0; mode < 2; mode++)
+        for (int rep = 0; rep < 5; rep++) {
+            cudaEventRecord(a);
+            if (mode == 0) fp64_peak_kernel<false><<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+            else fp64_peak_kernel<true><<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+            cudaEventRecord(b);
+            cudaError_t e = cudaEventSynchronize(b);
+            if (e != cudaSuccess) {
+                if (err) *err = cuda_err("fp64 probe", e);
+                cudaFree(d);
+                return -3;
+            }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, a, b);
+            if (rep > 0 && ms > 0.f) best[mode] = std::max(best[mode], flops / (ms * 1e-3) / 1e9);
+        }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    if (nofma_gflops) *nofma_gflops = best[0];
+    if (fma_gflops) *fma_gflops = best[1];
+    return 0;
+}
+
+void* pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // namespace rtc

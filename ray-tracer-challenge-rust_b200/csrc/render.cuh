@@ -1,0 +1,45 @@
+// render.cuh — host-callable interface of the CUDA translation unit (render.cu).  Internal to librtc_b200.so; the
+// public boundary is include/rtc.h.
+#pragma once
+#include <cstdint>
+#include <string>
+
+#include "device_scene.h"
+
+namespace rtc {
+
+struct FlatScene;
+
+// Device-resident copy of a FlatScene (one cudaMalloc slab) plus per-scene scratch (work-queue counter, ray counters).
+struct DeviceScene;
+
+struct LaunchStats {
+    unsigned long long primary = 0, shadow = 0, reflect = 0, refract = 0;
+    unsigned long long launches = 0;
+    double device_ms = 0.;
+};
+
+int cuda_device_count(std::string* err);
+int device_scene_create(const FlatScene& flat, int device, DeviceScene** out, std::string* err);
+void device_scene_destroy(DeviceScene* s);
+uint64_t device_scene_bytes(const DeviceScene* s);
+int device_scene_device(const DeviceScene* s);
+
+// Camera::render for the rows selected by `rows` into device buffers (either may be null), asynchronously on `stream`.
+// With `stats` non-null the call brackets the kernel with CUDA events, synchronises the stream and fills *stats.
+int render_device(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d_rgba8, void* d_rgb_f64, void* stream,
+                  LaunchStats* stats, std::string* err);
+// Same with host outputs (pinned or pageable), including the device->host copies.
+int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* rgba8, double* rgb_f64,
+                LaunchStats* stats, std::string* err);
+// World::color_at for explicit rays (host in, host out).
+int color_at_host(DeviceScene* s, const double* rays, uint64_t n, double* rgb, std::string* err);
+
+int measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops, std::string* err);
+
+// Pinned host memory for frame buffers (so device->host copies run at PCIe speed); falls back to nothing — returns null
+// on failure and the caller reports RTC_ERR_CUDA.
+void* pinned_alloc(size_t bytes);
+void pinned_free(void* p);
+
+}  // namespace rtc

@@ -1,0 +1,131 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on the same worlds (-m gpu)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+# BASELINE.json's correctness bar for PPMs: every channel within +-1/255, >= 99.9 % of pixels exact.  The f64 frame is
+# additionally required to be bit-identical except where the specular pow() (CUDA <= 2 ulp vs glibc < 1 ulp,
+# material.rs:68) contributes, where a relative 1e-12 is allowed.
+PPM_MAX_DIFF = 1
+PPM_MIN_EXACT = 0.999
+F64_RTOL = 1e-12
+
+SMALL = [("hexagon", 400, 200), ("table", 320, 180), ("teapot", 160, 90), ("cow", 160, 80), ("cow_teddy", 160, 90),
+         ("pumpkin", 160, 90)]
+FULL = [("hexagon", 1920, 960), ("table", 1920, 1080), ("teapot", 1920, 1080), ("cow_teddy", 3840, 2160),
+        ("pumpkin", 7680, 4320)]
+
+
+def _check(ref_rgb, got_rgb, ref_rgba, got_rgba):
+    exact, md = helpers.compare_rgba(ref_rgba, got_rgba)
+    assert md <= PPM_MAX_DIFF, f"channel differs by {md}/255"
+    assert exact >= PPM_MIN_EXACT, f"only {exact:.5f} of pixels exact"
+    if got_rgb is not None:
+        np.testing.assert_allclose(got_rgb, ref_rgb, rtol=F64_RTOL, atol=1e-15)
+        bit_equal = (ref_rgb.view(np.uint64) == got_rgb.view(np.uint64)).all(axis=1).mean()
+        assert bit_equal >= 0.95, f"only {bit_equal:.4f} of f64 pixels bit-identical"
+    return exact, md
+
+
+@pytest.mark.parametrize("name,w,h", SMALL)
+def test_full_frame_matches_oracle(rtc, oracle, name, w, h):
+    world, cam = rtc.build_scene(name, w, h)
+    st = rtc.Stats()
+    canvas = cam.render(world, want_f64=True, stats=st)
+    ow, oc = helpers.scenes.build(oracle, name, w, h)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    got = canvas.pixels_f64().reshape(-1, 3)
+    _check(ref, got, oracle.quantise_rgba8(ref), canvas.pixels_rgba8())
+    # ray accounting is exact
+    assert (st.primary_rays, st.shadow_rays, st.reflect_rays, st.refract_rays) == \
+        (cnt.primary, cnt.shadow, cnt.reflect, cnt.refract)
+    # and the PPM text is the reference encoder's, byte for byte, when the quantised frame is identical
+    if np.array_equal(oracle.quantise_rgba8(ref).reshape(-1), canvas.pixels_rgba8().reshape(-1)):
+        assert canvas.to_ppm() == oracle.ppm(ref, w, h)
+
+
+@pytest.mark.parametrize("name,w,h", FULL)
+def test_full_resolution_subset_matches_oracle(rtc, oracle, name, w, h):
+    """BASELINE resolutions: the GPU renders the whole frame; the oracle renders the deterministic 1/256 pixel subset
+    of the same camera, compared pixel for pixel."""
+    world, cam = rtc.build_scene(name, w, h)
+    rgba = np.empty((h, w, 4), dtype=np.uint8)
+    st = rtc.Stats()
+    cam.render_into(world, rgba8=rgba, stats=st)
+    assert st.primary_rays == w * h
+    step = 16 if w <= 3840 else 32
+    px = helpers.subset_pixels(w, h, step, step // 2)
+    ow, oc = helpers.scenes.build(oracle, name, w, h)
+    ref, _ = oracle.render(ow, oc, mode=oracle.CACHED, pixels=px)
+    got = rgba[px[:, 1], px[:, 0]]
+    _check(ref, None, oracle.quantise_rgba8(ref), got)
+
+
+def test_default_world_known_answers(rtc):
+    """camera.rs:145-155 and world.rs:212-260 through the CUDA path."""
+    import math
+    T = rtc.Transformations(rtc.api())
+    w = rtc.World.default_world()
+    c = rtc.Camera(11, 11, math.pi / 2.)
+    c.set_transform(T.view_transform((0., 0., -5.), (0., 0., 0.), (0., 1., 0.)))
+    image = c.render(w)
+    np.testing.assert_allclose(image.get_pixel(5, 5), [0.38066, 0.47583, 0.2855], atol=1e-5)
+    cols = w.color_at([[0, 0, -5, 0, 1, 0], [0, 0, -5, 0, 0, 1]])
+    np.testing.assert_allclose(cols[0], [0, 0, 0], atol=1e-5)
+    np.testing.assert_allclose(cols[1], [0.38066, 0.47583, 0.2855], atol=1e-5)
+
+
+def test_row_bands_tile_the_frame(rtc):
+    """rtc_rows: cyclic row bands rendered separately reassemble into the full frame (the multi-GPU sharding)."""
+    world, cam = rtc.build_scene("table", 200, 117)  # 117 rows: the last band is ragged
+    full = np.empty((117, 200, 4), dtype=np.uint8)
+    cam.render_into(world, rgba8=full)
+    for band_rows, stride in ((8, 3), (16, 2), (5, 4)):
+        out = np.zeros_like(full)
+        for first in range(stride):
+            rows = rtc.Rows(band_rows, first, stride)
+            n = cam.rows_count(rows)
+            part = np.empty((n, 200, 4), dtype=np.uint8)
+            cam.render_into(world, rgba8=part, rows=rows)
+            k = 0
+            for b in range(first, (117 + band_rows - 1) // band_rows, stride):
+                r0, r1 = b * band_rows, min(117, (b + 1) * band_rows)
+                out[r0:r1] = part[k:k + r1 - r0]
+                k += r1 - r0
+            assert k == n
+        assert np.array_equal(out, full)
+
+
+def test_device_output_and_torch_stream(rtc):
+    """rtc_render_device writes into torch-owned device memory on torch's current stream."""
+    import torch
+    world, cam = rtc.build_scene("hexagon", 256, 128)
+    host = np.empty((128, 256, 4), dtype=np.uint8)
+    cam.render_into(world, rgba8=host)
+    buf = torch.zeros((128, 256, 4), dtype=torch.uint8, device="cuda:0")
+    st = rtc.Stats()
+    cam.render_device(world, d_rgba8=buf.data_ptr(), stream=torch.cuda.current_stream().cuda_stream, stats=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.cpu().numpy(), host)
+    assert st.kernel_launches == 1 and st.device_ms > 0
+
+
+def test_edge_sizes(rtc, oracle):
+    """1x1, a single row, a single column, widths that are not a multiple of the 8x4 tile."""
+    for w, h in ((1, 1), (37, 1), (1, 29), (13, 7)):
+        world, cam = rtc.build_scene("table", w, h)
+        canvas = cam.render(world)
+        ow, oc = helpers.scenes.build(oracle, "table", w, h)
+        ref, _ = oracle.render(ow, oc, mode=oracle.CACHED)
+        _check(ref, canvas.pixels_f64().reshape(-1, 3), oracle.quantise_rgba8(ref), canvas.pixels_rgba8())
+
+
+def test_empty_world_is_black(rtc):
+    w = rtc.World(rtc.Light((0, 10, 0), (1, 1, 1)))
+    c = rtc.Camera(16, 8, 1.0)
+    assert not c.render(w).pixels_f64().any()
