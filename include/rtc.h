@@ -150,6 +150,13 @@ uint32_t rtc_rows_count(const rtc_camera_desc* camera, const rtc_rows* rows);
 /* World::color_at (src/world.rs:80-82) for `n` explicit rays (origin xyz, direction xyz; host pointers) -> rgb f64. */
 int rtc_color_at(const rtc_scene* scene, const double* rays, uint64_t n, double* rgb_out);
 
+/* Work tallies of one frame for the FP64 roofline: renders the rows with a counting build of the same per-ray program
+ * (nothing is stored or timed) and fills counts[rtc_tally_count()] — how many ray transforms, gate tests, leaf tests by
+ * kind, triangle tests by outcome, BVH box tests, shaded hits, pattern evaluations, pow calls, refraction set-ups,
+ * Schlick evaluations and n1/n2 walks the frame needed (order: TallyIndex in csrc/rt_core.cuh). */
+int rtc_tally_count(void);
+int rtc_render_tally(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows, uint64_t* counts);
+
 /* Self-measured FP64 issue peaks of the device (independent DADD+DMUL chains, and DFMA chains), in Gflop/s with an FMA
  * counted as 2.  Used as the FP64 roofline denominator (the path must run without FMA contraction). */
 int rtc_measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops);

@@ -110,3 +110,26 @@ class BuilderApi:
     def error(self):
         m = self.last_error()
         return m.decode("utf-8", "replace") if m else ""
+
+
+# ---- layer-1 description structs (rtc_scene_desc and friends) ---------------------------------------------------------
+class TransformDesc(C.Structure):
+    _fields_ = [("transform", C.c_double * 16), ("inverse", C.c_double * 16)]
+
+
+class TriangleDesc(C.Structure):
+    _fields_ = [("p1", C.c_double * 3), ("p2", C.c_double * 3), ("p3", C.c_double * 3), ("e1", C.c_double * 3),
+                ("e2", C.c_double * 3), ("normal", C.c_double * 3)]
+
+
+class ShapeDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("material", C.c_int32), ("transform", C.c_int32), ("capped", C.c_int32),
+                ("minimum", C.c_double), ("maximum", C.c_double), ("child_count", C.c_int32), ("triangle", C.c_int32)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("shapes", C.POINTER(ShapeDesc)), ("shape_count", C.c_uint32), ("root_count", C.c_uint32),
+                ("transforms", C.POINTER(TransformDesc)), ("transform_count", C.c_uint32),
+                ("materials", C.POINTER(Material)), ("material_count", C.c_uint32),
+                ("triangles", C.POINTER(TriangleDesc)), ("triangle_count", C.c_uint32),
+                ("light_position", C.c_double * 3), ("light_intensity", C.c_double * 3)]

@@ -62,7 +62,10 @@ def build(force=False, verbose=False):
     with open(os.path.join(BUILD, "build.log"), "w") as log:
         _run(["g++", *HOST_FLAGS, "-c", os.path.join(CSRC, "capi.cpp"), "-o", os.path.join(BUILD, "capi.o")], log)
         _run([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "render.cu"), "-o", os.path.join(BUILD, "render.o")], log)
-        _run([nvcc, "-shared", "-o", LIB, os.path.join(BUILD, "capi.o"), os.path.join(BUILD, "render.o")], log)
+        _run([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "render_tally.cu"), "-o",
+              os.path.join(BUILD, "render_tally.o")], log)
+        _run([nvcc, "-shared", "-o", LIB, os.path.join(BUILD, "capi.o"), os.path.join(BUILD, "render.o"),
+              os.path.join(BUILD, "render_tally.o")], log)
     if verbose:
         print(open(os.path.join(BUILD, "build.log")).read())
     return LIB

@@ -183,6 +183,18 @@ int rtc_color_at(const rtc_scene* scene, const double* rays, uint64_t n, double*
     return RTC_OK;
 }
 
+int rtc_tally_count(void) { return tally_count(); }
+int rtc_render_tally(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows, uint64_t* counts) {
+    if (!scene || !camera || !counts) return set_err(RTC_ERR_INVALID, "null argument");
+    DRows dr;
+    int rc = to_drows(*camera, rows, &dr);
+    if (rc != RTC_OK) return rc;
+    std::string e;
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+    if (render_tally(scene->dev, to_dcamera(*camera), dr, (unsigned long long*)counts, &e) != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+
 int rtc_measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops) {
     std::string e;
     if (measure_fp64_peak(device, nofma_gflops, fma_gflops, &e) != 0) return set_err(RTC_ERR_CUDA, e);

@@ -12,9 +12,12 @@
 
 #include "flat_scene.hpp"
 #include "render.cuh"
+#include "device_scene_impl.cuh"
 #include "rt_core.cuh"
 
 namespace rtc {
+
+using namespace core;
 
 namespace {
 
@@ -22,11 +25,6 @@ constexpr int kBlockThreads = 128;
 constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
 constexpr int kBlocksPerSm = 4;
 
-struct DQueue {
-    unsigned long long primary, shadow, reflect, refract;
-    unsigned int next_tile;
-    unsigned int pad;
-};
 
 __global__ void __launch_bounds__(kBlockThreads) render_kernel(const __grid_constant__ DScene s,
                                                                const __grid_constant__ DCamera cam,
@@ -38,6 +36,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const __grid_cons
     const uint32_t tiles_y = (rows.local_rows + kTileH - 1) / kTileH;
     const uint32_t ntiles = tiles_x * tiles_y;
     RayCounters rc;
+    Tally tl;
     uint32_t primary = 0;
     for (;;) {
         unsigned tile = 0;
@@ -52,7 +51,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const __grid_cons
             const uint32_t py = (rows.band_first + band * rows.band_stride) * rows.band_rows + (lrow % rows.band_rows);
             const Ray ray = ray_for_pixel(cam, px, py);
             primary++;
-            const V3 c = color_at(s, ray, rc);
+            const V3 c = color_at(s, ray, rc, tl);
             const size_t o = (size_t)lrow * cam.hsize + px;
             if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
             if (out64) {
@@ -85,7 +84,8 @@ __global__ void __launch_bounds__(kBlockThreads) color_at_kernel(const __grid_co
     if (i >= n) return;
     Ray r{v3(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]), v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};
     RayCounters rc;
-    V3 c = color_at(s, r, rc);
+    Tally tl;
+    V3 c = color_at(s, r, rc, tl);
     rgb[3 * i + 0] = c.x;
     rgb[3 * i + 1] = c.y;
     rgb[3 * i + 2] = c.z;
@@ -129,22 +129,6 @@ size_t slab_bytes(const std::vector<T>& v) {
 
 }  // namespace
 
-struct DeviceScene {
-    int device = 0;
-    int sm_count = 0;
-    void* slab = nullptr;
-    size_t slab_size = 0;
-    DScene view{};
-    DQueue* queue = nullptr;
-    // grow-only output scratch for render_host
-    void* out8 = nullptr;
-    size_t out8_size = 0;
-    void* out64 = nullptr;
-    size_t out64_size = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::mutex mu;
-};
 
 int cuda_device_count(std::string* err) {
     int n = 0;

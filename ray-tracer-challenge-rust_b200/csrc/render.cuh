@@ -35,6 +35,10 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* 
 // World::color_at for explicit rays (host in, host out).
 int color_at_host(DeviceScene* s, const double* rays, uint64_t n, double* rgb, std::string* err);
 
+// Work tallies of one frame (render_tally.cu): counts[tally_count()] in TallyIndex order (rt_core.cuh).
+int tally_count();
+int render_tally(DeviceScene* s, const DCamera& cam, const DRows& rows, unsigned long long* counts, std::string* err);
+
 int measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops, std::string* err);
 
 // Pinned host memory for frame buffers (so device->host copies run at PCIe speed); falls back to nothing — returns null

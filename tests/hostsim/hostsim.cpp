@@ -15,6 +15,7 @@
 #include "../../ray-tracer-challenge-rust_b200/csrc/rt_core.cuh"
 
 using namespace rtc;
+using namespace rtc::core;
 
 namespace {
 thread_local std::string g_err;
@@ -86,7 +87,8 @@ int sim_render(void* scene, const rtc_camera_desc* cam, const uint32_t* pixel_xy
                     y = (uint32_t)(i / cam->hsize);
                 }
                 Ray r = ray_for_pixel(dc, x, y);
-                V3 c = color_at(s->view, r, rcs[tid]);
+                Tally tl;
+                V3 c = color_at(s->view, r, rcs[tid], tl);
                 if (out_rgb) {
                     out_rgb[3 * i] = c.x;
                     out_rgb[3 * i + 1] = c.y;
@@ -121,7 +123,8 @@ int sim_color_at(void* scene, const double* rays, uint64_t n, double* rgb) {
     RayCounters rc;
     for (uint64_t i = 0; i < n; i++) {
         Ray r{v3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};
-        V3 c = color_at(s->view, r, rc);
+        Tally tl;
+        V3 c = color_at(s->view, r, rc, tl);
         rgb[3 * i] = c.x;
         rgb[3 * i + 1] = c.y;
         rgb[3 * i + 2] = c.z;

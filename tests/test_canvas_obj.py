@@ -1,0 +1,144 @@
+"""Canvas / to_ppm (canvas.rs tests :75-175) and the OBJ parser (obj_file.rs tests :139-293) of the host mirror."""
+import ctypes as C
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+capi = importlib.import_module("ray-tracer-challenge-rust_b200._capi")
+
+
+def test_creating_a_canvas_and_writing_pixels(rtc):
+    c = rtc.Canvas(10, 20)
+    assert (c.width, c.height) == (10, 20)
+    assert not c.pixels_f64().any()
+    c.set_pixel(2, 3, (1, 0, 0))
+    assert list(c.get_pixel(2, 3)) == [1, 0, 0]
+    with pytest.raises(rtc.RtcError):
+        c.get_pixel(10, 0)
+
+
+def test_ppm_header_pixel_data_and_terminator(rtc):
+    c = rtc.Canvas(5, 3)
+    lines = c.to_ppm().decode().split("\n")
+    assert lines[:3] == ["P3", "5 3", "255"] and lines[-1] == ""
+    c.set_pixel(0, 0, (1.5, 0, 0))
+    c.set_pixel(2, 1, (0, 0.5, 0))
+    c.set_pixel(4, 2, (-0.5, 0, 1))
+    lines = c.to_ppm().decode().split("\n")
+    assert len(lines) == 7
+    assert lines[3] == "255 0 0 0 0 0 0 0 0 0 0 0 0 0 0"
+    assert lines[4] == "0 0 0 0 0 0 0 128 0 0 0 0 0 0 0"
+    assert lines[5] == "0 0 0 0 0 0 0 0 0 0 0 0 0 0 255"
+
+
+def test_splitting_long_lines(rtc):
+    c = rtc.Canvas(10, 2)
+    for y in range(2):
+        for x in range(10):
+            c.set_pixel(x, y, (1, 0.8, 0.6))
+    lines = c.to_ppm().decode().split("\n")
+    assert len(lines) == 8
+    assert lines[3] == lines[5] == "255 204 153 255 204 153 255 204 153 255 204 153 255 204 153 255 204"
+    assert lines[4] == lines[6] == "153 255 204 153 255 204 153 255 204 153 255 204 153"
+
+
+def test_ppm_matches_oracle_on_random_frames(rtc, oracle):
+    rng = np.random.default_rng(3)
+    for w, h in ((1, 1), (7, 3), (23, 5), (64, 9), (301, 4)):
+        rgb = rng.uniform(-0.2, 1.2, (h * w, 3))
+        rgb[rng.integers(0, h * w, 3)] = np.nan  # NaN quantises to 0 (`as i32`)
+        rgba = oracle.quantise_rgba8(rgb)
+        assert rtc.ppm_from_rgba8(rgba, w, h) == oracle.ppm(rgb, w, h)
+        c = rtc.Canvas(w, h)
+        for i in range(h * w):
+            c.set_pixel(i % w, i // w, rgb[i])
+        assert c.to_ppm() == oracle.ppm(rgb, w, h)
+        assert np.array_equal(c.pixels_rgba8().reshape(-1, 4), rgba)
+
+
+TRIANGLES_OBJ = "v -1 1 0\nv -1 0 0\nv 1 0 0\nv 1 1 0\n\ng FirstGroup\nf 1 2 3\ng SecondGroup\nf 1 3 4\n"
+
+
+def _leaves(rtc, shape):
+    api = rtc.api()
+    w = rtc.World(rtc.Light((0, 0, 0), (1, 1, 1)))
+    w.push(shape)
+    m = C.c_void_p()
+    api.check(api.world_marshal(w.h, C.byref(m)))
+    d = C.cast(api.marshalled_desc(m), C.POINTER(capi.SceneDesc)).contents
+    shapes = [(d.shapes[i].kind, d.shapes[i].child_count, d.shapes[i].triangle) for i in range(d.shape_count)]
+    tris = [np.array([d.triangles[i].p1[:], d.triangles[i].p2[:], d.triangles[i].p3[:], d.triangles[i].e1[:],
+                      d.triangles[i].e2[:], d.triangles[i].normal[:]]) for i in range(d.triangle_count)]
+    api.marshalled_free(m)
+    return shapes, tris
+
+
+def test_obj_ignoring_unrecognized_lines(rtc):
+    S = rtc.Shapes(rtc.api())
+    g = S.obj_str("\nThere was a young lady named Bright\nwho traveled much faster than light.\nShe set out one day\n"
+                  "in a relative way,\nand came back the previous night.\n")
+    assert g.ignored_lines == 5 and g.leaf_count() == 0
+
+
+def test_obj_faces_fan_and_groups(rtc):
+    S = rtc.Shapes(rtc.api())
+    g = S.obj_str("v -1 1 0\nv -1 0 0\nv 1 0 0\nv 1 1 0\nv 0 2 0\n\nf 1 2 3 4 5\n")
+    shapes, tris = _leaves(rtc, g)
+    assert [s[0] for s in shapes] == [5, 5, 6, 6, 6]  # group{default_group{3 triangles}}
+    v = np.array([[-1, 1, 0], [-1, 0, 0], [1, 0, 0], [1, 1, 0], [0, 2, 0]], dtype=float)
+    for t, (a, b, c) in zip(tris, ((0, 1, 2), (0, 2, 3), (0, 3, 4))):
+        assert np.array_equal(t[0], v[a]) and np.array_equal(t[1], v[b]) and np.array_equal(t[2], v[c])
+        assert np.array_equal(t[3], v[b] - v[a]) and np.array_equal(t[4], v[c] - v[a])
+    # shape.rs:1545-1562: normal = normalize(e2 x e1)
+    shapes, tris = _leaves(rtc, S.triangle((0, 1, 0), (-1, 0, 0), (1, 0, 0)))
+    assert np.array_equal(tris[0][3], [-1, -1, 0]) and np.array_equal(tris[0][4], [1, -1, 0])
+    assert np.array_equal(np.abs(tris[0][5]), [0, 0, 1]) and tris[0][5][2] == -1
+    g = S.obj_str(TRIANGLES_OBJ)
+    shapes, tris = _leaves(rtc, g)
+    assert [s[:2] for s in shapes] == [(5, 3), (5, 0), (5, 1), (6, 0), (5, 1), (6, 0)]
+    assert g.ignored_lines == 0
+
+
+def test_obj_parser_panics(rtc):
+    S = rtc.Shapes(rtc.api())
+    for bad in ("v 1 2\n", "v 1 2 x\n", "f 1/2/3 2 3\n", "v 0 0 0\nf 1 2 9\n", "g\n", "f 1\n"):
+        with pytest.raises(ValueError):
+            S.obj_str(bad)
+
+
+def test_obj_matches_mesh_from_arrays_and_oracle(rtc, oracle, hostsim, tmp_path):
+    """Parsing OBJ text == building from arrays; product parser and oracle parser render identically."""
+    v, f = helpers.scenes.load_mesh("teddy")
+    text = "".join(f"v {repr(float(a))} {repr(float(b))} {repr(float(c))}\n" for a, b, c in v[:400])
+    faces = f[(f <= 400).all(axis=1)][:300]
+    text += "# comment\n" + "".join(f"f {a} {b} {c}\n" for a, b, c in faces)
+    p = tmp_path / "part.obj"
+    p.write_text(text)
+    T = rtc.Transformations(rtc.api())
+    outs = []
+    for make in (lambda S: S.obj_file(p), lambda S: S.obj_str(text), lambda S: S.mesh(v[:400], faces)):
+        for api in (rtc.api(), oracle):
+            S, Tx = rtc.Shapes(api), rtc.Transformations(api)
+            sa = importlib.import_module("ray-tracer-challenge-rust_b200.scene_api")
+            g = make(S)
+            g.set_transform(Tx.scaling(0.1, 0.1, 0.1))
+            w = sa.WorldHandle(api, rtc.Light((0, 6.9, -5), (1, 1, 0.9)))
+            w.push(g)
+            c = sa.CameraHandle(api, 40, 30, 0.8)
+            c.set_transform(Tx.view_transform((0, 1, -8), (0, 0, 0), (0, 1, 0)))
+            if api is oracle:
+                outs.append(oracle.render(w, c, mode=oracle.CACHED)[0])
+            else:
+                world = rtc.World(_handle=w.h)
+                w.h = None
+                cam = rtc.Camera.__new__(rtc.Camera)
+                cam.api, cam.hsize, cam.vsize, cam.field_of_view, cam.h = c.api, 40, 30, 0.8, c.h
+                c.h = None
+                outs.append(hostsim.scene(world).render(cam)[0])
+    assert outs[0].any()
+    for o in outs[1:]:
+        assert np.array_equal(o.view(np.uint64), outs[0].view(np.uint64))

@@ -1,0 +1,206 @@
+"""The C ABI and the host mirror of the reference API (no GPU needed): exported symbols, transformations/matrix KATs
+against the oracle bit for bit, construction semantics (push-down, panics), marshalling, flattening and gate boxes."""
+import ctypes as C
+import importlib
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers
+
+capi = importlib.import_module("ray-tracer-challenge-rust_b200._capi")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(rtc):
+    header = open(os.path.join(ROOT, "include", "rtc.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b(rtc_[a-z0-9_]+)\s*\(", header))
+    assert len(names) > 50
+    lib = C.CDLL(rtc.LIB_PATH)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback(rtc, has_gpu):
+    """Without a CUDA device every rendering entry point fails loudly with RTC_ERR_CUDA."""
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    w, c = rtc.build_scene("hexagon", 16, 8)
+    with pytest.raises(rtc.RtcError) as e:
+        c.render(w)
+    assert e.value.code == rtc.RTC_ERR_CUDA
+    with pytest.raises(rtc.RtcError) as e:
+        w.color_at([[0, 0, -5, 0, 0, 1]])
+    assert e.value.code == rtc.RTC_ERR_CUDA
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "ray-tracer-challenge-rust_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(d, f)).read()
+                assert "liboracle" not in text and "oracle.hpp" not in text and "oracle_capi" not in text, f
+
+
+def _mat(api, fn, *args):
+    out = np.empty(16)
+    getattr(api, fn)(*args, capi.dptr(out))
+    return out
+
+
+def test_transformations_match_oracle_bitwise(rtc, oracle):
+    rng = np.random.default_rng(1)
+    a, o = rtc.api(), oracle
+    for _ in range(50):
+        x, y, z = rng.uniform(-5, 5, 3)
+        for fn, args in (("translation", (x, y, z)), ("scaling", (x, y, z)), ("rotation_x", (x,)), ("rotation_y", (y,)),
+                         ("rotation_z", (z,)), ("shearing", tuple(rng.uniform(-1, 1, 6)))):
+            assert np.array_equal(_mat(a, fn, *args).view(np.uint64), _mat(o, fn, *args).view(np.uint64)), fn
+    Ta, To = rtc.Transformations(a), rtc.Transformations(o)
+    for _ in range(50):
+        frm, to = rng.uniform(-9, 9, 3), rng.uniform(-2, 2, 3)
+        mo = To.view_transform(frm, to, (0, 1, 0)) * To.rotation_y(0.3)
+        ma = Ta.view_transform(frm, to, (0, 1, 0)) * Ta.rotation_y(0.3)
+        s = rng.uniform(0.2, 3, 3)
+        ma, mo = ma * Ta.scaling(*s), mo * To.scaling(*s)
+        assert np.array_equal(ma.v.view(np.uint64), mo.v.view(np.uint64))
+        assert np.array_equal(ma.inverse().v.view(np.uint64), mo.inverse().v.view(np.uint64))
+        assert np.array_equal(ma.transpose().v.view(np.uint64), mo.transpose().v.view(np.uint64))
+        t = rng.uniform(-3, 3, 4)
+        assert np.array_equal(ma.mul_tuple(t).view(np.uint64), mo.mul_tuple(t).view(np.uint64))
+
+
+def test_matrix_known_answers(rtc):
+    """matrix.rs:483-559, transformations.rs:278-319 (5-decimal KATs of the reference)."""
+    T = rtc.Transformations(rtc.api())
+    a = rtc.Matrix(rtc.api(), [-5, 2, 6, -8, 1, -5, 1, 8, 7, 7, -6, -7, 1, -3, 7, 4])
+    b = a.inverse().array()
+    np.testing.assert_allclose(b, [[0.21805, 0.45113, 0.24060, -0.04511], [-0.80827, -1.45677, -0.44361, 0.52068],
+                                   [-0.07895, -0.22368, -0.05263, 0.19737], [-0.52256, -0.81391, -0.30075, 0.30639]],
+                               atol=1e-5)
+    with pytest.raises(ValueError):  # |det| < 1e-5 (matrix.rs:140)
+        rtc.Matrix(rtc.api(), [-4, 2, -2, -3, 9, 6, 2, 6, 0, -5, 1, -5, 0, 0, 0, 0]).inverse()
+    with pytest.raises(ValueError):  # scaling(0.01)^3 has det 1e-6: the reference refuses it
+        T.scaling(0.01, 0.01, 0.01).inverse()
+    v = T.view_transform((1, 3, 2), (4, -2, 8), (1, 1, 0)).array()
+    np.testing.assert_allclose(v, [[-0.50709, 0.50709, 0.67612, -2.36643], [0.76772, 0.60609, 0.12122, -2.82843],
+                                   [-0.35857, 0.59761, -0.71714, 0.0], [0, 0, 0, 1]], atol=1e-5)
+    np.testing.assert_allclose(T.view_transform((0, 0, 0), (0, 0, 1), (0, 1, 0)).array(), T.scaling(-1, 1, -1).array())
+
+
+def test_camera_known_answers(rtc):
+    """camera.rs:84-142"""
+    c = rtc.Camera(200, 125, math.pi / 2).desc()
+    assert abs(c.pixel_size - 0.01) < 1e-5
+    c = rtc.Camera(125, 200, math.pi / 2).desc()
+    assert abs(c.pixel_size - 0.01) < 1e-5
+
+
+def _desc(rtc, world):
+    api = rtc.api()
+    m = C.c_void_p()
+    api.check(api.world_marshal(world.h, C.byref(m)))
+    d = C.cast(api.marshalled_desc(m), C.POINTER(capi.SceneDesc)).contents
+    return m, d
+
+
+def test_set_transform_pushes_down_and_panics_like_the_reference(rtc):
+    """shape.rs:196-218: groups keep the identity, leaves get T * own; a second call panics; singular matrices panic."""
+    T, S = rtc.Transformations(rtc.api()), rtc.Shapes(rtc.api())
+    g = S.group()
+    s = S.sphere()
+    s.set_transform(T.translation(5, 0, 0))
+    g.push_shape(s)
+    g.set_transform(T.scaling(2, 2, 2))
+    with pytest.raises(ValueError, match="more than once"):
+        g.set_transform(T.scaling(2, 2, 2))
+    w = rtc.World(rtc.Light((0, 0, 0), (1, 1, 1)))
+    w.push(g)
+    m, d = _desc(rtc, w)
+    try:
+        assert d.shape_count == 2 and d.root_count == 1
+        assert d.shapes[0].kind == rtc.api().GROUP and d.shapes[0].child_count == 1
+        gt = np.array(d.transforms[d.shapes[0].transform].transform[:]).reshape(4, 4)
+        assert np.array_equal(gt, np.eye(4))
+        lt = np.array(d.transforms[d.shapes[1].transform].transform[:]).reshape(4, 4)
+        expect = (T.scaling(2, 2, 2) * T.translation(5, 0, 0)).array()
+        assert np.array_equal(lt, expect)
+        li = np.array(d.transforms[d.shapes[1].transform].inverse[:])
+        assert np.array_equal(li, (T.scaling(2, 2, 2) * T.translation(5, 0, 0)).inverse().v)
+    finally:
+        rtc.api().marshalled_free(m)
+    s2 = S.sphere()
+    with pytest.raises(ValueError, match="invertible"):
+        s2.set_transform(T.scaling(0.01, 0.01, 0.01))
+    with pytest.raises(ValueError, match="group"):
+        S.sphere().push_shape(S.sphere())
+
+
+def test_uncapped_cylinder_in_group_is_a_reference_panic(rtc):
+    """bounds.rs:143: Bounds::add asserts is_point(); 0 * inf = NaN in w makes the reference panic on the first ray."""
+    S = rtc.Shapes(rtc.api())
+    g = S.group()
+    g.push_shape(S.cylinder())
+    w = rtc.World(rtc.Light((0, 0, 0), (1, 1, 1)))
+    w.push(g)
+    with pytest.raises(rtc.RtcError) as e:
+        w.flatten_info()
+    assert e.value.code == rtc.RTC_ERR_PANIC and "bounds.rs:143" in e.value.message
+
+
+def test_flattening_of_the_configs(rtc):
+    w, _ = rtc.build_scene("hexagon", 8, 4)
+    info = w.flatten_info(want_gates=True)
+    assert (info["leaves"], info["gates"], info["meshes"]) == (12, 7, 0)
+    # the hexagon's outer gate contains the origin and spans the ring (bounds.rs:50-125)
+    lo, hi = info["gate_boxes"][0][:3], info["gate_boxes"][0][3:]
+    assert (lo <= 0).all() and (hi >= 0).all() and hi[0] > 2.5 and lo[0] < -2.5
+    w, _ = rtc.build_scene("teapot", 8, 4)
+    info = w.flatten_info(want_gates=True)
+    assert info["leaves"] == 6320 and info["mesh_triangles"] == 6320 and info["meshes"] == 1 and info["gates"] == 2
+    assert info["bvh_max_depth"] <= 40 and info["transforms"] == 1
+    # obj_to_group nests group{default_group{...}}: both gates are the same box
+    assert np.array_equal(info["gate_boxes"][0], info["gate_boxes"][1])
+    w, _ = rtc.build_scene("pumpkin", 8, 4)
+    g = w.flatten_info(want_gates=True)["gate_boxes"][0]
+    assert g[0] <= 0 <= g[3] and g[1] <= 0 <= g[4] and g[2] <= 0 <= g[5]  # origin-seeded even though the mesh is far away
+
+
+def test_scene_create_rejects_malformed_descriptions(rtc):
+    api = rtc.api()
+    shapes = (capi.ShapeDesc * 1)()
+    shapes[0].kind, shapes[0].material, shapes[0].transform = 0, 0, 0
+    tr = (capi.TransformDesc * 1)()
+    tr[0].transform[:] = list(np.eye(4).ravel())
+    tr[0].inverse[:] = list(np.eye(4).ravel())
+    mats = (capi.Material * 1)()
+    api.material_default(C.byref(mats[0]))
+    d = capi.SceneDesc()
+    d.shapes, d.shape_count, d.root_count = shapes, 1, 1
+    d.transforms, d.transform_count, d.materials, d.material_count = tr, 1, mats, 1
+    out = C.c_void_p()
+
+    def create():
+        return api.scene_create(C.cast(C.byref(d), C.c_void_p), 0, C.byref(out))
+
+    shapes[0].material = 3
+    assert create() == rtc.RTC_ERR_INVALID and "material index" in api.error()
+    shapes[0].material = 0
+    shapes[0].kind = 42
+    assert create() == rtc.RTC_ERR_INVALID
+    shapes[0].kind = 0
+    d.root_count = 2
+    assert create() == rtc.RTC_ERR_INVALID
+    d.root_count = 1
+    tr[0].transform[12] = 0.5  # projective row: not representable with the reference's point/vector asserts
+    assert create() == rtc.RTC_ERR_UNSUPPORTED
+    tr[0].transform[12] = 0.0
+    rc = create()  # valid now: succeeds on a GPU box, RTC_ERR_CUDA here
+    assert rc in (rtc.RTC_OK, rtc.RTC_ERR_CUDA)
+    if rc == rtc.RTC_OK:
+        api.scene_destroy(out)

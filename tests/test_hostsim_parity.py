@@ -1,0 +1,91 @@
+"""The product's per-ray program (csrc/rt_core.cuh) + flattener + BVH, compiled for the host by tests/hostsim, against
+the oracle — bit for bit.  This is the CPU-box check of the logic the GPU runs (the GPU run of the same comparisons is
+tests/test_gpu_parity.py); it is test infrastructure, not a product path."""
+import importlib
+
+import numpy as np
+import pytest
+
+import helpers
+import worldgen
+
+
+def _wrap(rtc, w, c):
+    """scene_api handles built on the product api -> product World/Camera wrappers."""
+    world = rtc.World(_handle=w.h)
+    w.h = None
+    cam = rtc.Camera.__new__(rtc.Camera)
+    cam.api, cam.hsize, cam.vsize, cam.field_of_view, cam.h = c.api, c.hsize, c.vsize, c.field_of_view, c.h
+    c.h = None
+    return world, cam
+
+
+def _bits_equal(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(b).view(np.uint64))
+
+
+@pytest.mark.parametrize("name,w,h", [("hexagon", 200, 100), ("table", 160, 90), ("teapot", 64, 36), ("cow", 64, 32),
+                                      ("cow_teddy", 64, 36), ("pumpkin", 64, 36)])
+def test_configs_bit_exact(rtc, oracle, hostsim, name, w, h):
+    world, cam = rtc.build_scene(name, w, h)
+    ow, oc = helpers.scenes.build(oracle, name, w, h)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    rgb, rgba, scnt = hostsim.scene(world).render(cam)
+    assert _bits_equal(ref, rgb)
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+    assert np.array_equal(rgba, oracle.quantise_rgba8(ref))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_worlds_bit_exact(rtc, oracle, hostsim, seed):
+    world, cam = _wrap(rtc, *worldgen.random_world(rtc.api(), seed))
+    ow, oc = worldgen.random_world(oracle, seed)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    rgb, _, scnt = hostsim.scene(world).render(cam)
+    assert _bits_equal(ref, rgb), f"seed {seed}: {np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+
+
+def test_faithful_and_cached_oracle_agree(oracle):
+    """The timed CPU arm (faithful: the reference's algorithm and cost) and the golden generator (cached) are one
+    arithmetic."""
+    ow, oc = helpers.scenes.build(oracle, "hexagon", 80, 40)
+    a, _ = oracle.render(ow, oc, mode=oracle.FAITHFUL, nthreads=1)
+    b, _ = oracle.render(ow, oc, mode=oracle.CACHED)
+    assert _bits_equal(a, b)
+    ow, oc = helpers.scenes.build(oracle, "teapot", 1920, 1080)
+    px = helpers.subset_pixels(1920, 1080, 240, 120)
+    a, _ = oracle.render(ow, oc, mode=oracle.FAITHFUL, nthreads=1, pixels=px)
+    b, _ = oracle.render(ow, oc, mode=oracle.CACHED, pixels=px)
+    assert _bits_equal(a, b)
+
+
+def test_full_resolution_subsets_bit_exact(rtc, oracle, hostsim):
+    """BASELINE resolutions (the ulp-sensitive wall checkers of the table scene need the real 1920x1080 camera)."""
+    for name, w, h, step in (("table", 1920, 1080, 24), ("teapot", 1920, 1080, 48), ("pumpkin", 7680, 4320, 160)):
+        world, cam = rtc.build_scene(name, w, h)
+        ow, oc = helpers.scenes.build(oracle, name, w, h)
+        px = helpers.subset_pixels(w, h, step, step // 2)
+        ref, _ = oracle.render(ow, oc, mode=oracle.CACHED, pixels=px)
+        rgb, _, _ = hostsim.scene(world).render(cam, pixels=px)
+        assert _bits_equal(ref, rgb), name
+
+
+def test_explicit_rays_and_ties(rtc, oracle, hostsim):
+    """color_at on explicit rays, including rays aimed exactly at shared mesh vertices/edges and cube edges."""
+    world, cam = rtc.build_scene("teapot", 32, 16)
+    ow, _ = helpers.scenes.build(oracle, "teapot", 32, 16)
+    v, f = helpers.scenes.load_mesh("teapot")
+    rng = np.random.default_rng(5)
+    rays = []
+    origin = np.array([0.0, 4.0, -12.0])
+    for i in rng.integers(0, len(v), 200):
+        target = v[i] + np.array([0.0, -1.5, 0.0])  # the teapot's translation
+        d = target - origin
+        rays.append(np.concatenate([origin, d / np.linalg.norm(d)]))
+    for i in rng.integers(0, len(f), 200):  # edge midpoints
+        a, b = v[f[i][0] - 1], v[f[i][1] - 1]
+        d = (a + b) / 2 + np.array([0.0, -1.5, 0.0]) - origin
+        rays.append(np.concatenate([origin, d / np.linalg.norm(d)]))
+    rays = np.array(rays)
+    assert _bits_equal(oracle.color_at(ow, rays), hostsim.scene(world).color_at(rays))

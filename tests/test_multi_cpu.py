@@ -1,0 +1,77 @@
+"""Row-band sharding (multi.py): the plan, and the world_size-2 gather + reassembly over gloo on CPU."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+multi = importlib.import_module("ray-tracer-challenge-rust_b200.multi")
+
+
+@pytest.mark.parametrize("vsize,g,br", [(1080, 8, 8), (1080, 2, 8), (4320, 8, 8), (117, 4, 8), (200, 3, 16), (7, 8, 4),
+                                        (1, 1, 8), (2160, 4, 8)])
+def test_band_plan_partitions_the_rows(vsize, g, br):
+    plan = multi.BandPlan(vsize, g, br)
+    assert vsize % plan.band_rows == 0 and plan.band_rows <= br
+    seen = []
+    for r in range(g):
+        rows = plan.rows(r)
+        assert (rows.band_rows, rows.band_first, rows.band_stride) == (plan.band_rows, r, g)
+        for b in plan.bands_of(r):
+            seen += list(range(b * plan.band_rows, (b + 1) * plan.band_rows))
+        assert plan.local_rows(r) <= plan.padded_rows
+    assert sorted(seen) == list(range(vsize))
+    # assemble() inverts the dealing: fill each rank's compact buffer with its frame-row numbers
+    w = 3
+    gathered = torch.full((g, plan.padded_rows, w, 4), -1, dtype=torch.int32)
+    for r in range(g):
+        k = 0
+        for b in plan.bands_of(r):
+            for i in range(plan.band_rows):
+                gathered[r, k] = b * plan.band_rows + i
+                k += 1
+    frame = plan.assemble(gathered)
+    assert frame.shape == (vsize, w, 4)
+    assert torch.equal(frame[:, 0, 0], torch.arange(vsize, dtype=torch.int32))
+
+
+def _worker(rank, world_size, port, vsize, width, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    plan = multi.BandPlan(vsize, world_size, 8)
+    # stand-in for the render kernel: every rank fills its compact band buffer with (frame row, column, rank, 255)
+    local = torch.zeros((plan.padded_rows, width, 4), dtype=torch.uint8)
+    k = 0
+    for b in plan.bands_of(rank):
+        for i in range(plan.band_rows):
+            row = b * plan.band_rows + i
+            local[k, :, 0] = row % 251
+            local[k, :, 1] = torch.arange(width) % 256
+            local[k, :, 2] = rank
+            local[k, :, 3] = 255
+            k += 1
+    gathered = torch.empty((world_size, plan.padded_rows, width, 4), dtype=torch.uint8) if rank == 0 else None
+    dist.gather(local, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+    if rank == 0:
+        np.save(out_path, plan.assemble(gathered).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("vsize", [64, 120])
+def test_gloo_world_size_2_gather_reassembles_the_frame(tmp_path, vsize):
+    port = 29500 + (os.getpid() + vsize) % 2000
+    out = str(tmp_path / "frame.npy")
+    mp.spawn(_worker, args=(2, port, vsize, 16, out), nprocs=2, join=True)
+    frame = np.load(out)
+    assert frame.shape == (vsize, 16, 4)
+    rows = np.arange(vsize)
+    assert np.array_equal(frame[:, 0, 0], rows % 251)
+    assert np.array_equal(frame[:, :, 1], np.tile(np.arange(16), (vsize, 1)))
+    plan = multi.BandPlan(vsize, 2, 8)
+    assert np.array_equal(frame[:, 0, 2], (rows // plan.band_rows) % 2)  # band b came from rank b mod 2
+    assert (frame[:, :, 3] == 255).all()
