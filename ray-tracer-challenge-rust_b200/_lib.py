@@ -5,7 +5,8 @@ import os
 from ._capi import BuilderApi, CameraDesc, Material, Rows, Stats, c_double_p, c_u64_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librtc_b200.so")
+# RTC_B200_LIB selects a tuning variant built by tools/tune_variants.py (same sources, other launch shape)
+LIB_PATH = os.environ.get("RTC_B200_LIB") or os.path.join(HERE, "librtc_b200.so")
 
 RTC_OK, RTC_ERR_INVALID, RTC_ERR_PANIC, RTC_ERR_CUDA, RTC_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 

@@ -53,22 +53,27 @@ def _run(cmd, log):
         raise RuntimeError("build step failed: " + " ".join(cmd))
 
 
-def build(force=False, verbose=False):
-    """Compile if sources are newer than the library; returns the library path."""
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile if sources are newer than the library; returns the library path.  `defines` / `out` build a tuning
+    variant (extra -D macros for render.cu, written to another path) without touching the default library."""
+    lib = out or LIB
+    if not force and not out and not _stale():
         return LIB
-    os.makedirs(BUILD, exist_ok=True)
+    bdir = BUILD if not out else os.path.join(BUILD, os.path.basename(out) + ".d")
+    os.makedirs(bdir, exist_ok=True)
     nvcc = _nvcc()
-    with open(os.path.join(BUILD, "build.log"), "w") as log:
-        _run(["g++", *HOST_FLAGS, "-c", os.path.join(CSRC, "capi.cpp"), "-o", os.path.join(BUILD, "capi.o")], log)
-        _run([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "render.cu"), "-o", os.path.join(BUILD, "render.o")], log)
+    dflags = ["-D" + d for d in defines]
+    with open(os.path.join(bdir, "build.log"), "w") as log:
+        _run(["g++", *HOST_FLAGS, "-c", os.path.join(CSRC, "capi.cpp"), "-o", os.path.join(bdir, "capi.o")], log)
+        _run([nvcc, *NVCC_FLAGS, *dflags, "-c", os.path.join(CSRC, "render.cu"), "-o", os.path.join(bdir, "render.o")],
+             log)
         _run([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "render_tally.cu"), "-o",
-              os.path.join(BUILD, "render_tally.o")], log)
-        _run([nvcc, "-shared", "-o", LIB, os.path.join(BUILD, "capi.o"), os.path.join(BUILD, "render.o"),
-              os.path.join(BUILD, "render_tally.o")], log)
+              os.path.join(bdir, "render_tally.o")], log)
+        _run([nvcc, "-shared", "-o", lib, os.path.join(bdir, "capi.o"), os.path.join(bdir, "render.o"),
+              os.path.join(bdir, "render_tally.o")], log)
     if verbose:
-        print(open(os.path.join(BUILD, "build.log")).read())
-    return LIB
+        print(open(os.path.join(bdir, "build.log")).read())
+    return lib
 
 
 if __name__ == "__main__":

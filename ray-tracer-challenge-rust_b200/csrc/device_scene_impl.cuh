@@ -16,21 +16,36 @@ struct DQueue {
     unsigned int pad;
 };
 
-struct DeviceScene {
+constexpr int kQueueSlots = 16;
+
+// Per-device state created on first use and kept for the life of the process: creating streams, events and querying
+// device properties costs milliseconds, a frame costs less.
+struct DeviceContext {
     int device = 0;
     int sm_count = 0;
-    void* slab = nullptr;
-    size_t slab_size = 0;
-    DScene view{};
-    DQueue* queue = nullptr;
-    // grow-only output scratch for render_host
+    cudaStream_t stream = nullptr;  // the library's own stream (uploads, host-output renders)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DQueue* queues = nullptr;       // kQueueSlots work queues handed out round-robin (one per in-flight launch)
+    unsigned next_queue = 0;
+    // grow-only scratch
     void* out8 = nullptr;
     size_t out8_size = 0;
     void* out64 = nullptr;
     size_t out64_size = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* staging = nullptr;        // pinned upload staging
+    size_t staging_size = 0;
     std::mutex mu;
+};
+
+struct DeviceScene {
+    DeviceContext* ctx = nullptr;
+    int device = 0;
+    int sm_count = 0;
+    void* slab = nullptr;           // all tables, one stream-ordered allocation
+    size_t slab_size = 0;
+    DScene view{};
+    cudaStream_t stream = nullptr;  // == ctx->stream
+    std::mutex& mu() { return ctx->mu; }
 };
 
 inline std::string cuda_err_string(const char* what, cudaError_t e) {

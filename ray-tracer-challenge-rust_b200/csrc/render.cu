@@ -21,12 +21,19 @@ using namespace core;
 
 namespace {
 
-constexpr int kBlockThreads = 128;
+// launch shape (tunable at build time: tools/tune_variants.py)
+#ifndef RTC_BLOCK_THREADS
+#define RTC_BLOCK_THREADS 128
+#endif
+#ifndef RTC_BLOCKS_PER_SM
+#define RTC_BLOCKS_PER_SM 4
+#endif
+constexpr int kBlockThreads = RTC_BLOCK_THREADS;
 constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
-constexpr int kBlocksPerSm = 4;
+constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;
 
 
-__global__ void __launch_bounds__(kBlockThreads) render_kernel(const __grid_constant__ DScene s,
+__global__ void __launch_bounds__(kBlockThreads, kBlocksPerSm) render_kernel(const __grid_constant__ DScene s,
                                                                const __grid_constant__ DCamera cam,
                                                                const __grid_constant__ DRows rows,
                                                                uint32_t* __restrict__ out8, double* __restrict__ out64,
@@ -140,30 +147,65 @@ int cuda_device_count(std::string* err) {
     return n;
 }
 
-int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::string* err) {
+// one context per device, created on first use
+static DeviceContext* context_for(int device, std::string* err) {
+    static std::mutex gmu;
+    static DeviceContext* table[64] = {};
+    std::lock_guard<std::mutex> lk(gmu);
     int ndev = 0;
-    RTC_CUDA(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) {
-        if (err) *err = "no such CUDA device";
-        return -3;
-    }
-    RTC_CUDA(cudaSetDevice(device));
-    DeviceScene* s = new DeviceScene();
-    s->device = device;
-    cudaDeviceProp prop;
-    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess) {
-        delete s;
-        if (err) *err = cuda_err("cudaGetDeviceProperties", e);
-        return -3;
+        if (err) *err = cuda_err("cudaGetDeviceCount(&ndev)", e);
+        return nullptr;
     }
-    s->sm_count = prop.multiProcessorCount;
+    if (device < 0 || device >= ndev || device >= 64) {
+        if (err) *err = "no such CUDA device";
+        return nullptr;
+    }
+    if (table[device]) return table[device];
+    DeviceContext* c = new DeviceContext();
+    c->device = device;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->queues, sizeof(DQueue) * kQueueSlots);
+    if (e == cudaSuccess) {  // keep freed scene slabs in the stream-ordered pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        if (err) *err = cuda_err("creating the device context", e);
+        delete c;
+        return nullptr;
+    }
+    table[device] = c;
+    return c;
+}
+
+int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::string* err) {
+    DeviceContext* ctx = context_for(device, err);
+    if (!ctx) return -3;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    RTC_CUDA(cudaSetDevice(device));
     const size_t sizes[9] = {slab_bytes(f.program), slab_bytes(f.xforms),   slab_bytes(f.prims),
                              slab_bytes(f.gates),   slab_bytes(f.meshes),   slab_bytes(f.bvh),
                              slab_bytes(f.tris),    slab_bytes(f.tri_attr), slab_bytes(f.materials)};
     size_t total = 256;
     for (size_t b : sizes) total += b;
-    std::vector<unsigned char> host(total, 0);
+    if (ctx->staging_size < total) {
+        if (ctx->staging) cudaFreeHost(ctx->staging);
+        ctx->staging = nullptr;
+        ctx->staging_size = 0;
+        RTC_CUDA(cudaHostAlloc(&ctx->staging, total * 2, cudaHostAllocDefault));
+        ctx->staging_size = total * 2;
+    }
+    unsigned char* host = (unsigned char*)ctx->staging;
     size_t off[9], at = 0;
     const void* src[9] = {f.program.data(), f.xforms.data(),   f.prims.data(),    f.gates.data(), f.meshes.data(),
                           f.bvh.data(),     f.tris.data(),     f.tri_attr.data(), f.materials.data()};
@@ -174,34 +216,25 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
                            f.materials.size() * sizeof(DMaterial)};
     for (int k = 0; k < 9; k++) {
         off[k] = at;
-        if (raw[k]) std::memcpy(host.data() + at, src[k], raw[k]);
+        if (raw[k]) std::memcpy(host + at, src[k], raw[k]);
         at += sizes[k];
     }
-    auto cleanup = [&]() {
-        if (s->slab) cudaFree(s->slab);
-        if (s->queue) cudaFree(s->queue);
-        if (s->stream) cudaStreamDestroy(s->stream);
-        if (s->ev0) cudaEventDestroy(s->ev0);
-        if (s->ev1) cudaEventDestroy(s->ev1);
-        delete s;
-    };
-#define RTC_CUDA_C(call)                                       \
-    do {                                                       \
-        cudaError_t e_ = (call);                               \
-        if (e_ != cudaSuccess) {                               \
-            if (err) *err = cuda_err(#call, e_);               \
-            cleanup();                                         \
-            return -3;                                         \
-        }                                                      \
-    } while (0)
-    RTC_CUDA_C(cudaMalloc(&s->slab, total));
+    void* slab = nullptr;
+    RTC_CUDA(cudaMallocAsync(&slab, total, ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(slab, host, at, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the tables are now visible to every stream
+    if (e != cudaSuccess) {
+        cudaFreeAsync(slab, ctx->stream);
+        if (err) *err = cuda_err("uploading the scene", e);
+        return -3;
+    }
+    DeviceScene* s = new DeviceScene();
+    s->ctx = ctx;
+    s->device = device;
+    s->sm_count = ctx->sm_count;
+    s->stream = ctx->stream;
+    s->slab = slab;
     s->slab_size = total;
-    RTC_CUDA_C(cudaMemcpy(s->slab, host.data(), total, cudaMemcpyHostToDevice));
-    RTC_CUDA_C(cudaMalloc((void**)&s->queue, sizeof(DQueue)));
-    RTC_CUDA_C(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    RTC_CUDA_C(cudaEventCreate(&s->ev0));
-    RTC_CUDA_C(cudaEventCreate(&s->ev1));
-#undef RTC_CUDA_C
     unsigned char* base = (unsigned char*)s->slab;
     s->view.program = (const DProgramNode*)(base + off[0]);
     s->view.xforms = (const DXform*)(base + off[1]);
@@ -223,14 +256,13 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
 
 void device_scene_destroy(DeviceScene* s) {
     if (!s) return;
-    cudaSetDevice(s->device);
-    if (s->out8) cudaFree(s->out8);
-    if (s->out64) cudaFree(s->out64);
-    if (s->slab) cudaFree(s->slab);
-    if (s->queue) cudaFree(s->queue);
-    if (s->stream) cudaStreamDestroy(s->stream);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
+    {
+        std::lock_guard<std::mutex> lk(s->ctx->mu);
+        cudaSetDevice(s->device);
+        // stream-ordered free: frames already queued on the library stream finish first.  Frames the caller queued on
+        // its OWN stream must be synchronised by the caller before destroying the scene (see rtc_render_device).
+        if (s->slab) cudaFreeAsync(s->slab, s->ctx->stream);
+    }
     delete s;
 }
 uint64_t device_scene_bytes(const DeviceScene* s) { return s->slab_size; }
@@ -242,22 +274,24 @@ static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
         if (stats) *stats = LaunchStats{};
         return 0;
     }
-    RTC_CUDA(cudaMemsetAsync(s->queue, 0, sizeof(DQueue), st));
+    DeviceContext* ctx = s->ctx;
+    DQueue* queue = ctx->queues + (ctx->next_queue++ % kQueueSlots);
+    RTC_CUDA(cudaMemsetAsync(queue, 0, sizeof(DQueue), st));
     const uint64_t tiles = (uint64_t)((cam.hsize + kTileW - 1) / kTileW) * ((rows.local_rows + kTileH - 1) / kTileH);
     const uint64_t warps_per_block = kBlockThreads / 32;
     uint64_t blocks = (tiles + warps_per_block - 1) / warps_per_block;
     const uint64_t cap = (uint64_t)s->sm_count * kBlocksPerSm;
     if (blocks > cap) blocks = cap;
-    if (stats) RTC_CUDA(cudaEventRecord(s->ev0, st));
-    render_kernel<<<(unsigned)blocks, kBlockThreads, 0, st>>>(s->view, cam, rows, (uint32_t*)d8, (double*)d64, s->queue);
+    if (stats) RTC_CUDA(cudaEventRecord(ctx->ev0, st));
+    render_kernel<<<(unsigned)blocks, kBlockThreads, 0, st>>>(s->view, cam, rows, (uint32_t*)d8, (double*)d64, queue);
     RTC_CUDA(cudaGetLastError());
     if (stats) {
-        RTC_CUDA(cudaEventRecord(s->ev1, st));
+        RTC_CUDA(cudaEventRecord(ctx->ev1, st));
         DQueue h;
-        RTC_CUDA(cudaMemcpyAsync(&h, s->queue, sizeof(h), cudaMemcpyDeviceToHost, st));
+        RTC_CUDA(cudaMemcpyAsync(&h, queue, sizeof(h), cudaMemcpyDeviceToHost, st));
         RTC_CUDA(cudaStreamSynchronize(st));
         float ms = 0.f;
-        RTC_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        RTC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         stats->primary = h.primary;
         stats->shadow = h.shadow;
         stats->reflect = h.reflect;
@@ -270,40 +304,40 @@ static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
 
 int render_device(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d_rgba8, void* d_rgb_f64, void* stream,
                   LaunchStats* stats, std::string* err) {
-    std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lk(s->mu());
     RTC_CUDA(cudaSetDevice(s->device));
     return launch(s, cam, rows, d_rgba8, d_rgb_f64, (cudaStream_t)stream, stats, err);
 }
 
 int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* rgba8, double* rgb_f64,
                 LaunchStats* stats, std::string* err) {
-    std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lk(s->mu());
     RTC_CUDA(cudaSetDevice(s->device));
     const size_t px = (size_t)rows.local_rows * cam.hsize;
-    if (rgba8 && s->out8_size < px * 4) {
-        if (s->out8) cudaFree(s->out8);
-        s->out8 = nullptr;
-        s->out8_size = 0;
-        RTC_CUDA(cudaMalloc(&s->out8, px * 4));
-        s->out8_size = px * 4;
+    if (rgba8 && s->ctx->out8_size < px * 4) {
+        if (s->ctx->out8) cudaFree(s->ctx->out8);
+        s->ctx->out8 = nullptr;
+        s->ctx->out8_size = 0;
+        RTC_CUDA(cudaMalloc(&s->ctx->out8, px * 4));
+        s->ctx->out8_size = px * 4;
     }
-    if (rgb_f64 && s->out64_size < px * 24) {
-        if (s->out64) cudaFree(s->out64);
-        s->out64 = nullptr;
-        s->out64_size = 0;
-        RTC_CUDA(cudaMalloc(&s->out64, px * 24));
-        s->out64_size = px * 24;
+    if (rgb_f64 && s->ctx->out64_size < px * 24) {
+        if (s->ctx->out64) cudaFree(s->ctx->out64);
+        s->ctx->out64 = nullptr;
+        s->ctx->out64_size = 0;
+        RTC_CUDA(cudaMalloc(&s->ctx->out64, px * 24));
+        s->ctx->out64_size = px * 24;
     }
-    int rc = launch(s, cam, rows, rgba8 ? s->out8 : nullptr, rgb_f64 ? s->out64 : nullptr, s->stream, stats, err);
+    int rc = launch(s, cam, rows, rgba8 ? s->ctx->out8 : nullptr, rgb_f64 ? s->ctx->out64 : nullptr, s->stream, stats, err);
     if (rc) return rc;
-    if (rgba8 && px) RTC_CUDA(cudaMemcpyAsync(rgba8, s->out8, px * 4, cudaMemcpyDeviceToHost, s->stream));
-    if (rgb_f64 && px) RTC_CUDA(cudaMemcpyAsync(rgb_f64, s->out64, px * 24, cudaMemcpyDeviceToHost, s->stream));
+    if (rgba8 && px) RTC_CUDA(cudaMemcpyAsync(rgba8, s->ctx->out8, px * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (rgb_f64 && px) RTC_CUDA(cudaMemcpyAsync(rgb_f64, s->ctx->out64, px * 24, cudaMemcpyDeviceToHost, s->stream));
     RTC_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
 
 int color_at_host(DeviceScene* s, const double* rays, uint64_t n, double* rgb, std::string* err) {
-    std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lk(s->mu());
     if (n == 0) return 0;
     RTC_CUDA(cudaSetDevice(s->device));
     double *d_rays = nullptr, *d_rgb = nullptr;

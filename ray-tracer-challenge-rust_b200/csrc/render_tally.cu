@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) tally_kernel(const __grid_constant__ DSce
 int tally_count() { return T_COUNT; }
 
 int render_tally(DeviceScene* s, const DCamera& cam, const DRows& rows, unsigned long long* counts, std::string* err) {
-    std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lk(s->mu());
     cudaError_t e = cudaSetDevice(s->device);
     unsigned long long* d = nullptr;
     if (e == cudaSuccess) e = cudaMalloc((void**)&d, sizeof(unsigned long long) * (T_COUNT + 1));
