@@ -31,9 +31,16 @@ namespace {
 constexpr int kBlockThreads = RTC_BLOCK_THREADS;
 constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
 constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;
+#ifndef RTC_BLOCKS_PER_SM_PRIMS
+#define RTC_BLOCKS_PER_SM_PRIMS 8
+#endif
+constexpr int kBlocksPerSmPrims = RTC_BLOCKS_PER_SM_PRIMS;
 
 
-__global__ void __launch_bounds__(kBlockThreads, kBlocksPerSm) render_kernel(const __grid_constant__ DScene s,
+// kMinBlocks = CTAs per SM the register allocation must allow: 4 (128 registers) suits BVH traversal, 8 (64 registers,
+// twice the warps to hide FP64 latency) suits scenes that are only a short list of primitives (measured: profiles/).
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const __grid_constant__ DScene s,
                                                                const __grid_constant__ DCamera cam,
                                                                const __grid_constant__ DRows rows,
                                                                uint32_t* __restrict__ out8, double* __restrict__ out64,
@@ -246,6 +253,7 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->view.tri_attr = (const DTriAttr*)(base + off[7]);
     s->view.materials = (const DMaterial*)(base + off[8]);
     s->view.program_count = (int32_t)f.program.size();
+    s->mesh_count = (int)f.meshes.size();
     for (int k = 0; k < 3; k++) {
         s->view.light_pos[k] = f.light_pos[k];
         s->view.light_int[k] = f.light_int[k];
@@ -280,10 +288,17 @@ static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
     const uint64_t tiles = (uint64_t)((cam.hsize + kTileW - 1) / kTileW) * ((rows.local_rows + kTileH - 1) / kTileH);
     const uint64_t warps_per_block = kBlockThreads / 32;
     uint64_t blocks = (tiles + warps_per_block - 1) / warps_per_block;
-    const uint64_t cap = (uint64_t)s->sm_count * kBlocksPerSm;
+    const bool prims_only = s->mesh_count == 0;
+    const int per_sm = prims_only ? kBlocksPerSmPrims : kBlocksPerSm;
+    const uint64_t cap = (uint64_t)s->sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     if (stats) RTC_CUDA(cudaEventRecord(ctx->ev0, st));
-    render_kernel<<<(unsigned)blocks, kBlockThreads, 0, st>>>(s->view, cam, rows, (uint32_t*)d8, (double*)d64, queue);
+    if (prims_only)
+        render_kernel<kBlocksPerSmPrims><<<(unsigned)blocks, kBlockThreads, 0, st>>>(s->view, cam, rows, (uint32_t*)d8,
+                                                                                  (double*)d64, queue);
+    else
+        render_kernel<kBlocksPerSm><<<(unsigned)blocks, kBlockThreads, 0, st>>>(s->view, cam, rows, (uint32_t*)d8,
+                                                                             (double*)d64, queue);
     RTC_CUDA(cudaGetLastError());
     if (stats) {
         RTC_CUDA(cudaEventRecord(ctx->ev1, st));
