@@ -5,8 +5,8 @@
 // padded (kPadRel of the mesh's largest coordinate, ~1e9 ulps) and the device test against them is conservative; which
 // triangle wins is still decided by the exact Moller-Trumbore arithmetic and the (t, DFS leaf) order.
 //
-// Binary tree, binned SAH (kBins bins per axis, all three axes), leaves of <= kLeafMax triangles.  Each 128-byte node
-// carries the boxes of BOTH children, so one node fetch decides two subtrees.  Depth is bounded (median splits past
+// Binary tree, binned SAH (kBins bins per axis, all three axes), leaves of <= kLeafMax triangles.  Each 64-byte node
+// carries the f32 boxes (rounded outward) of BOTH children, so one node fetch decides two subtrees.  Depth is bounded (median splits past
 // kSahDepth) so the device's fixed traversal stack (kBvhStackDepth) cannot overflow.
 #pragma once
 #include <algorithm>
@@ -56,6 +56,18 @@ struct Aabb {
         return dx * dy + dy * dz + dz * dx;
     }
 };
+
+// the largest float <= x / smallest float >= x, then one more step outward (so the f32 box strictly contains the f64 one)
+inline float f32_below(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+    return std::nextafterf(f, -std::numeric_limits<float>::infinity());
+}
+inline float f32_above(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+    return std::nextafterf(f, std::numeric_limits<float>::infinity());
+}
 
 struct BvhBuilder {
     const std::vector<BvhTri>& tris;
@@ -163,12 +175,11 @@ struct BvhBuilder {
         Sub r = build(mid, end, depth + 1);
         DBvhNode& nd = nodes[me];
         for (int a = 0; a < 3; a++) {
-            nd.lo0[a] = l.box.lo[a] - pad; nd.hi0[a] = l.box.hi[a] + pad;
-            nd.lo1[a] = r.box.lo[a] - pad; nd.hi1[a] = r.box.hi[a] + pad;
+            nd.lo0[a] = f32_below(l.box.lo[a] - pad); nd.hi0[a] = f32_above(l.box.hi[a] + pad);
+            nd.lo1[a] = f32_below(r.box.lo[a] - pad); nd.hi1[a] = f32_above(r.box.hi[a] + pad);
         }
         nd.child0 = l.index; nd.count0 = l.leaf ? l.count : 0;
         nd.child1 = r.index; nd.count1 = r.leaf ? r.count : 0;
-        nd.pad[0] = nd.pad[1] = 0.;
         return Sub{false, me, 0, box};
     }
 };
@@ -178,11 +189,18 @@ struct BvhBuilder {
 // Appends the mesh's nodes to `nodes`; fills `order` (slot -> input triangle; the caller stores triangles in this order
 // starting at global slot `tri_base`).  Returns the root node index, or -1 when the mesh is small enough to scan.
 inline int32_t build_bvh(const std::vector<BvhTri>& tris, std::vector<DBvhNode>& nodes, int32_t tri_base,
-                         std::vector<uint32_t>& order, int* max_depth) {
+                         std::vector<uint32_t>& order, int* max_depth, double* max_abs_out = nullptr) {
     const uint32_t n = (uint32_t)tris.size();
     order.resize(n);
     for (uint32_t i = 0; i < n; i++) order[i] = i;
     if (max_depth) *max_depth = 0;
+    if (max_abs_out) {
+        double m = 0.;
+        for (uint32_t i = 0; i < n; i++)
+            for (int v = 0; v < 3; v++)
+                for (int a = 0; a < 3; a++) m = std::max(m, std::fabs(tris[i].p[v][a]));
+        *max_abs_out = m;
+    }
     if (n <= (uint32_t)kLeafMax) return -1;
     detail::BvhBuilder b{tris, nodes, tri_base, order, {}, {}, {}, {}, 0., 0};
     b.boxes.resize(n);

@@ -9,7 +9,7 @@
 //   prims[]    : tag-switched non-triangle leaves (sphere/plane/cube/cylinder/cone).
 //   gates[]    : world-space boxes exactly as Bounds::new computes them (bounds.rs:50-125).
 //   meshes[]   : per mesh: transform, BVH root, triangle range.
-//   bvh[]      : 128-byte nodes holding BOTH children's boxes (padded, conservative) so one fetch tests two boxes.
+//   bvh[]      : 64-byte nodes holding BOTH children's boxes (f32, padded and rounded outward) so one fetch tests two boxes.
 //   tris[]     : p1,e1,e2 of each triangle in BVH-leaf order + its DFS leaf index (the reference's tie-break order).
 //   tri_attr[] : per triangle (same order): precomputed world normal (shape.rs:509-518 is point-independent) + material.
 //   materials[]: material.rs:4-14 + flattened pattern with rows 0..2 of the pattern inverse.
@@ -29,22 +29,33 @@ struct DProgramNode {
 struct DXform {
     double m[12];  // inverse, rows 0..2
 };
-struct DPrim {
+// reject: 0 = always run the exact test; 1 = a ray that misses the padded world box [blo,bhi] cannot intersect the
+// leaf; 2 = same, but valid only when every object-space direction component is clearly >= EPSILON (the cube's
+// check_axis treats smaller ones as parallel, shape.rs:593-599), decided in f32 with m32 (rows of the inverse's 3x3) and
+// the per-row rounding slack k.
+struct alignas(16) DPrim {
     int32_t kind, material, xform, capped;
     double minimum, maximum;
     int32_t leaf;  // DFS leaf index
-    int32_t pad;
+    int32_t reject;
+    float k[3];
+    float m32[9];
+    float padf[2];  // keeps blo 16-byte aligned: the record is read with 16-byte loads
+    double blo[3], bhi[3];
 };
+static_assert(sizeof(DPrim) == 144, "DPrim layout");
 struct DGate {
     double lo[3], hi[3];
 };
 struct DMesh {
     int32_t xform, root, tri_base, tri_count;  // root < 0: no BVH (tiny mesh), scan [tri_base, tri_base + tri_count)
+    float extent;                              // max |coordinate| of the mesh in object space (f32 slab error bound)
+    int32_t pad[3];
 };
-struct alignas(128) DBvhNode {
-    double lo0[3], hi0[3], lo1[3], hi1[3];
+// f32 boxes rounded OUTWARD from the padded f64 boxes: 64 bytes hold both children, one fetch decides two subtrees.
+struct alignas(64) DBvhNode {
+    float lo0[3], hi0[3], lo1[3], hi1[3];
     int32_t child0, count0, child1, count1;  // count > 0: leaf, child = first triangle slot; count == 0: inner node
-    double pad[2];
 };
 struct alignas(16) DTri {
     double p1[3], e1[3], e2[3];
@@ -75,7 +86,7 @@ struct DScene {
     const DTriAttr* tri_attr;
     const DMaterial* materials;
     int32_t program_count;
-    int32_t pad;
+    int32_t reject_prims;  // how many prims carry a reject box (0: the walker skips the per-ray set-up for them)
     double light_pos[3];
     double light_int[3];
 };

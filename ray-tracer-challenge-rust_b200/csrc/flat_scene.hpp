@@ -19,6 +19,7 @@ struct FlatScene {
     std::vector<DMaterial> materials;
     double light_pos[3] = {0, 0, 0}, light_int[3] = {0, 0, 0};
     uint64_t leaf_count = 0;
+    int32_t reject_prims = 0;
     int bvh_max_depth = 0;
 };
 

@@ -186,6 +186,61 @@ class Flattener {
         }
     }
 
+    static float f32_above_(double x) {
+        float f = (float)x;
+        if ((double)f < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+        return std::nextafterf(f, std::numeric_limits<float>::infinity());
+    }
+
+    // A conservative world-space box for a bounded leaf, so the walker can skip its exact test for rays that pass far
+    // away (own structure, not reference arithmetic: it may only skip tests whose exact result is "no intersection").
+    //   sphere / cube : the unit cube [-1,1]^3 (shape.rs:258-319)
+    //   cylinder      : radius 1 walls for min < y < max; caps accept x^2 + z^2 <= |y| (shape.rs:584), i.e. radius
+    //                   sqrt(|y|) — the box takes the larger of the two; needs finite min and max
+    //   cone, plane   : no box (the cone's a ~ 0 branch reports an intersection without a y-range check, shape.rs:363-368)
+    // The cube's check_axis treats |direction| < EPSILON as parallel (shape.rs:593-599), which reports intersections
+    // that drift outside the true cube by up to t * EPSILON; for cubes the box is therefore only used when all three
+    // object-space direction components are clearly >= EPSILON, which the walker decides in f32 from m32 and k.
+    void reject_box(const rtc_shape_desc& s, DPrim& p) {
+        double r = 1.0, ylo = -1.0, yhi = 1.0;
+        if (s.kind == RTC_SPHERE || s.kind == RTC_CUBE) {
+        } else if (s.kind == RTC_CYLINDER && std::isfinite(s.minimum) && std::isfinite(s.maximum)) {
+            ylo = std::fmin(s.minimum, s.maximum);
+            yhi = std::fmax(s.minimum, s.maximum);
+            if (s.capped) r = std::fmax(1.0, std::sqrt(std::fmax(std::fabs(s.minimum), std::fabs(s.maximum))));
+        } else {
+            return;
+        }
+        const rtc_transform_desc& td = d_.transforms[s.transform];
+        const Mat4 t = Mat4::from(td.transform);
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, mag = 0.;
+        for (int c = 0; c < 8; c++) {
+            Vec4 w = mul(t, point((c & 1) ? r : -r, (c & 2) ? yhi : ylo, (c & 4) ? r : -r));
+            const double v[3] = {w.x, w.y, w.z};
+            for (int a = 0; a < 3; a++) {
+                if (!std::isfinite(v[a])) return;
+                lo[a] = std::fmin(lo[a], v[a]);
+                hi[a] = std::fmax(hi[a], v[a]);
+                mag = std::fmax(mag, std::fabs(v[a]));
+            }
+        }
+        const double pad = 1e-7 * std::fmax(mag, 1e-30);
+        for (int a = 0; a < 3; a++) {
+            p.blo[a] = lo[a] - pad;
+            p.bhi[a] = hi[a] + pad;
+        }
+        p.reject = (s.kind == RTC_CUBE) ? 2 : 1;
+        for (int a = 0; a < 3; a++) {
+            double l1 = 0.;
+            for (int c = 0; c < 3; c++) {
+                p.m32[a * 3 + c] = (float)td.inverse[a * 4 + c];
+                l1 += std::fabs(td.inverse[a * 4 + c]);
+            }
+            // |f32 dot - exact dot| <= ~4 * 2^-24 * l1 * max|d|; k carries an 8x margin on top (2^-19)
+            p.k[a] = f32_above_(l1 * 1.9073486328125e-06);
+        }
+    }
+
     // ---- emission ---------------------------------------------------------------------------------------------------
     bool same_inverse(uint32_t a, uint32_t b) const {
         return std::memcmp(d_.transforms[d_.shapes[a].transform].inverse, d_.transforms[d_.shapes[b].transform].inverse,
@@ -214,6 +269,8 @@ class Flattener {
                 p.minimum = s.minimum;
                 p.maximum = s.maximum;
                 p.leaf = (int32_t)next_leaf_++;
+                reject_box(s, p);
+                if (p.reject) out_.reject_prims++;
                 out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, 0});
                 out_.prims.push_back(p);
                 i++;
@@ -259,7 +316,10 @@ class Flattener {
         m.tri_count = (int32_t)n;
         std::vector<uint32_t> order;
         int depth = 0;
-        m.root = build_bvh(bt, out_.bvh, m.tri_base, order, &depth);
+        double max_abs = 0.;
+        m.root = build_bvh(bt, out_.bvh, m.tri_base, order, &depth, &max_abs);
+        m.extent = f32_above_(max_abs * (1.0 + 2.0 * kPadRel));
+        m.pad[0] = m.pad[1] = m.pad[2] = 0;
         if (depth > out_.bvh_max_depth) out_.bvh_max_depth = depth;
         const uint32_t leaf0 = next_leaf_;
         next_leaf_ += n;

@@ -26,20 +26,20 @@ namespace {
 #define RTC_BLOCK_THREADS 128
 #endif
 #ifndef RTC_BLOCKS_PER_SM
-#define RTC_BLOCKS_PER_SM 4
+#define RTC_BLOCKS_PER_SM 6
 #endif
 constexpr int kBlockThreads = RTC_BLOCK_THREADS;
 constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
 constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;
 #ifndef RTC_BLOCKS_PER_SM_PRIMS
-#define RTC_BLOCKS_PER_SM_PRIMS 8
+#define RTC_BLOCKS_PER_SM_PRIMS 6
 #endif
 constexpr int kBlocksPerSmPrims = RTC_BLOCKS_PER_SM_PRIMS;
 
 
-// kMinBlocks = CTAs per SM the register allocation must allow: 4 (128 registers) suits BVH traversal, 8 (64 registers,
-// twice the warps to hide FP64 latency) suits scenes that are only a short list of primitives (measured: profiles/).
-template <int kMinBlocks>
+// kMinBlocks = CTAs per SM the register allocation must allow (6 -> 80 registers, 24 warps/SM: the measured optimum of
+// the launch-shape sweeps in profiles/: more warps hide FP64 latency and fetch bubbles, fewer registers spill).
+template <int kMinBlocks, int kFeatures>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const __grid_constant__ DScene s,
                                                                const __grid_constant__ DCamera cam,
                                                                const __grid_constant__ DRows rows,
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
             const uint32_t py = (rows.band_first + band * rows.band_stride) * rows.band_rows + (lrow % rows.band_rows);
             const Ray ray = ray_for_pixel(cam, px, py);
             primary++;
-            const V3 c = color_at(s, ray, rc, tl);
+            const V3 c = color_at<kFeatures>(s, ray, rc, tl);
             const size_t o = (size_t)lrow * cam.hsize + px;
             if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
             if (out64) {
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kBlockThreads) color_at_kernel(const __grid_co
     Ray r{v3(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]), v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};
     RayCounters rc;
     Tally tl;
-    V3 c = color_at(s, r, rc, tl);
+    V3 c = color_at<FEAT_ALL>(s, r, rc, tl);
     rgb[3 * i + 0] = c.x;
     rgb[3 * i + 1] = c.y;
     rgb[3 * i + 2] = c.z;
@@ -253,7 +253,10 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->view.tri_attr = (const DTriAttr*)(base + off[7]);
     s->view.materials = (const DMaterial*)(base + off[8]);
     s->view.program_count = (int32_t)f.program.size();
+    s->view.reject_prims = f.reject_prims;
     s->mesh_count = (int)f.meshes.size();
+    s->prim_count = (int)f.prims.size();
+    s->gate_count = (int)f.gates.size();
     for (int k = 0; k < 3; k++) {
         s->view.light_pos[k] = f.light_pos[k];
         s->view.light_int[k] = f.light_int[k];
@@ -293,12 +296,21 @@ static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
     const uint64_t cap = (uint64_t)s->sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     if (stats) RTC_CUDA(cudaEventRecord(ctx->ev0, st));
-    if (prims_only)
-        render_kernel<kBlocksPerSmPrims><<<(unsigned)blocks, kBlockThreads, 0, st>>>(s->view, cam, rows, (uint32_t*)d8,
-                                                                                  (double*)d64, queue);
+    // instantiations by scene content: the kernel for a scene without meshes (or without primitives/gates) carries none
+    // of that code
+    const unsigned g = (unsigned)blocks;
+    uint32_t* o8 = (uint32_t*)d8;
+    double* o64 = (double*)d64;
+    if (prims_only && s->gate_count == 0)
+        render_kernel<kBlocksPerSmPrims, FEAT_PRIMS><<<g, kBlockThreads, 0, st>>>(s->view, cam, rows, o8, o64, queue);
+    else if (prims_only)
+        render_kernel<kBlocksPerSmPrims, FEAT_PRIMS | FEAT_GATES><<<g, kBlockThreads, 0, st>>>(s->view, cam, rows, o8,
+                                                                                            o64, queue);
+    else if (s->prim_count == 0)
+        render_kernel<kBlocksPerSm, FEAT_MESHES | FEAT_GATES><<<g, kBlockThreads, 0, st>>>(s->view, cam, rows, o8, o64,
+                                                                                        queue);
     else
-        render_kernel<kBlocksPerSm><<<(unsigned)blocks, kBlockThreads, 0, st>>>(s->view, cam, rows, (uint32_t*)d8,
-                                                                             (double*)d64, queue);
+        render_kernel<kBlocksPerSm, FEAT_ALL><<<g, kBlockThreads, 0, st>>>(s->view, cam, rows, o8, o64, queue);
     RTC_CUDA(cudaGetLastError());
     if (stats) {
         RTC_CUDA(cudaEventRecord(ctx->ev1, st));
