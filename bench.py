@@ -43,6 +43,8 @@ def parse_args():
     p.add_argument("--width", type=int, default=None)
     p.add_argument("--height", type=int, default=None)
     p.add_argument("--band-rows", type=int, default=8)
+    p.add_argument("--exchange", default="auto", choices=["auto", "peer", "gather"],
+                   help="N > 1: how bands reach rank 0 (peer = direct NVLink stores, gather = NCCL gather)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the informative per-config table")
     return p.parse_args()
@@ -193,7 +195,7 @@ def run_b200(args):
 
     w, h = workload_size(args)
     world, cam = rtc.build_scene(args.workload, w, h)
-    renderer = multi.ShardedRenderer(world, cam, rank, world_size, local_rank, args.band_rows)
+    renderer = multi.ShardedRenderer(world, cam, rank, world_size, local_rank, args.band_rows, args.exchange)
     info = world.scene_info(local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -244,7 +246,7 @@ def run_b200(args):
     for _ in range(args.steps):
         flush.zero_()
         s2 = rtc.Stats()
-        cam.render_device(world, d_rgba8=renderer.local.data_ptr(), rows=renderer.rows,
+        cam.render_device(world, d_rgba8=renderer.out_ptr(), rows=renderer.rows,
                           stream=torch.cuda.current_stream().cuda_stream, stats=s2, device=local_rank)
         kernel_ms.append(s2.device_ms)
     kernel_ms_avg = sum(kernel_ms) / len(kernel_ms)
@@ -262,13 +264,7 @@ def run_b200(args):
     def e2e_step():
         scene = C.c_void_p()
         api.check(api.scene_create(desc, local_rank, C.byref(scene)))
-        api.check(api.render_device(scene, C.byref(cdesc), C.byref(renderer.rows), C.c_void_p(renderer.local.data_ptr()),
-                                    None, C.c_void_p(stream) if stream else None, 0, None))
-        if world_size > 1:
-            dist.gather(renderer.local, list(renderer.gathered.unbind(0)) if rank == 0 else None, dst=0)
-            frame = renderer.plan.assemble(renderer.gathered) if rank == 0 else None
-        else:
-            frame = renderer.local[:h]
+        frame = renderer.render(scene=scene)
         if rank == 0:
             host_frame.copy_(frame, non_blocking=True)
         torch.cuda.synchronize()
@@ -288,6 +284,8 @@ def run_b200(args):
 
     if rank != 0:
         if world_size > 1:
+            dist.barrier()  # rank 0 still reads the shared frame until its report is out
+            renderer.close()
             dist.destroy_process_group()
         return 0
 
@@ -313,7 +311,7 @@ def run_b200(args):
     except OSError:
         pass
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    rows_local = cam.rows_count(renderer.rows)
+    rows_local = renderer.plan.local_rows(rank)
     alg_bytes = 4 * w * rows_local + info["device_bytes"]
     hbm_achieved = alg_bytes / (kernel_ms_avg * 1e-3) / 1e9
     tally = roofline.frame_tally(world, cam, renderer.rows, local_rank)
@@ -327,8 +325,11 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload} {w}x{h}", "scene": args.workload, "hsize": w, "vsize": h,
                    "rays_per_frame": {"primary": rays[0], "shadow": rays[1], "reflect": rays[2], "refract": rays[3]},
-                   "sharding": f"cyclic {renderer.plan.band_rows}-row bands over {world_size} rank(s), NCCL gather to rank 0"
+                   "sharding": (f"cyclic {renderer.plan.band_rows}-row bands over {world_size} ranks; "
+                                + ("kernels store straight into rank 0's frame over NVLink peer mapping, one barrier"
+                                   if renderer.mode == "peer" else "NCCL gather to rank 0 + one interleaving copy"))
                    if world_size > 1 else "single GPU, one launch per frame",
+                   "exchange": renderer.mode,
                    "l2": "256 MiB device memset between steps, outside the per-step CUDA-event brackets",
                    "flattened": info},
         "frame_ms": ms_per_step, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
@@ -383,6 +384,8 @@ def run_b200(args):
 
     emit(line)
     if world_size > 1:
+        dist.barrier()
+        renderer.close()
         dist.destroy_process_group()
     return 0
 

@@ -108,7 +108,13 @@ typedef struct rtc_camera_desc {
  * {band_rows = vsize, band_first = 0, band_stride = 1} (or a NULL pointer) is the whole frame. */
 typedef struct rtc_rows {
     uint32_t band_rows, band_first, band_stride;
+    uint32_t layout; /* RTC_ROWS_COMPACT: the output buffers hold only this call's rows, packed;
+                        RTC_ROWS_FRAME: the output pointers address the WHOLE frame (vsize rows) and each rendered row is
+                        written at its frame position — e.g. a frame buffer on another GPU mapped over NVLink, so the
+                        ranks of a sharded render store straight into rank 0's frame and no gather step is needed */
 } rtc_rows;
+#define RTC_ROWS_COMPACT 0u
+#define RTC_ROWS_FRAME 1u
 
 /* Work counters of one render (exact; the numerators of Mrays/s). */
 typedef struct rtc_stats {
@@ -163,6 +169,16 @@ int rtc_measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops);
 
 const char* rtc_last_error(void);
 int rtc_device_count(void);
+/* cudaDeviceEnablePeerAccess(peer) from `device` (no-op if already enabled): lets kernels launched on `device` store into
+ * buffers that live on `peer` (RTC_ROWS_FRAME renders into another GPU's frame). */
+int rtc_enable_peer_access(int device, int peer);
+/* A frame buffer on `device` that other PROCESSES (one per GPU) can map over NVLink: create() allocates it and returns a
+ * 64-byte CUDA IPC handle; open() (called with the caller's own device) maps it into that device's address space with
+ * peer access enabled and returns a pointer its kernels can store through (RTC_ROWS_FRAME); close() unmaps (owner = 0) or
+ * frees (owner = 1). */
+int rtc_frame_share_create(int device, uint64_t bytes, void** d_ptr, uint8_t handle64[64]);
+int rtc_frame_share_open(int device, const uint8_t handle64[64], void** d_ptr);
+int rtc_frame_share_close(int device, void* d_ptr, int owner);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * 2. HOST MIRROR of the reference API (C++ inside; the Rust host in the reference)

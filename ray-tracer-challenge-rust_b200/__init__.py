@@ -162,7 +162,8 @@ class Camera(CameraHandle):
         """rtc_render_device: DEVICE pointers (ints, e.g. torch tensor .data_ptr()), asynchronous on `stream` (a
         cudaStream_t as int).  With `stats` the call synchronises the stream and fills it."""
         d = self.desc()
-        self.api.check(self.api.render_device(world.scene(device), C.byref(d),
+        scene = world.scene(device) if hasattr(world, "scene") else world  # a World, or a raw rtc_scene handle
+        self.api.check(self.api.render_device(scene, C.byref(d),
                                               C.byref(rows) if rows is not None else None,
                                               C.c_void_p(d_rgba8) if d_rgba8 else None,
                                               C.c_void_p(d_rgb_f64) if d_rgb_f64 else None,

@@ -34,7 +34,9 @@ class CameraDesc(C.Structure):
 
 class Rows(C.Structure):
     """rtc_rows"""
-    _fields_ = [("band_rows", C.c_uint32), ("band_first", C.c_uint32), ("band_stride", C.c_uint32)]
+    _fields_ = [("band_rows", C.c_uint32), ("band_first", C.c_uint32), ("band_stride", C.c_uint32),
+                ("layout", C.c_uint32)]
+    COMPACT, FRAME = 0, 1
 
 
 class Stats(C.Structure):

@@ -29,6 +29,10 @@ class RtcApi(BuilderApi):
         f, vp = self._fn, C.c_void_p
         u8p = C.POINTER(C.c_uint8)
         f("device_count", C.c_int)
+        f("enable_peer_access", C.c_int, C.c_int, C.c_int)
+        f("frame_share_create", C.c_int, C.c_int, C.c_uint64, C.POINTER(vp), C.c_char_p)
+        f("frame_share_open", C.c_int, C.c_int, C.c_char_p, C.POINTER(vp))
+        f("frame_share_close", C.c_int, C.c_int, vp, C.c_int)
         f("scene_create", C.c_int, vp, C.c_int, C.POINTER(vp))
         f("scene_destroy", None, vp)
         f("scene_info", C.c_int, vp, c_u64_p)

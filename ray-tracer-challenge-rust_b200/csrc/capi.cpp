@@ -37,8 +37,11 @@ int to_drows(const rtc_camera_desc& cam, const rtc_rows* rows, DRows* out) {
         out->band_first = 0;
         out->band_stride = 1;
         out->local_rows = cam.vsize;
+        out->frame_layout = 0;
         return RTC_OK;
     }
+    if (rows->layout > RTC_ROWS_FRAME) return set_err(RTC_ERR_INVALID, "unknown rtc_rows.layout");
+    out->frame_layout = rows->layout;
     if (rows->band_rows == 0 || rows->band_stride == 0) return set_err(RTC_ERR_INVALID, "band_rows and band_stride must be > 0");
     out->band_rows = rows->band_rows;
     out->band_first = rows->band_first;
@@ -98,6 +101,28 @@ struct rtc_canvas {
 extern "C" {
 
 const char* rtc_last_error(void) { return g_err.c_str(); }
+int rtc_enable_peer_access(int device, int peer) {
+    std::string e;
+    if (enable_peer_access(device, peer, &e) != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+int rtc_frame_share_create(int device, uint64_t bytes, void** d_ptr, uint8_t handle64[64]) {
+    if (!d_ptr || !handle64) return set_err(RTC_ERR_INVALID, "null argument");
+    std::string e;
+    if (frame_share_create(device, bytes, d_ptr, handle64, &e) != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+int rtc_frame_share_open(int device, const uint8_t handle64[64], void** d_ptr) {
+    if (!d_ptr || !handle64) return set_err(RTC_ERR_INVALID, "null argument");
+    std::string e;
+    if (frame_share_open(device, handle64, d_ptr, &e) != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+int rtc_frame_share_close(int device, void* d_ptr, int owner) {
+    std::string e;
+    if (frame_share_close(device, d_ptr, owner, &e) != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
 int rtc_device_count(void) {
     std::string e;
     int n = cuda_device_count(&e);
@@ -147,6 +172,7 @@ int rtc_render(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_
     if (rc != RTC_OK) return rc;
     LaunchStats ls;
     std::string e;
+    if (dr.frame_layout) return set_err(RTC_ERR_INVALID, "RTC_ROWS_FRAME needs device buffers (rtc_render_device)");
     rc = render_host(scene->dev, to_dcamera(*camera), dr, rgba8_out, rgb_f64_out, stats ? &ls : nullptr, &e);
     if (rc != 0) return set_err(RTC_ERR_CUDA, e);
     fill_stats(ls, stats);

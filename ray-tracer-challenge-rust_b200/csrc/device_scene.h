@@ -97,6 +97,7 @@ struct DCamera {
 };
 struct DRows {
     uint32_t band_rows, band_first, band_stride, local_rows;  // local_rows = rows this call renders
+    uint32_t frame_layout, pad[3];                            // 1: outputs are addressed by FRAME row, not by local row
 };
 struct DStats {
     unsigned long long primary, shadow, reflect, refract;

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
             const Ray ray = ray_for_pixel(cam, px, py);
             primary++;
             const V3 c = color_at<kFeatures>(s, ray, rc, tl);
-            const size_t o = (size_t)lrow * cam.hsize + px;
+            const size_t o = (size_t)(rows.frame_layout ? py : lrow) * cam.hsize + px;
             if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
             if (out64) {
                 out64[3 * o + 0] = c.x;
@@ -143,6 +143,56 @@ size_t slab_bytes(const std::vector<T>& v) {
 
 }  // namespace
 
+
+int enable_peer_access(int device, int peer, std::string* err) {
+    if (device == peer) return 0;
+    RTC_CUDA(cudaSetDevice(device));
+    int can = 0;
+    RTC_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) {
+        if (err) *err = "devices cannot access each other's memory";
+        return -3;
+    }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return 0;
+    }
+    RTC_CUDA(e);
+    return 0;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+int frame_share_create(int device, uint64_t bytes, void** d_ptr, unsigned char* handle64, std::string* err) {
+    RTC_CUDA(cudaSetDevice(device));
+    void* p = nullptr;
+    RTC_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        if (err) *err = cuda_err("cudaIpcGetMemHandle", e);
+        return -3;
+    }
+    std::memcpy(handle64, &h, 64);
+    *d_ptr = p;
+    return 0;
+}
+int frame_share_open(int device, const unsigned char* handle64, void** d_ptr, std::string* err) {
+    RTC_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    // opened with the CALLER's device current: the mapping lands in that device's address space and peer access to the
+    // owning device is enabled on the way
+    RTC_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int frame_share_close(int device, void* d_ptr, int owner, std::string* err) {
+    RTC_CUDA(cudaSetDevice(device));
+    if (owner) RTC_CUDA(cudaFree(d_ptr));
+    else RTC_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
 
 int cuda_device_count(std::string* err) {
     int n = 0;

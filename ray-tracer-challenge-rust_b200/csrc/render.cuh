@@ -20,6 +20,10 @@ struct LaunchStats {
 };
 
 int cuda_device_count(std::string* err);
+int enable_peer_access(int device, int peer, std::string* err);
+int frame_share_create(int device, uint64_t bytes, void** d_ptr, unsigned char* handle64, std::string* err);
+int frame_share_open(int device, const unsigned char* handle64, void** d_ptr, std::string* err);
+int frame_share_close(int device, void* d_ptr, int owner, std::string* err);
 int device_scene_create(const FlatScene& flat, int device, DeviceScene** out, std::string* err);
 void device_scene_destroy(DeviceScene* s);
 uint64_t device_scene_bytes(const DeviceScene* s);

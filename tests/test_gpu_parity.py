@@ -101,6 +101,21 @@ def test_row_bands_tile_the_frame(rtc):
         assert np.array_equal(out, full)
 
 
+def test_frame_layout_rows_write_in_place(rtc):
+    """RTC_ROWS_FRAME: each band call stores its rows at their frame position in ONE shared buffer (what the multi-GPU
+    peer path does with rank 0's frame mapped over NVLink)."""
+    import torch
+    world, cam = rtc.build_scene("hexagon", 200, 120)
+    full = np.empty((120, 200, 4), dtype=np.uint8)
+    cam.render_into(world, rgba8=full)
+    frame = torch.zeros((120, 200, 4), dtype=torch.uint8, device="cuda:0")
+    for first in range(3):
+        cam.render_device(world, d_rgba8=frame.data_ptr(), rows=rtc.Rows(8, first, 3, rtc.Rows.FRAME),
+                          stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(frame.cpu().numpy(), full)
+
+
 def test_device_output_and_torch_stream(rtc):
     """rtc_render_device writes into torch-owned device memory on torch's current stream."""
     import torch
