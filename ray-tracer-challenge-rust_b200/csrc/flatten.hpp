@@ -70,6 +70,8 @@ class Flattener {
     std::vector<uint32_t> end_;  // end_[i] = index just past shape i's subtree
     std::map<XKey, int32_t> xform_ids_;
     uint32_t next_leaf_ = 0;
+    int32_t parent_gate_ = -1;  // gate of the group being emitted, if this node is its ONLY child
+    bool only_child_ = false;
 
     [[noreturn]] static void fail(int code, const std::string& m) { throw FlattenError{code, m}; }
     static void check(bool c, const char* m) {
@@ -289,10 +291,29 @@ class Flattener {
         DGate g;
         g.lo[0] = b.min.x; g.lo[1] = b.min.y; g.lo[2] = b.min.z;
         g.hi[0] = b.max.x; g.hi[1] = b.max.y; g.hi[2] = b.max.z;
+        // group{ group{...} } with bit-identical boxes (what Parser::obj_to_group builds for an OBJ without `g` lines,
+        // obj_file.rs:120-128: the inner box already contains the origin the outer one is seeded with): both gates give
+        // the same verdict for every ray, so one test stands for both
+        if (parent_gate_ >= 0 && only_child_ && std::memcmp(&out_.gates[parent_gate_], &g, sizeof(g)) == 0) {
+            const int32_t saved_parent = parent_gate_;
+            const bool saved_only = only_child_;
+            only_child_ = (d_.shapes[i].child_count == 1);
+            emit_children(i + 1, end_[i]);
+            parent_gate_ = saved_parent;
+            only_child_ = saved_only;
+            out_.merged_gates++;
+            return;
+        }
         size_t at = out_.program.size();
         out_.program.push_back(DProgramNode{NODE_GATE, (int32_t)out_.gates.size(), 0, 0});
         out_.gates.push_back(g);
+        const int32_t saved_parent = parent_gate_;
+        const bool saved_only = only_child_;
+        parent_gate_ = (int32_t)out_.gates.size() - 1;
+        only_child_ = (d_.shapes[i].child_count == 1);
         emit_children(i + 1, end_[i]);
+        parent_gate_ = saved_parent;
+        only_child_ = saved_only;
         out_.program[at].skip = (int32_t)out_.program.size();
     }
 

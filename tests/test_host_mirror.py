@@ -162,10 +162,10 @@ def test_flattening_of_the_configs(rtc):
     assert (lo <= 0).all() and (hi >= 0).all() and hi[0] > 2.5 and lo[0] < -2.5
     w, _ = rtc.build_scene("teapot", 8, 4)
     info = w.flatten_info(want_gates=True)
-    assert info["leaves"] == 6320 and info["mesh_triangles"] == 6320 and info["meshes"] == 1 and info["gates"] == 2
+    # obj_to_group nests group{default_group{...}}: both groups have the same box, so the flattener
+    # lets one gate stand for both
+    assert info["leaves"] == 6320 and info["mesh_triangles"] == 6320 and info["meshes"] == 1 and info["gates"] == 1
     assert info["bvh_max_depth"] <= 40 and info["transforms"] == 1
-    # obj_to_group nests group{default_group{...}}: both gates are the same box
-    assert np.array_equal(info["gate_boxes"][0], info["gate_boxes"][1])
     w, _ = rtc.build_scene("pumpkin", 8, 4)
     g = w.flatten_info(want_gates=True)["gate_boxes"][0]
     assert g[0] <= 0 <= g[3] and g[1] <= 0 <= g[4] and g[2] <= 0 <= g[5]  # origin-seeded even though the mesh is far away

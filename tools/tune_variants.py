@@ -15,14 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "ray-tracer-challenge-rust_b200", "variants")
 VARIANTS = {
-    "t128_b3": ["RTC_BLOCK_THREADS=128", "RTC_BLOCKS_PER_SM=3", "RTC_BLOCKS_PER_SM_PRIMS=3"],
     "t128_b4": ["RTC_BLOCK_THREADS=128", "RTC_BLOCKS_PER_SM=4", "RTC_BLOCKS_PER_SM_PRIMS=4"],
     "t128_b5": ["RTC_BLOCK_THREADS=128", "RTC_BLOCKS_PER_SM=5", "RTC_BLOCKS_PER_SM_PRIMS=5"],
     "t128_b6": ["RTC_BLOCK_THREADS=128", "RTC_BLOCKS_PER_SM=6", "RTC_BLOCKS_PER_SM_PRIMS=6"],
     "t128_b8": ["RTC_BLOCK_THREADS=128", "RTC_BLOCKS_PER_SM=8", "RTC_BLOCKS_PER_SM_PRIMS=8"],
-    "t64_b8": ["RTC_BLOCK_THREADS=64", "RTC_BLOCKS_PER_SM=8", "RTC_BLOCKS_PER_SM_PRIMS=8"],
-    "t64_b12": ["RTC_BLOCK_THREADS=64", "RTC_BLOCKS_PER_SM=12", "RTC_BLOCKS_PER_SM_PRIMS=12"],
-    "t256_b2": ["RTC_BLOCK_THREADS=256", "RTC_BLOCKS_PER_SM=2", "RTC_BLOCKS_PER_SM_PRIMS=2"],
 }
 SCENES = [("table", 1920, 1080), ("teapot", 1920, 1080), ("hexagon", 1920, 960), ("cow_teddy", 3840, 2160),
           ("pumpkin", 3840, 2160)]
