@@ -40,10 +40,9 @@ struct alignas(16) DPrim {
     int32_t reject;
     float k[3];
     float m32[9];
-    float padf[2];  // keeps blo 16-byte aligned: the record is read with 16-byte loads
-    double blo[3], bhi[3];
+    float blo[3], bhi[3];  // padded world box, f32 rounded outward (tested like a BVH box)
 };
-static_assert(sizeof(DPrim) == 144, "DPrim layout");
+static_assert(sizeof(DPrim) == 112, "DPrim layout: read with 16-byte loads");
 struct DGate {
     double lo[3], hi[3];
 };
@@ -87,6 +86,8 @@ struct DScene {
     const DMaterial* materials;
     int32_t program_count;
     int32_t reject_prims;  // how many prims carry a reject box (0: the walker skips the per-ray set-up for them)
+    float reject_extent;   // max |coordinate| over those boxes (f32 slab error bound)
+    int32_t pad0;
     double light_pos[3];
     double light_int[3];
 };

@@ -20,6 +20,7 @@ struct FlatScene {
     double light_pos[3] = {0, 0, 0}, light_int[3] = {0, 0, 0};
     uint64_t leaf_count = 0;
     int32_t reject_prims = 0;
+    float reject_extent = 0.f;
     int32_t merged_gates = 0;  // nested single-child groups whose identical box shares the parent's gate
     int bvh_max_depth = 0;
 };

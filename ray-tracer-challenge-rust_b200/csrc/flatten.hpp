@@ -228,8 +228,9 @@ class Flattener {
         }
         const double pad = 1e-7 * std::fmax(mag, 1e-30);
         for (int a = 0; a < 3; a++) {
-            p.blo[a] = lo[a] - pad;
-            p.bhi[a] = hi[a] + pad;
+            p.blo[a] = detail::f32_below(lo[a] - pad);
+            p.bhi[a] = detail::f32_above(hi[a] + pad);
+            out_.reject_extent = std::fmax(out_.reject_extent, std::fmax(std::fabs(p.blo[a]), std::fabs(p.bhi[a])));
         }
         p.reject = (s.kind == RTC_CUBE) ? 2 : 1;
         for (int a = 0; a < 3; a++) {

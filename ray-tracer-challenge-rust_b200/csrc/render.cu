@@ -304,6 +304,7 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->view.materials = (const DMaterial*)(base + off[8]);
     s->view.program_count = (int32_t)f.program.size();
     s->view.reject_prims = f.reject_prims;
+    s->view.reject_extent = f.reject_extent;
     s->mesh_count = (int)f.meshes.size();
     s->prim_count = (int)f.prims.size();
     s->gate_count = (int)f.gates.size();

@@ -49,6 +49,7 @@ int sim_scene_create(const rtc_scene_desc* desc, void** out) {
     v.materials = s->flat.materials.data();
     v.program_count = (int32_t)s->flat.program.size();
     v.reject_prims = s->flat.reject_prims;
+    v.reject_extent = s->flat.reject_extent;
     for (int k = 0; k < 3; k++) {
         v.light_pos[k] = s->flat.light_pos[k];
         v.light_int[k] = s->flat.light_int[k];
