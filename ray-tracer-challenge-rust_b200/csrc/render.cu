@@ -30,6 +30,10 @@ namespace {
 #endif
 constexpr int kBlockThreads = RTC_BLOCK_THREADS;
 constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
+#ifndef RTC_MAX_TILE_BATCH
+#define RTC_MAX_TILE_BATCH 1
+#endif
+constexpr uint32_t kMaxTileBatch = RTC_MAX_TILE_BATCH;
 constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;
 #ifndef RTC_BLOCKS_PER_SM_PRIMS
 #define RTC_BLOCKS_PER_SM_PRIMS 6
@@ -52,12 +56,28 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
     RayCounters rc;
     Tally tl;
     uint32_t primary = 0;
+    // Tile queue with optional guided batches (a warp takes up to kMaxTileBatch consecutive tiles per atomic, shrinking
+    // to one as the queue runs out).  MEASURED (profiles/r01g_tile_batch_sweep.json): batches of 4/8/16 are 1.1x-3x
+    // SLOWER on every config — neighbouring heavy tiles land on one warp and a warp's time is the sum of its tiles — and
+    // the single-address atomic is not a bottleneck (64 800 grabs per 1080p frame, < 13 % of one L2 slice), so the
+    // default is one tile per grab.
+    const uint32_t nwarps = gridDim.x * (kBlockThreads / 32);
+    uint32_t batch = ntiles / (4u * nwarps);
+    batch = batch < 1u ? 1u : (batch > kMaxTileBatch ? kMaxTileBatch : batch);
+    uint32_t tile = 0, tile_end = 0;
     for (;;) {
-        unsigned tile = 0;
-        if (lane == 0) tile = atomicAdd(&q->next_tile, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= ntiles) break;
+        if (tile >= tile_end) {
+            unsigned first = 0;
+            if (lane == 0) first = atomicAdd(&q->next_tile, batch);
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (first >= ntiles) break;
+            tile = first;
+            tile_end = first + batch < ntiles ? first + batch : ntiles;
+            const uint32_t guided = (ntiles - tile_end) / (2u * nwarps);
+            batch = guided < 1u ? 1u : (guided > kMaxTileBatch ? kMaxTileBatch : guided);
+        }
         const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+        tile++;
         const uint32_t px = tx * kTileW + (lane & (kTileW - 1));
         const uint32_t lrow = ty * kTileH + (lane / kTileW);  // row inside this call's compact output
         if (px < cam.hsize && lrow < rows.local_rows) {
