@@ -244,6 +244,14 @@ class Flattener {
         }
     }
 
+    static constexpr uint32_t kRejectMinSiblings = 4;
+    uint32_t sibling_leaves(uint32_t begin, uint32_t end) const {
+        uint32_t n = 0;
+        for (uint32_t c = begin; c < end; c = end_[c])
+            if (d_.shapes[c].kind != RTC_GROUP && d_.shapes[c].kind != RTC_TRIANGLE) n++;
+        return n;
+    }
+
     // ---- emission ---------------------------------------------------------------------------------------------------
     bool same_inverse(uint32_t a, uint32_t b) const {
         return std::memcmp(d_.transforms[d_.shapes[a].transform].inverse, d_.transforms[d_.shapes[b].transform].inverse,
@@ -272,7 +280,10 @@ class Flattener {
                 p.minimum = s.minimum;
                 p.maximum = s.maximum;
                 p.leaf = (int32_t)next_leaf_++;
-                reject_box(s, p);
+                // a reject box pays for itself where many siblings share one parent (a list the ray would otherwise walk
+                // in full); a couple of leaves behind a tight group gate are cheaper to test outright (measured on the
+                // hexagon scene: 12 leaves in 6 two-leaf groups — boxes cost 12 %)
+                if (sibling_leaves(begin, end) > kRejectMinSiblings) reject_box(s, p);
                 if (p.reject) out_.reject_prims++;
                 out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, 0});
                 out_.prims.push_back(p);

@@ -15,11 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "ray-tracer-challenge-rust_b200", "variants")
 VARIANTS = {
-    "b6_batch1": ["RTC_MAX_TILE_BATCH=1"],
-    "b6_batch4": ["RTC_MAX_TILE_BATCH=4"],
-    "b6_batch8": ["RTC_MAX_TILE_BATCH=8"],
-    "b6_batch16": ["RTC_MAX_TILE_BATCH=16"],
-    "b5_batch8": ["RTC_BLOCKS_PER_SM=5", "RTC_BLOCKS_PER_SM_PRIMS=5", "RTC_MAX_TILE_BATCH=8"],
+    "t128_b5": ["RTC_BLOCKS_PER_SM=5", "RTC_BLOCKS_PER_SM_PRIMS=5"],
+    "t128_b6": ["RTC_BLOCKS_PER_SM=6", "RTC_BLOCKS_PER_SM_PRIMS=6"],
+    "t128_b8": ["RTC_BLOCKS_PER_SM=8", "RTC_BLOCKS_PER_SM_PRIMS=8"],
 }
 SCENES = [("table", 1920, 1080), ("teapot", 1920, 1080), ("hexagon", 1920, 960), ("cow_teddy", 3840, 2160),
           ("pumpkin", 3840, 2160)]
