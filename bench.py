@@ -319,6 +319,17 @@ def run_b200(args):
     nofma, fma = rtc.measure_fp64_peak(local_rank)
     fp64_achieved = alg_flops / (kernel_ms_avg * 1e-3) / 1e12
 
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this same command
+    # (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); null when no capture exists for this workload
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = tj.get(f"{args.workload} {w}x{h}")
+        if ent and world_size == 1:
+            traffic = ent["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
+
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -342,7 +353,7 @@ def run_b200(args):
         "gpu_launches": args.steps * 1,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": hbm_achieved / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                     "frac": hbm_achieved / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                      "kernel": "render_kernel", "kernel_ms": kernel_ms_avg, "algorithmic_bytes": alg_bytes,
                      "note": "neither contract bound binds this kernel: a frame's HBM traffic is its RGBA8 store plus a "
                              "< 2 MB L2-resident scene; the binding resource is FP64 issue without FMA (roofline_fp64)"},

@@ -64,7 +64,7 @@ def build(force=False, verbose=False, defines=(), out=None):
     nvcc = _nvcc()
     dflags = ["-D" + d for d in defines]
     with open(os.path.join(bdir, "build.log"), "w") as log:
-        _run(["g++", *HOST_FLAGS, "-c", os.path.join(CSRC, "capi.cpp"), "-o", os.path.join(bdir, "capi.o")], log)
+        _run(["g++", *HOST_FLAGS, *dflags, "-c", os.path.join(CSRC, "capi.cpp"), "-o", os.path.join(bdir, "capi.o")], log)
         _run([nvcc, *NVCC_FLAGS, *dflags, "-c", os.path.join(CSRC, "render.cu"), "-o", os.path.join(bdir, "render.o")],
              log)
         _run([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "render_tally.cu"), "-o",

@@ -21,7 +21,10 @@
 
 namespace rtc {
 
-constexpr int kLeafMax = 4;
+#ifndef RTC_BVH_LEAF_MAX
+#define RTC_BVH_LEAF_MAX 4
+#endif
+constexpr int kLeafMax = RTC_BVH_LEAF_MAX;
 constexpr int kBins = 32;
 constexpr int kSahDepth = 24;
 constexpr double kPadRel = 1e-7;

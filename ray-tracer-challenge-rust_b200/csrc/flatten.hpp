@@ -259,6 +259,7 @@ class Flattener {
     }
 
     void emit_children(uint32_t begin, uint32_t end) {
+        const bool boxes_pay = sibling_leaves(begin, end) > kRejectMinSiblings;
         uint32_t i = begin;
         while (i < end) {
             const rtc_shape_desc& s = d_.shapes[i];
@@ -283,7 +284,7 @@ class Flattener {
                 // a reject box pays for itself where many siblings share one parent (a list the ray would otherwise walk
                 // in full); a couple of leaves behind a tight group gate are cheaper to test outright (measured on the
                 // hexagon scene: 12 leaves in 6 two-leaf groups — boxes cost 12 %)
-                if (sibling_leaves(begin, end) > kRejectMinSiblings) reject_box(s, p);
+                if (boxes_pay) reject_box(s, p);
                 if (p.reject) out_.reject_prims++;
                 out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, 0});
                 out_.prims.push_back(p);

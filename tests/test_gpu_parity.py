@@ -66,6 +66,25 @@ def test_full_resolution_subset_matches_oracle(rtc, oracle, name, w, h):
     _check(ref, None, oracle.quantise_rgba8(ref), got)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_worlds_match_oracle(rtc, oracle, seed):
+    """Seeded random worlds (nested groups, glass in glass, cones, shears, patterns, small meshes) on the GPU."""
+    import worldgen
+    w, c = worldgen.random_world(rtc.api(), seed, hsize=96, vsize=64)
+    world = rtc.World(_handle=w.h)
+    w.h = None
+    cam = rtc.Camera.__new__(rtc.Camera)
+    cam.api, cam.hsize, cam.vsize, cam.field_of_view, cam.h = c.api, c.hsize, c.vsize, c.field_of_view, c.h
+    c.h = None
+    st = rtc.Stats()
+    canvas = cam.render(world, stats=st)
+    ow, oc = worldgen.random_world(oracle, seed, hsize=96, vsize=64)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    _check(ref, canvas.pixels_f64().reshape(-1, 3), oracle.quantise_rgba8(ref), canvas.pixels_rgba8())
+    assert (st.primary_rays, st.shadow_rays, st.reflect_rays, st.refract_rays) == \
+        (cnt.primary, cnt.shadow, cnt.reflect, cnt.refract)
+
+
 def test_default_world_known_answers(rtc):
     """camera.rs:145-155 and world.rs:212-260 through the CUDA path."""
     import math
