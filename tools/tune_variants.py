@@ -15,10 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "ray-tracer-challenge-rust_b200", "variants")
 VARIANTS = {
-    "leaf2": ["RTC_BVH_LEAF_MAX=2"],
-    "leaf3": ["RTC_BVH_LEAF_MAX=3"],
-    "leaf4": ["RTC_BVH_LEAF_MAX=4"],
-    "leaf6": ["RTC_BVH_LEAF_MAX=6"],
+    "t128_b5": ["RTC_BLOCKS_PER_SM=5", "RTC_BLOCKS_PER_SM_PRIMS=5"],
+    "t128_b6": ["RTC_BLOCKS_PER_SM=6", "RTC_BLOCKS_PER_SM_PRIMS=6"],
+    "t128_b8": ["RTC_BLOCKS_PER_SM=8", "RTC_BLOCKS_PER_SM_PRIMS=8"],
 }
 SCENES = [("table", 1920, 1080), ("teapot", 1920, 1080), ("hexagon", 1920, 960), ("cow_teddy", 3840, 2160),
           ("pumpkin", 3840, 2160)]
