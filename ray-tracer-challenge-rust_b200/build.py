@@ -38,11 +38,24 @@ def _sources():
     return out
 
 
+STAMP = LIB + ".sources.sha256"
+
+
+def _digest():
+    """Content hash of everything the library is built from (file times do not survive the copy to a GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(_sources()):
+        h.update(os.path.relpath(path, ROOT).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(s) > t for s in _sources())
+    return open(STAMP).read().strip() != _digest()
 
 
 def _run(cmd, log):
@@ -71,6 +84,9 @@ def build(force=False, verbose=False, defines=(), out=None):
               os.path.join(bdir, "render_tally.o")], log)
         _run([nvcc, "-shared", "-o", lib, os.path.join(bdir, "capi.o"), os.path.join(bdir, "render.o"),
               os.path.join(bdir, "render_tally.o")], log)
+    if not out:
+        with open(STAMP, "w") as f:
+            f.write(_digest() + "\n")
     if verbose:
         print(open(os.path.join(bdir, "build.log")).read())
     return lib
