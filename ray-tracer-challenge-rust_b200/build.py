@@ -30,6 +30,14 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def _instance_masks():
+    """The feature masks render_kernel is instantiated for (RTC_RENDER_INSTANCES in csrc/render_launch.cuh)."""
+    import re
+    text = open(os.path.join(CSRC, "render_launch.cuh")).read()
+    line = re.search(r"#define RTC_RENDER_INSTANCES\(X\)(.*)", text).group(1)
+    return [int(m) for m in re.findall(r"X\((\d+)\)", line)]
+
+
 def _sources():
     out = []
     for d, _, files in os.walk(CSRC):
@@ -78,12 +86,25 @@ def build(force=False, verbose=False, defines=(), out=None):
     dflags = ["-D" + d for d in defines]
     with open(os.path.join(bdir, "build.log"), "w") as log:
         _run(["g++", *HOST_FLAGS, *dflags, "-c", os.path.join(CSRC, "capi.cpp"), "-o", os.path.join(bdir, "capi.o")], log)
-        _run([nvcc, *NVCC_FLAGS, *dflags, "-c", os.path.join(CSRC, "render.cu"), "-o", os.path.join(bdir, "render.o")],
-             log)
-        _run([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "render_tally.cu"), "-o",
-              os.path.join(bdir, "render_tally.o")], log)
-        _run([nvcc, "-shared", "-o", lib, os.path.join(bdir, "capi.o"), os.path.join(bdir, "render.o"),
-              os.path.join(bdir, "render_tally.o")], log)
+        # the CUDA translation units in parallel: management + small kernels, the tally build, and render_kernel once
+        # per feature mask (csrc/render_launch.cuh RTC_RENDER_INSTANCES)
+        jobs = [("render.o", ["render.cu"], dflags), ("render_tally.o", ["render_tally.cu"], [])]
+        for mask in _instance_masks():
+            jobs.append((f"render_inst_{mask}.o", ["render_inst.cu"], dflags + [f"-DRTC_INST_MASK={mask}"]))
+        from concurrent.futures import ThreadPoolExecutor
+        import io
+
+        def compile_one(job):
+            obj, srcs, flags = job
+            buf = io.StringIO()
+            _run([nvcc, *NVCC_FLAGS, *flags, "-c", *[os.path.join(CSRC, s) for s in srcs], "-o",
+                  os.path.join(bdir, obj)], buf)
+            return buf.getvalue()
+
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as pool:
+            for text in pool.map(compile_one, jobs):
+                log.write(text)
+        _run([nvcc, "-shared", "-o", lib, os.path.join(bdir, "capi.o"), *[os.path.join(bdir, j[0]) for j in jobs]], log)
     if not out:
         with open(STAMP, "w") as f:
             f.write(_digest() + "\n")

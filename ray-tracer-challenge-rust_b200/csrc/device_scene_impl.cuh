@@ -44,7 +44,7 @@ struct DeviceScene {
     void* slab = nullptr;           // all tables, one stream-ordered allocation
     size_t slab_size = 0;
     DScene view{};
-    int mesh_count = 0, prim_count = 0, gate_count = 0;
+    int feature_mask = 0;           // FEAT_* bits of what the flattened world contains (picks the kernel instantiation)
     cudaStream_t stream = nullptr;  // == ctx->stream
     std::mutex& mu() { return ctx->mu; }
 };

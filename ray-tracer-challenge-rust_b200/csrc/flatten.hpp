@@ -62,6 +62,10 @@ class Flattener {
         }
         emit_children(0, d_.shape_count);  // World.objects in order (world.rs:46-50)
         out_.leaf_count = next_leaf_;
+        if (!out_.meshes.empty()) out_.feature_mask |= 32;
+        if (!out_.gates.empty()) out_.feature_mask |= 64;
+        for (const DMaterial& m : out_.materials)
+            if (m.transparency != 0.0) out_.feature_mask |= 128;
     }
 
   private:
@@ -281,6 +285,7 @@ class Flattener {
                 p.minimum = s.minimum;
                 p.maximum = s.maximum;
                 p.leaf = (int32_t)next_leaf_++;
+                out_.feature_mask |= 1 << s.kind;
                 // a reject box pays for itself where many siblings share one parent (a list the ray would otherwise walk
                 // in full); a couple of leaves behind a tight group gate are cheaper to test outright (measured on the
                 // hexagon scene: 12 leaves in 6 two-leaf groups — boxes cost 12 %)

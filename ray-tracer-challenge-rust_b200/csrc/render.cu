@@ -13,6 +13,7 @@
 #include "flat_scene.hpp"
 #include "render.cuh"
 #include "device_scene_impl.cuh"
+#include "render_launch.cuh"
 #include "rt_core.cuh"
 
 namespace rtc {
@@ -21,95 +22,6 @@ using namespace core;
 
 namespace {
 
-// launch shape (tunable at build time: tools/tune_variants.py)
-#ifndef RTC_BLOCK_THREADS
-#define RTC_BLOCK_THREADS 128
-#endif
-#ifndef RTC_BLOCKS_PER_SM
-#define RTC_BLOCKS_PER_SM 6
-#endif
-constexpr int kBlockThreads = RTC_BLOCK_THREADS;
-constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
-#ifndef RTC_MAX_TILE_BATCH
-#define RTC_MAX_TILE_BATCH 1
-#endif
-constexpr uint32_t kMaxTileBatch = RTC_MAX_TILE_BATCH;
-constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;
-#ifndef RTC_BLOCKS_PER_SM_PRIMS
-#define RTC_BLOCKS_PER_SM_PRIMS 6
-#endif
-constexpr int kBlocksPerSmPrims = RTC_BLOCKS_PER_SM_PRIMS;
-
-
-// kMinBlocks = CTAs per SM the register allocation must allow (6 -> 80 registers, 24 warps/SM: the measured optimum of
-// the launch-shape sweeps in profiles/: more warps hide FP64 latency and fetch bubbles, fewer registers spill).
-template <int kMinBlocks, int kFeatures>
-__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const __grid_constant__ DScene s,
-                                                               const __grid_constant__ DCamera cam,
-                                                               const __grid_constant__ DRows rows,
-                                                               uint32_t* __restrict__ out8, double* __restrict__ out64,
-                                                               DQueue* __restrict__ q) {
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t tiles_x = (cam.hsize + kTileW - 1) / kTileW;
-    const uint32_t tiles_y = (rows.local_rows + kTileH - 1) / kTileH;
-    const uint32_t ntiles = tiles_x * tiles_y;
-    RayCounters rc;
-    Tally tl;
-    uint32_t primary = 0;
-    // Tile queue with optional guided batches (a warp takes up to kMaxTileBatch consecutive tiles per atomic, shrinking
-    // to one as the queue runs out).  MEASURED (profiles/r01g_tile_batch_sweep.json): batches of 4/8/16 are 1.1x-3x
-    // SLOWER on every config — neighbouring heavy tiles land on one warp and a warp's time is the sum of its tiles — and
-    // the single-address atomic is not a bottleneck (64 800 grabs per 1080p frame, < 13 % of one L2 slice), so the
-    // default is one tile per grab.
-    const uint32_t nwarps = gridDim.x * (kBlockThreads / 32);
-    uint32_t batch = ntiles / (4u * nwarps);
-    batch = batch < 1u ? 1u : (batch > kMaxTileBatch ? kMaxTileBatch : batch);
-    uint32_t tile = 0, tile_end = 0;
-    for (;;) {
-        if (tile >= tile_end) {
-            unsigned first = 0;
-            if (lane == 0) first = atomicAdd(&q->next_tile, batch);
-            first = __shfl_sync(0xffffffffu, first, 0);
-            if (first >= ntiles) break;
-            tile = first;
-            tile_end = first + batch < ntiles ? first + batch : ntiles;
-            const uint32_t guided = (ntiles - tile_end) / (2u * nwarps);
-            batch = guided < 1u ? 1u : (guided > kMaxTileBatch ? kMaxTileBatch : guided);
-        }
-        const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
-        tile++;
-        const uint32_t px = tx * kTileW + (lane & (kTileW - 1));
-        const uint32_t lrow = ty * kTileH + (lane / kTileW);  // row inside this call's compact output
-        if (px < cam.hsize && lrow < rows.local_rows) {
-            const uint32_t band = lrow / rows.band_rows;
-            const uint32_t py = (rows.band_first + band * rows.band_stride) * rows.band_rows + (lrow % rows.band_rows);
-            const Ray ray = ray_for_pixel(cam, px, py);
-            primary++;
-            const V3 c = color_at<kFeatures>(s, ray, rc, tl);
-            const size_t o = (size_t)(rows.frame_layout ? py : lrow) * cam.hsize + px;
-            if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
-            if (out64) {
-                out64[3 * o + 0] = c.x;
-                out64[3 * o + 1] = c.y;
-                out64[3 * o + 2] = c.z;
-            }
-        }
-    }
-    // ray counters: warp reduce, one atomic per warp and counter
-    unsigned long long v[4] = {primary, rc.shadow, rc.reflect, rc.refract};
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        unsigned x = (unsigned)v[k];
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-        v[k] = x;
-    }
-    if (lane == 0) {
-        if (v[0]) atomicAdd(&q->primary, v[0]);
-        if (v[1]) atomicAdd(&q->shadow, v[1]);
-        if (v[2]) atomicAdd(&q->reflect, v[2]);
-        if (v[3]) atomicAdd(&q->refract, v[3]);
-    }
-}
 
 __global__ void __launch_bounds__(kBlockThreads) color_at_kernel(const __grid_constant__ DScene s,
                                                                  const double* __restrict__ rays, uint64_t n,
@@ -325,9 +237,7 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->view.program_count = (int32_t)f.program.size();
     s->view.reject_prims = f.reject_prims;
     s->view.reject_extent = f.reject_extent;
-    s->mesh_count = (int)f.meshes.size();
-    s->prim_count = (int)f.prims.size();
-    s->gate_count = (int)f.gates.size();
+    s->feature_mask = f.feature_mask;
     for (int k = 0; k < 3; k++) {
         s->view.light_pos[k] = f.light_pos[k];
         s->view.light_int[k] = f.light_int[k];
@@ -362,26 +272,25 @@ static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
     const uint64_t tiles = (uint64_t)((cam.hsize + kTileW - 1) / kTileW) * ((rows.local_rows + kTileH - 1) / kTileH);
     const uint64_t warps_per_block = kBlockThreads / 32;
     uint64_t blocks = (tiles + warps_per_block - 1) / warps_per_block;
-    const bool prims_only = s->mesh_count == 0;
-    const int per_sm = prims_only ? kBlocksPerSmPrims : kBlocksPerSm;
-    const uint64_t cap = (uint64_t)s->sm_count * per_sm;
+    const uint64_t cap = (uint64_t)s->sm_count * kBlocksPerSm;
     if (blocks > cap) blocks = cap;
     if (stats) RTC_CUDA(cudaEventRecord(ctx->ev0, st));
-    // instantiations by scene content: the kernel for a scene without meshes (or without primitives/gates) carries none
-    // of that code
-    const unsigned g = (unsigned)blocks;
-    uint32_t* o8 = (uint32_t*)d8;
-    double* o64 = (double*)d64;
-    if (prims_only && s->gate_count == 0)
-        render_kernel<kBlocksPerSmPrims, FEAT_PRIMS><<<g, kBlockThreads, 0, st>>>(s->view, cam, rows, o8, o64, queue);
-    else if (prims_only)
-        render_kernel<kBlocksPerSmPrims, FEAT_PRIMS | FEAT_GATES><<<g, kBlockThreads, 0, st>>>(s->view, cam, rows, o8,
-                                                                                            o64, queue);
-    else if (s->prim_count == 0)
-        render_kernel<kBlocksPerSm, FEAT_MESHES | FEAT_GATES><<<g, kBlockThreads, 0, st>>>(s->view, cam, rows, o8, o64,
-                                                                                        queue);
-    else
-        render_kernel<kBlocksPerSm, FEAT_ALL><<<g, kBlockThreads, 0, st>>>(s->view, cam, rows, o8, o64, queue);
+    // the smallest instantiation whose feature mask covers the scene's (render_launch.cuh)
+    static const struct {
+        int mask;
+        RenderLaunchFn fn;
+    } kInstances[] = {
+#define RTC_TABLE_ENTRY(mask) {mask, launch_render_##mask},
+        RTC_RENDER_INSTANCES(RTC_TABLE_ENTRY)
+#undef RTC_TABLE_ENTRY
+    };
+    RenderLaunchFn fn = nullptr;
+    for (const auto& inst : kInstances)
+        if ((inst.mask & s->feature_mask) == s->feature_mask) {
+            fn = inst.fn;
+            break;
+        }
+    fn((unsigned)blocks, st, s->view, cam, rows, (uint32_t*)d8, (double*)d64, queue);
     RTC_CUDA(cudaGetLastError());
     if (stats) {
         RTC_CUDA(cudaEventRecord(ctx->ev1, st));

@@ -1,0 +1,44 @@
+// render_launch.cuh — launch shape of render_kernel and the list of its instantiations (private).
+//
+// render_kernel<features> is compiled once per FEATURE MASK (rt_core.cuh FEAT_*), each in its own translation unit
+// (render_inst.cu with -DRTC_INST_MASK=<mask>, built in parallel by build.py), so that the kernel a scene runs carries no
+// code the scene cannot reach: the hot loop's footprint is what the instruction cache sees (profiles/r01h: the
+// everything-kernel spent 40 % of its warp-state samples waiting for instructions on the pumpkin scene; dropping the
+// unused quadric code alone was worth 8-10 %).  The dispatcher picks the FIRST listed mask that covers the scene's.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_scene.h"
+#include "device_scene_impl.cuh"
+
+namespace rtc {
+
+// launch shape (tunable at build time: tools/tune_variants.py)
+#ifndef RTC_BLOCK_THREADS
+#define RTC_BLOCK_THREADS 128
+#endif
+#ifndef RTC_BLOCKS_PER_SM
+#define RTC_BLOCKS_PER_SM 6
+#endif
+constexpr int kBlockThreads = RTC_BLOCK_THREADS;
+constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;  // 6 -> 80 registers, 24 warps/SM: the measured optimum (profiles/r01d)
+constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
+#ifndef RTC_MAX_TILE_BATCH
+#define RTC_MAX_TILE_BATCH 1
+#endif
+constexpr uint32_t kMaxTileBatch = RTC_MAX_TILE_BATCH;
+
+// mask, in dispatch order (smallest first):  cubes + refraction (table) | spheres + cylinders + groups (hexagon) |
+// mesh + groups (teapot) | + plane (cow & teddy) | + refraction (pumpkin) | every primitive kind, no meshes | everything
+#define RTC_RENDER_INSTANCES(X) X(132) X(73) X(96) X(98) X(226) X(223) X(255)
+
+using RenderLaunchFn = void (*)(unsigned grid, cudaStream_t stream, const DScene& s, const DCamera& cam, const DRows& rows,
+                                uint32_t* out8, double* out64, DQueue* q);
+#define RTC_DECLARE_LAUNCH(mask) \
+    void launch_render_##mask(unsigned, cudaStream_t, const DScene&, const DCamera&, const DRows&, uint32_t*, double*, DQueue*);
+RTC_RENDER_INSTANCES(RTC_DECLARE_LAUNCH)
+#undef RTC_DECLARE_LAUNCH
+
+}  // namespace rtc
