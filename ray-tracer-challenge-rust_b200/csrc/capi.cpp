@@ -38,6 +38,9 @@ int to_drows(const rtc_camera_desc& cam, const rtc_rows* rows, DRows* out) {
         out->band_stride = 1;
         out->local_rows = cam.vsize;
         out->frame_layout = 0;
+        out->row_begin = 0;
+        out->row_count = cam.vsize;
+        out->pad = 0;
         return RTC_OK;
     }
     if (rows->layout > RTC_ROWS_FRAME) return set_err(RTC_ERR_INVALID, "unknown rtc_rows.layout");
@@ -56,6 +59,9 @@ int to_drows(const rtc_camera_desc& cam, const rtc_rows* rows, DRows* out) {
         local += r1 - r0;
     }
     out->local_rows = (uint32_t)local;
+    out->row_begin = 0;
+    out->row_count = (uint32_t)local;
+    out->pad = 0;
     return RTC_OK;
 }
 void fill_stats(const LaunchStats& ls, rtc_stats* st) {

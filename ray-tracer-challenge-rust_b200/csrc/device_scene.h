@@ -98,7 +98,9 @@ struct DCamera {
 };
 struct DRows {
     uint32_t band_rows, band_first, band_stride, local_rows;  // local_rows = rows this call renders
-    uint32_t frame_layout, pad[3];                            // 1: outputs are addressed by FRAME row, not by local row
+    uint32_t frame_layout;                                    // 1: outputs are addressed by FRAME row, not by local row
+    uint32_t row_begin, row_count;                            // the local rows THIS launch renders (a chunk of the call)
+    uint32_t pad;
 };
 struct DStats {
     unsigned long long primary, shadow, reflect, refract;

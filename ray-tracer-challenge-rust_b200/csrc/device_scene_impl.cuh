@@ -25,6 +25,8 @@ struct DeviceContext {
     int sm_count = 0;
     cudaStream_t stream = nullptr;  // the library's own stream (uploads, host-output renders)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;  // device->host copies that overlap the next chunk's kernel (render_host)
+    cudaEvent_t chunk_done = nullptr, copy_done = nullptr;
     DQueue* queues = nullptr;       // kQueueSlots work queues handed out round-robin (one per in-flight launch)
     unsigned next_queue = 0;
     // grow-only scratch

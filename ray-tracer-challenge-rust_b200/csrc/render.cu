@@ -262,14 +262,14 @@ int device_scene_device(const DeviceScene* s) { return s->device; }
 
 static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d8, void* d64, cudaStream_t st,
                   LaunchStats* stats, std::string* err) {
-    if (rows.local_rows == 0 || cam.hsize == 0) {
+    if (rows.row_count == 0 || cam.hsize == 0) {
         if (stats) *stats = LaunchStats{};
         return 0;
     }
     DeviceContext* ctx = s->ctx;
     DQueue* queue = ctx->queues + (ctx->next_queue++ % kQueueSlots);
     RTC_CUDA(cudaMemsetAsync(queue, 0, sizeof(DQueue), st));
-    const uint64_t tiles = (uint64_t)((cam.hsize + kTileW - 1) / kTileW) * ((rows.local_rows + kTileH - 1) / kTileH);
+    const uint64_t tiles = (uint64_t)((cam.hsize + kTileW - 1) / kTileW) * ((rows.row_count + kTileH - 1) / kTileH);
     const uint64_t warps_per_block = kBlockThreads / 32;
     uint64_t blocks = (tiles + warps_per_block - 1) / warps_per_block;
     const uint64_t cap = (uint64_t)s->sm_count * kBlocksPerSm;
@@ -335,10 +335,41 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* 
         RTC_CUDA(cudaMalloc(&s->ctx->out64, px * 24));
         s->ctx->out64_size = px * 24;
     }
-    int rc = launch(s, cam, rows, rgba8 ? s->ctx->out8 : nullptr, rgb_f64 ? s->ctx->out64 : nullptr, s->stream, stats, err);
-    if (rc) return rc;
-    if (rgba8 && px) RTC_CUDA(cudaMemcpyAsync(rgba8, s->ctx->out8, px * 4, cudaMemcpyDeviceToHost, s->stream));
-    if (rgb_f64 && px) RTC_CUDA(cudaMemcpyAsync(rgb_f64, s->ctx->out64, px * 24, cudaMemcpyDeviceToHost, s->stream));
+    // Overlap the device->host copy with rendering: the call's rows are rendered in two launches (3/4, then 1/4) and the
+    // first chunk's pixels cross PCIe on a second stream while the second chunk renders.  Ray counters are per launch;
+    // with `stats` requested the frame is rendered in one launch so that the reported kernel time is one kernel's.
+    const bool split = !stats && !rgb_f64 && rgba8 && rows.local_rows >= 256;
+    if (!split) {
+        int rc = launch(s, cam, rows, rgba8 ? s->ctx->out8 : nullptr, rgb_f64 ? s->ctx->out64 : nullptr, s->stream, stats, err);
+        if (rc) return rc;
+        if (rgba8 && px) RTC_CUDA(cudaMemcpyAsync(rgba8, s->ctx->out8, px * 4, cudaMemcpyDeviceToHost, s->stream));
+        if (rgb_f64 && px) RTC_CUDA(cudaMemcpyAsync(rgb_f64, s->ctx->out64, px * 24, cudaMemcpyDeviceToHost, s->stream));
+    } else {
+        DeviceContext* ctx = s->ctx;
+        if (!ctx->copy_stream) {
+            RTC_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            RTC_CUDA(cudaEventCreateWithFlags(&ctx->chunk_done, cudaEventDisableTiming));
+            RTC_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+        }
+        const uint32_t first = ((rows.local_rows * 3 / 4) + kTileH - 1) / kTileH * kTileH;
+        DRows a = rows, b = rows;
+        a.row_begin = 0;
+        a.row_count = first;
+        b.row_begin = first;
+        b.row_count = rows.local_rows - first;
+        int rc = launch(s, cam, a, ctx->out8, nullptr, s->stream, nullptr, err);
+        if (rc) return rc;
+        RTC_CUDA(cudaEventRecord(ctx->chunk_done, s->stream));
+        rc = launch(s, cam, b, ctx->out8, nullptr, s->stream, nullptr, err);
+        if (rc) return rc;
+        const size_t bytes_a = (size_t)first * cam.hsize * 4;
+        RTC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done, 0));
+        RTC_CUDA(cudaMemcpyAsync(rgba8, ctx->out8, bytes_a, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        RTC_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+        RTC_CUDA(cudaMemcpyAsync(rgba8 + bytes_a, (const unsigned char*)ctx->out8 + bytes_a, px * 4 - bytes_a,
+                                 cudaMemcpyDeviceToHost, s->stream));
+        RTC_CUDA(cudaStreamWaitEvent(s->stream, ctx->copy_done, 0));
+    }
     RTC_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
                                                                DQueue* __restrict__ q) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t tiles_x = (cam.hsize + kTileW - 1) / kTileW;
-    const uint32_t tiles_y = (rows.local_rows + kTileH - 1) / kTileH;
+    const uint32_t tiles_y = (rows.row_count + kTileH - 1) / kTileH;
     const uint32_t ntiles = tiles_x * tiles_y;
     RayCounters rc;
     Tally tl;
@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
         const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
         tile++;
         const uint32_t px = tx * kTileW + (lane & (kTileW - 1));
-        const uint32_t lrow = ty * kTileH + (lane / kTileW);  // row inside this call's compact output
-        if (px < cam.hsize && lrow < rows.local_rows) {
+        const uint32_t lrow = rows.row_begin + ty * kTileH + (lane / kTileW);  // row inside this call's compact output
+        if (px < cam.hsize && lrow < rows.row_begin + rows.row_count) {
             const uint32_t band = lrow / rows.band_rows;
             const uint32_t py = (rows.band_first + band * rows.band_stride) * rows.band_rows + (lrow % rows.band_rows);
             const Ray ray = ray_for_pixel(cam, px, py);
