@@ -67,7 +67,8 @@ def cpu_reference_sample(workload, w, h, step, threads=1):
     orc = helpers.load_oracle()
     ow, oc = helpers.scenes.build(orc, workload, w, h)
     px = helpers.subset_pixels(w, h, step, step // 2)
-    _, cnt = orc.render(ow, oc, mode=orc.FAITHFUL, nthreads=threads, pixels=px)
+    rgb, cnt = orc.render(ow, oc, mode=orc.FAITHFUL, nthreads=threads, pixels=px)
+    cpu_reference_sample.last = (px, orc.quantise_rgba8(rgb))  # the sample's pixels, for the caller's parity check
     return cnt.total_rays, cnt.seconds, len(px)
 
 
@@ -294,20 +295,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- parity spot check of the frame this run produced (checker only; not timed) ---------------------------------
     frame_np = host_frame.numpy()
-    parity = None
-    try:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import helpers
-        orc = helpers.load_oracle()
-        ow, oc = helpers.scenes.build(orc, args.workload, w, h)
-        px = helpers.subset_pixels(w, h, 64, 32)
-        ref, _ = orc.render(ow, oc, mode=orc.CACHED, pixels=px)
-        exact, md = helpers.compare_rgba(orc.quantise_rgba8(ref), frame_np[px[:, 1], px[:, 0]])
-        parity = {"pixels_checked": int(len(px)), "exact_fraction": exact, "max_channel_diff": md}
-    except Exception as e:  # the checker is optional here; tests/ is where parity is enforced
-        parity = {"error": str(e)}
 
     # ---- rooflines ---------------------------------------------------------------------------------------------------
     peaks = {}
@@ -371,12 +359,17 @@ def run_b200(args):
                           "peak_source": "self-measured DMUL+DADD chains on this GPU (rtc_measure_fp64_peak)",
                           "peak_fma_tflops": fma / 1e3, "algorithmic_flops": alg_flops,
                           "bvh_box_flops_not_counted": bvh_flops, "tally": tally},
-        "parity": parity,
     }
 
     if not args.no_cpu_baseline and world_size == 1:
         step_px = {"table": 8, "hexagon": 2, "teapot": 64, "cow_teddy": 96, "pumpkin": 192}.get(args.workload, 32)
         r, s, n = cpu_reference_sample(args.workload, w, h, step_px)
+        # the CPU leg's pixels double as the parity check of the frame this run produced (same camera, same pixels)
+        import helpers
+        px, ref_rgba = cpu_reference_sample.last
+        exact, md = helpers.compare_rgba(ref_rgba, frame_np[px[:, 1], px[:, 0]])
+        line["parity"] = {"pixels_checked": int(len(px)), "exact_fraction": exact, "max_channel_diff": md,
+                          "against": "the cpu_baseline sample's own pixels (reference algorithm, same camera)"}
         line["cpu_baseline"] = {
             "value": r / s / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
             "sample": f"every {step_px}th pixel in x and y of the {w}x{h} camera ({n} px, {r} rays, {s:.1f} s) with the "
