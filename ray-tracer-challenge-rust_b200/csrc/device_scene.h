@@ -88,6 +88,7 @@ struct DScene {
     int32_t reject_prims;  // how many prims carry a reject box (0: the walker skips the per-ray set-up for them)
     float reject_extent;   // max |coordinate| over those boxes (f32 slab error bound)
     int32_t pad0;
+    uint32_t n_prims, n_xforms, n_gates, n_materials;  // table lengths (shared-memory staging)
     double light_pos[3];
     double light_int[3];
 };

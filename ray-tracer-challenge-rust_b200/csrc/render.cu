@@ -237,6 +237,10 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->view.program_count = (int32_t)f.program.size();
     s->view.reject_prims = f.reject_prims;
     s->view.reject_extent = f.reject_extent;
+    s->view.n_prims = (uint32_t)f.prims.size();
+    s->view.n_xforms = (uint32_t)f.xforms.size();
+    s->view.n_gates = (uint32_t)f.gates.size();
+    s->view.n_materials = (uint32_t)f.materials.size();
     s->feature_mask = f.feature_mask;
     for (int k = 0; k < 3; k++) {
         s->view.light_pos[k] = f.light_pos[k];

@@ -9,6 +9,11 @@
 #endif
 #include <cuda_runtime.h>
 
+// Instantiations without meshes are a short list of leaves: their tables (prims, transforms, gates, program, materials —
+// a few KB) are staged in SHARED memory once per persistent CTA and read from there.
+#if defined(RTC_TRY_STAGE_SMEM) && ((RTC_INST_MASK & 32) == 0)
+#define RTC_STAGE_SMEM 1
+#endif
 #include "render_launch.cuh"
 #include "rt_core.cuh"
 
@@ -21,11 +26,44 @@ namespace {
 // kMinBlocks = CTAs per SM the register allocation must allow (6 -> 80 registers, 24 warps/SM: the measured optimum of
 // the launch-shape sweeps in profiles/: more warps hide FP64 latency and fetch bubbles, fewer registers spill).
 template <int kMinBlocks, int kFeatures>
-__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const __grid_constant__ DScene s,
+__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const __grid_constant__ DScene s_in,
                                                                const __grid_constant__ DCamera cam,
                                                                const __grid_constant__ DRows rows,
                                                                uint32_t* __restrict__ out8, double* __restrict__ out64,
                                                                DQueue* __restrict__ q) {
+#if defined(RTC_STAGE_SMEM)
+    // stage the small tables (16-byte granules) and retarget the scene's pointers; scenes too large for the buffer keep
+    // reading from global memory
+    constexpr uint32_t kStageBytes = 16 * 1024;
+    __shared__ __align__(16) unsigned char stage[kStageBytes];
+    DScene ls = s_in;
+    {
+        const uint32_t np = (uint32_t)ls.program_count * (uint32_t)sizeof(DProgramNode);
+        const uint32_t npr = ls.n_prims * (uint32_t)sizeof(DPrim), nx = ls.n_xforms * (uint32_t)sizeof(DXform);
+        const uint32_t ng = ls.n_gates * (uint32_t)sizeof(DGate), nm = ls.n_materials * (uint32_t)sizeof(DMaterial);
+        if (np + npr + nx + ng + nm <= kStageBytes) {
+            const void* src[5] = {ls.program, ls.prims, ls.xforms, ls.gates, ls.materials};
+            const uint32_t len[5] = {np, npr, nx, ng, nm};
+            uint32_t off = 0;
+            for (int t = 0; t < 5; t++) {
+                const int4* g = (const int4*)src[t];
+                int4* d = (int4*)(stage + off);
+                for (uint32_t i = threadIdx.x; i < len[t] / 16; i += blockDim.x) d[i] = g[i];
+                off += len[t];
+            }
+            __syncthreads();
+            off = 0;
+            ls.program = (const DProgramNode*)(stage + off); off += np;
+            ls.prims = (const DPrim*)(stage + off); off += npr;
+            ls.xforms = (const DXform*)(stage + off); off += nx;
+            ls.gates = (const DGate*)(stage + off); off += ng;
+            ls.materials = (const DMaterial*)(stage + off);
+        }
+    }
+    const DScene& s = ls;
+#else
+    const DScene& s = s_in;
+#endif
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t tiles_x = (cam.hsize + kTileW - 1) / kTileW;
     const uint32_t tiles_y = (rows.row_count + kTileH - 1) / kTileH;
