@@ -103,10 +103,7 @@ struct DRows {
     uint32_t row_begin, row_count;                            // the local rows THIS launch renders (a chunk of the call)
     uint32_t pad;
 };
-struct DStats {
-    unsigned long long primary, shadow, reflect, refract;
-};
-
+// depth of the per-thread traversal stack; flatten.hpp refuses a mesh whose BVH is deeper (the builder bounds depth)
 constexpr int kBvhStackDepth = 48;
 
 }  // namespace rtc

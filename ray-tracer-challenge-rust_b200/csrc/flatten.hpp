@@ -360,6 +360,8 @@ class Flattener {
         m.extent = f32_above_(max_abs * (1.0 + 2.0 * kPadRel));
         m.pad[0] = m.pad[1] = m.pad[2] = 0;
         if (depth > out_.bvh_max_depth) out_.bvh_max_depth = depth;
+        if (depth + 2 > kBvhStackDepth)
+            fail(RTC_ERR_UNSUPPORTED, "mesh BVH deeper than the device traversal stack (more than ~16M triangles)");
         const uint32_t leaf0 = next_leaf_;
         next_leaf_ += n;
         for (uint32_t slot = 0; slot < n; slot++) {
