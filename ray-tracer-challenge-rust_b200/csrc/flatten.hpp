@@ -73,6 +73,7 @@ class Flattener {
     FlatScene& out_;
     std::vector<uint32_t> end_;  // end_[i] = index just past shape i's subtree
     std::map<XKey, int32_t> xform_ids_;
+    std::map<uint32_t, Box4> group_bounds_;
     uint32_t next_leaf_ = 0;
     int32_t parent_gate_ = -1;  // gate of the group being emitted, if this node is its ONLY child
     bool only_child_ = false;
@@ -173,7 +174,9 @@ class Flattener {
                 add(b, point(t.p3[0], t.p3[1], t.p3[2]));
                 return b;
             }
-            default: {  // group, bounds.rs:50-125
+            default: {  // group, bounds.rs:50-125 (memoised: a nested group's box is asked for by its parent and by itself)
+                auto hit = group_bounds_.find(i);
+                if (hit != group_bounds_.end()) return hit->second;
                 Box4 out{point(0., 0., 0.), point(0., 0., 0.)};
                 for (uint32_t c = i + 1; c < end_[i]; c = end_[c]) {
                     Box4 pb = bounds_of(c);
@@ -187,6 +190,7 @@ class Flattener {
                     add(out, mul(tr, point(pb.max.x, pb.max.y, pb.min.z)));
                     add(out, mul(tr, pb.max));
                 }
+                group_bounds_.emplace(i, out);
                 return out;
             }
         }
