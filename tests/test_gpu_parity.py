@@ -99,6 +99,35 @@ def test_default_world_known_answers(rtc):
     np.testing.assert_allclose(cols[1], [0.38066, 0.47583, 0.2855], atol=1e-5)
 
 
+def test_reference_world_known_answers(rtc):
+    """world.rs:335-352, 488-546 (reflective / transparent / Schlick shade_hit) through World::color_at on the GPU.
+    The reference tests call shade_hit(comps, 5) directly; color_at reaches shade_hit with 4 — both budgets give exactly
+    two shaded generations, so the 5-decimal answers are the same."""
+    import math
+    T, S = rtc.Transformations(rtc.api()), rtc.Shapes(rtc.api())
+    r2 = math.sqrt(2.0) / 2.0
+    ray = [[0, 0, -3, 0, -r2, r2]]
+
+    w = rtc.World.default_world()
+    plane = S.plane()
+    plane.material.reflective = 0.5
+    plane.set_transform(T.translation(0, -1, 0))
+    w.push(plane)
+    np.testing.assert_allclose(w.color_at(ray)[0], [0.87675, 0.92434, 0.82918], atol=1e-5)
+
+    for reflective, want in ((0.0, [0.93642, 0.68642, 0.68642]), (0.5, [0.93391, 0.69643, 0.69243])):
+        w = rtc.World.default_world()
+        floor = S.plane()
+        floor.set_transform(T.translation(0, -1, 0))
+        floor.material.reflective, floor.material.transparency, floor.material.refractive_index = reflective, 0.5, 1.5
+        w.push(floor)
+        ball = S.sphere()
+        ball.material.color, ball.material.ambient = (1, 0, 0), 0.5
+        ball.set_transform(T.translation(0, -3.5, -0.5))
+        w.push(ball)
+        np.testing.assert_allclose(w.color_at(ray)[0], want, atol=1e-5)
+
+
 def test_row_bands_tile_the_frame(rtc):
     """rtc_rows: cyclic row bands rendered separately reassemble into the full frame (the multi-GPU sharding)."""
     world, cam = rtc.build_scene("table", 200, 117)  # 117 rows: the last band is ragged
