@@ -265,6 +265,15 @@ const double* rtc_canvas_pixels_f64(const rtc_canvas* c); /* NULL if rendered wi
 const uint8_t* rtc_canvas_pixels_rgba8(const rtc_canvas* c);
 /* canvas.rs:28-58: P3 text, 70-column wrap.  Returns a malloc'd buffer (free with rtc_free). */
 char* rtc_canvas_to_ppm(const rtc_canvas* c, uint64_t* len);
+/* Canvas::to_ppm ON THE DEVICE: encodes an RGBA8 frame that is still in HBM (e.g. the output of rtc_render_device, or
+ * the frame gathered on rank 0) straight into the reference's P3 text — rows in parallel, 70-column wrap per row, prefix
+ * sum of row sizes — and copies only the text to out_host (capacity >= rtc_ppm_max_bytes(w, h) always suffices; pinned
+ * memory from rtc_pinned_alloc makes the copy run at PCIe speed).  Byte-identical to rtc_canvas_to_ppm. */
+uint64_t rtc_ppm_max_bytes(uint64_t width, uint64_t height);
+int rtc_ppm_encode_device(int device, const void* d_rgba8, uint64_t width, uint64_t height, void* cuda_stream,
+                          char* out_host, uint64_t capacity, uint64_t* len);
+void* rtc_pinned_alloc(uint64_t bytes); /* NULL without a CUDA device */
+void rtc_pinned_free(void* p);
 /* the same encoder over a caller-owned RGBA8 frame (e.g. a frame gathered from several GPUs) */
 char* rtc_ppm_from_rgba8(const uint8_t* rgba8, uint64_t width, uint64_t height, uint64_t* len);
 void rtc_free(void* p);

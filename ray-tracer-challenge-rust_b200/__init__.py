@@ -20,7 +20,7 @@ from .scene_api import (BLACK, BLUE, GREEN, RED, WHITE, CameraHandle, Light, Mat
                         Transformations, WorldHandle)
 
 __all__ = ["api", "World", "Camera", "Canvas", "Light", "Material", "Pattern", "Shapes", "Transformations", "Matrix",
-           "Rows", "Stats", "RtcError", "scenes", "device_count", "measure_fp64_peak", "ppm_from_rgba8"]
+           "Rows", "Stats", "RtcError", "scenes", "device_count", "measure_fp64_peak", "ppm_from_rgba8", "ppm_from_device"]
 
 
 def device_count():
@@ -45,6 +45,23 @@ def ppm_from_rgba8(rgba8, width, height):
         return C.string_at(p, n.value)
     finally:
         api().free(p)
+
+
+def ppm_from_device(d_rgba8, width, height, device=0, stream=0):
+    """Canvas::to_ppm on the GPU for an RGBA8 frame that lives in device memory (d_rgba8: device pointer as int, e.g.
+    tensor.data_ptr()) -> bytes.  Only the text crosses PCIe."""
+    a = api()
+    cap = a.ppm_max_bytes(width, height)
+    buf = a.pinned_alloc(cap)
+    if not buf:
+        raise RtcError(RTC_ERR_CUDA, "cannot allocate pinned memory: " + a.error())
+    try:
+        n = C.c_uint64(0)
+        a.check(a.ppm_encode_device(device, C.c_void_p(d_rgba8), width, height, C.c_void_p(stream) if stream else None,
+                                    C.c_void_p(buf), cap, C.byref(n)))
+        return C.string_at(buf, n.value)
+    finally:
+        a.pinned_free(buf)
 
 
 class Canvas:

@@ -60,6 +60,10 @@ class RtcApi(BuilderApi):
         f("canvas_pixels_rgba8", u8p, vp)
         f("canvas_to_ppm", vp, vp, c_u64_p)
         f("ppm_from_rgba8", vp, vp, C.c_uint64, C.c_uint64, c_u64_p)
+        f("ppm_max_bytes", C.c_uint64, C.c_uint64, C.c_uint64)
+        f("ppm_encode_device", C.c_int, C.c_int, vp, C.c_uint64, C.c_uint64, vp, vp, C.c_uint64, c_u64_p)
+        f("pinned_alloc", vp, C.c_uint64)
+        f("pinned_free", None, vp)
         f("free", None, vp)
 
     def check(self, rc):

@@ -587,6 +587,18 @@ char* rtc_ppm_from_rgba8(const uint8_t* rgba8, uint64_t width, uint64_t height, 
     *len = s.size();
     return out;
 }
+uint64_t rtc_ppm_max_bytes(uint64_t width, uint64_t height) { return ppm_max_bytes(width, height); }
+int rtc_ppm_encode_device(int device, const void* d_rgba8, uint64_t width, uint64_t height, void* cuda_stream,
+                          char* out_host, uint64_t capacity, uint64_t* len) {
+    if (!d_rgba8 || !out_host || !len) return set_err(RTC_ERR_INVALID, "null argument");
+    std::string e;
+    int rc = ppm_encode_device(device, d_rgba8, width, height, cuda_stream, out_host, capacity, len, &e);
+    if (rc == -1) return set_err(RTC_ERR_INVALID, "output buffer too small (see rtc_ppm_max_bytes)");
+    if (rc != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+void* rtc_pinned_alloc(uint64_t bytes) { return pinned_alloc((size_t)bytes); }
+void rtc_pinned_free(void* p) { pinned_free(p); }
 void rtc_free(void* p) { std::free(p); }
 
 }  // extern "C"

@@ -45,6 +45,12 @@ int render_tally(DeviceScene* s, const DCamera& cam, const DRows& rows, unsigned
 
 int measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops, std::string* err);
 
+// Canvas::to_ppm on the device (ppm_encode.cu): RGBA8 frame in HBM -> P3 text in out_host.  -1: capacity too small
+// (*len is set); -3: CUDA error.
+uint64_t ppm_max_bytes(uint64_t width, uint64_t height);
+int ppm_encode_device(int device, const void* d_rgba8, uint64_t width, uint64_t height, void* stream, char* out_host,
+                      uint64_t capacity, uint64_t* len, std::string* err);
+
 // Pinned host memory for frame buffers (so device->host copies run at PCIe speed); falls back to nothing — returns null
 // on failure and the caller reports RTC_ERR_CUDA.
 void* pinned_alloc(size_t bytes);

@@ -203,6 +203,29 @@ def test_host_output_chunks_match_single_launch(rtc):
     assert np.array_equal(one, two)
 
 
+def test_device_ppm_encoder_is_byte_identical(rtc, oracle):
+    """rtc_ppm_encode_device (to_ppm on the GPU) == the host encoder == the reference encoder, on random
+    frames (every digit count, every wrap position), ragged sizes, and a rendered frame that never left the device."""
+    import torch
+    rng = np.random.default_rng(11)
+    for w, h in ((1, 1), (5, 3), (23, 7), (24, 1), (640, 33), (1921, 5)):
+        frame = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        frame[..., 3] = 255
+        if w > 20:
+            frame[0, :, :3] = 255   # a row of three-digit values
+            frame[-1, :, :3] = 7    # a row of one-digit values
+        d = torch.from_numpy(frame).cuda()
+        got = rtc.ppm_from_device(d.data_ptr(), w, h)
+        assert got == rtc.ppm_from_rgba8(frame, w, h)
+        rgb = frame[..., :3].reshape(-1, 3).astype(np.float64) / 255.0
+        assert got == oracle.ppm(rgb, w, h)
+    world, cam = rtc.build_scene("table", 640, 360)
+    buf = torch.zeros((360, 640, 4), dtype=torch.uint8, device="cuda:0")
+    cam.render_device(world, d_rgba8=buf.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rtc.ppm_from_device(buf.data_ptr(), 640, 360) == cam.render(world).to_ppm()
+
+
 def test_device_output_and_torch_stream(rtc):
     """rtc_render_device writes into torch-owned device memory on torch's current stream."""
     import torch
