@@ -3,10 +3,11 @@
 //
 // The format's only sequential dependence is the 70-column line wrap, and it restarts at every image row
 // (canvas.rs:34), so rows are independent:
-//   1. ppm_row_bytes_kernel — one thread per row walks the row's 3*W channel values with the reference's wrap rule and
-//      counts the row's bytes;
+//   1. ppm_row_bytes_kernel — one thread per row walks the row's 3*W channel values with the reference's wrap rule,
+//      counts the row's bytes and notes where every text line starts;
 //   2. ppm_row_offsets_kernel — exclusive prefix sum of the row sizes (one block; H is at most a few thousand);
-//   3. ppm_row_write_kernel  — one thread per row replays the walk and writes the characters at its row's offset.
+//   3. ppm_line_write_kernel — one CTA per row, one thread per text LINE (pass 1 recorded where each line starts):
+//      digits, single spaces and the line's newline, written in place.
 // Byte/integer work, bound by HBM writes of ~12 bytes per pixel; no floating point at all.
 #include <cuda_runtime.h>
 
@@ -38,24 +39,31 @@ __device__ __forceinline__ unsigned ppm_token(unsigned& len, unsigned n, bool& n
     return add;
 }
 
-__global__ void ppm_row_bytes_kernel(const uchar4* __restrict__ px, unsigned width, unsigned height,
-                                     unsigned long long* __restrict__ row_bytes) {
+// pass 1: the wrap rule is a sequential walk of the row's tokens — do it once, per row, and write down where every LINE of
+// the row starts (token index and byte offset inside the row) so that pass 3 can give every line its own thread
+__global__ void ppm_row_bytes_kernel(const uchar4* __restrict__ px, unsigned width, unsigned height, unsigned max_lines,
+                                     unsigned long long* __restrict__ row_bytes, unsigned* __restrict__ row_lines,
+                                     uint2* __restrict__ lines) {
     const unsigned y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= height) return;
     const uchar4* row = px + (size_t)y * width;
-    unsigned len = 0;
-    unsigned long long bytes = 0;
+    uint2* mine = lines + (size_t)y * max_lines;
+    unsigned len = 0, bytes = 0, nlines = 0, tok = 0;
+    mine[nlines++] = make_uint2(0u, 0u);
     for (unsigned x = 0; x < width; x++) {
         const uchar4 p = row[x];
         const unsigned v[3] = {p.x, p.y, p.z};
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
+        for (int c = 0; c < 3; c++, tok++) {
             const unsigned n = 1u + (v[c] >= 10u) + (v[c] >= 100u);
             bool nl;
-            bytes += ppm_token(len, n, nl);
+            const unsigned add = ppm_token(len, n, nl);
+            if (nl) mine[nlines++] = make_uint2(tok, bytes + 1);  // the line starts after the newline character
+            bytes += add;
         }
     }
-    row_bytes[y] = bytes + 1;  // the newline that ends the row (canvas.rs:56)
+    row_bytes[y] = (unsigned long long)bytes + 1;  // the newline that ends the row (canvas.rs:56)
+    row_lines[y] = nlines;
 }
 
 // one block: row_off[y] = header + sum of row_bytes[0..y); total at row_off[height]
@@ -86,31 +94,31 @@ __global__ void ppm_row_offsets_kernel(const unsigned long long* __restrict__ ro
     }
 }
 
-__global__ void ppm_row_write_kernel(const uchar4* __restrict__ px, unsigned width, unsigned height,
-                                     const unsigned long long* __restrict__ row_off, char* __restrict__ out) {
-    const unsigned y = blockIdx.x * blockDim.x + threadIdx.x;
-    if (y >= height) return;
+// pass 3: one CTA per row, one thread per text line (<= 70 characters): digits, single spaces, the line's newline
+__global__ void ppm_line_write_kernel(const uchar4* __restrict__ px, unsigned width, unsigned max_lines,
+                                      const unsigned long long* __restrict__ row_off,
+                                      const unsigned* __restrict__ row_lines, const uint2* __restrict__ lines,
+                                      char* __restrict__ out) {
+    const unsigned y = blockIdx.x;
     const uchar4* row = px + (size_t)y * width;
-    char* o = out + row_off[y];
-    unsigned len = 0;
-    for (unsigned x = 0; x < width; x++) {
-        const uchar4 p = row[x];
-        const unsigned v[3] = {p.x, p.y, p.z};
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const unsigned n = 1u + (v[c] >= 10u) + (v[c] >= 100u);
-            const bool had = len > 0;
-            bool nl;
-            ppm_token(len, n, nl);
-            if (nl) *o++ = '\n';
-            else if (had) *o++ = ' ';
-            const unsigned h = v[c] / 100u, t = (v[c] / 10u) % 10u, u = v[c] % 10u;
-            if (n == 3) *o++ = (char)('0' + h);
-            if (n >= 2) *o++ = (char)('0' + t);
-            *o++ = (char)('0' + u);
+    const uint2* mine = lines + (size_t)y * max_lines;
+    const unsigned nlines = row_lines[y], ntok = 3u * width;
+    char* base = out + row_off[y];
+    for (unsigned k = threadIdx.x; k < nlines; k += blockDim.x) {
+        const uint2 ln = mine[k];
+        const unsigned end = (k + 1 < nlines) ? mine[k + 1].x : ntok;
+        char* o = base + ln.y;
+        for (unsigned tok = ln.x; tok < end; tok++) {
+            const uchar4 p = row[tok / 3u];
+            const unsigned c = tok % 3u;
+            const unsigned v = c == 0 ? p.x : (c == 1 ? p.y : p.z);
+            if (tok != ln.x) *o++ = ' ';
+            if (v >= 100u) *o++ = (char)('0' + v / 100u);
+            if (v >= 10u) *o++ = (char)('0' + (v / 10u) % 10u);
+            *o++ = (char)('0' + v % 10u);
         }
+        *o = '\n';  // ends the line — for the row's last line this is the row terminator (canvas.rs:56)
     }
-    *o = '\n';
 }
 
 }  // namespace
@@ -138,18 +146,25 @@ int ppm_encode_device(int device, const void* d_rgba8, uint64_t width, uint64_t 
         return 0;
     }
     unsigned long long *d_bytes = nullptr, *d_off = nullptr;
+    unsigned* d_nlines = nullptr;
+    uint2* d_lines = nullptr;
     char* d_text = nullptr;
     const uint64_t cap = ppm_max_bytes(width, height);
+    // a line holds at least 17 tokens (17 * 4 = 68 <= 70 characters), plus the row's first line
+    const unsigned max_lines = (unsigned)((3 * width) / 17 + 2);
     e = cudaMallocAsync((void**)&d_bytes, sizeof(unsigned long long) * height, st);
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_off, sizeof(unsigned long long) * (height + 1), st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_nlines, sizeof(unsigned) * height, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_lines, sizeof(uint2) * height * max_lines, st);
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_text, cap, st);
     int rc = 0;
     if (e == cudaSuccess) {
         const unsigned h = (unsigned)height, w = (unsigned)width;
         // 32-thread blocks: rows are long sequential walks, spread them over as many SMs as there are
-        ppm_row_bytes_kernel<<<(h + 31) / 32, 32, 0, st>>>((const uchar4*)d_rgba8, w, h, d_bytes);
+        ppm_row_bytes_kernel<<<(h + 31) / 32, 32, 0, st>>>((const uchar4*)d_rgba8, w, h, max_lines, d_bytes, d_nlines,
+                                                           d_lines);
         ppm_row_offsets_kernel<<<1, 1024, 0, st>>>(d_bytes, h, (unsigned long long)hl, d_off);
-        ppm_row_write_kernel<<<(h + 31) / 32, 32, 0, st>>>((const uchar4*)d_rgba8, w, h, d_off, d_text);
+        ppm_line_write_kernel<<<h, 128, 0, st>>>((const uchar4*)d_rgba8, w, max_lines, d_off, d_nlines, d_lines, d_text);
         e = cudaGetLastError();
     }
     unsigned long long total = 0;
@@ -166,6 +181,8 @@ int ppm_encode_device(int device, const void* d_rgba8, uint64_t width, uint64_t 
     }
     if (d_bytes) cudaFreeAsync(d_bytes, st);
     if (d_off) cudaFreeAsync(d_off, st);
+    if (d_nlines) cudaFreeAsync(d_nlines, st);
+    if (d_lines) cudaFreeAsync(d_lines, st);
     if (d_text) cudaFreeAsync(d_text, st);
     if (e != cudaSuccess) return fail("ppm_encode_device", e);
     return rc;
