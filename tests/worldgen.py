@@ -88,6 +88,11 @@ def random_world(api, seed, hsize=48, vsize=32, nobjects=10, groups=True):
                 leaf.set_transform(_rand_transform(T, rng, spread=1.0))
                 leaf.material = _rand_material(T, rng)
                 g.push_shape(leaf)
+            if rng.random() < 0.25:  # a plane inside a group: Bounds::new gives it the (sic) box (-1,-1,0)..(1,1,0)
+                pl = S.plane()
+                pl.set_transform(T.translation(0, rng.uniform(-0.5, 0.5), 0) * T.rotation_x(rng.uniform(-0.4, 0.4)))
+                pl.material = _rand_material(T, rng)
+                g.push_shape(pl)
             if rng.random() < 0.5:  # nested group
                 inner = S.group()
                 leaf = S.sphere()
