@@ -67,8 +67,22 @@ def cpu_reference_sample(workload, w, h, step, threads=1):
     orc = helpers.load_oracle()
     ow, oc = helpers.scenes.build(orc, workload, w, h)
     px = helpers.subset_pixels(w, h, step, step // 2)
-    rgb, cnt = orc.render(ow, oc, mode=orc.FAITHFUL, nthreads=threads, pixels=px)
+    # the reference is one thread: pin it to one core for the timed sample, then give the cores back
+    allowed = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    try:
+        if allowed and threads == 1:
+            os.sched_setaffinity(0, {sorted(allowed)[0]})
+        rgb, cnt = orc.render(ow, oc, mode=orc.FAITHFUL, nthreads=threads, pixels=px)
+    finally:
+        if allowed:
+            os.sched_setaffinity(0, allowed)
     cpu_reference_sample.last = (px, orc.quantise_rgba8(rgb))  # the sample's pixels, for the caller's parity check
+    # informative second baseline: the same arithmetic with the reference's two per-ray recomputations cached
+    # (Matrix::inverse, Bounds::new), on every host core
+    _, c2 = orc.render(ow, oc, mode=orc.CACHED, nthreads=os.cpu_count() or 1, pixels=px)
+    cpu_reference_sample.cached = {"value": c2.total_rays / max(c2.seconds, 1e-9) / 1e6, "unit": "Mrays/s",
+                                   "cores": os.cpu_count() or 1,
+                                   "what": "oracle cached mode (inverses and group boxes precomputed), all host cores"}
     return cnt.total_rays, cnt.seconds, len(px)
 
 
@@ -374,7 +388,8 @@ def run_b200(args):
             "value": r / s / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
             "sample": f"every {step_px}th pixel in x and y of the {w}x{h} camera ({n} px, {r} rays, {s:.1f} s) with the "
                       "reference's algorithm (oracle faithful mode); 1 thread because the reference is single-threaded",
-            "frame_ms_extrapolated": s * 1e3 * (w * h / n), "host_cores_available": os.cpu_count()}
+            "frame_ms_extrapolated": s * 1e3 * (w * h / n), "host_cores_available": os.cpu_count(),
+            "pinned_to_one_core": True, "cached_all_cores": cpu_reference_sample.cached}
 
     if not args.no_extras and world_size == 1:
         extras = {}
