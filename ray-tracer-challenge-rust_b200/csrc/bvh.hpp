@@ -10,6 +10,7 @@
 // kSahDepth) so the device's fixed traversal stack (kBvhStackDepth) cannot overflow.
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -230,14 +231,68 @@ struct BvhBuilder {
 
 // Appends the mesh's nodes to `nodes`; fills `order` (slot -> input triangle; the caller stores triangles in this order
 // starting at global slot `tri_base`).  Returns the root node index, or -1 when the mesh is small enough to scan.
-// The top kParallelDepth levels are split on the calling thread; the subtrees below them are built concurrently, each into
-// its own node array, and spliced in a fixed order — the result does not depend on thread timing.
+// The top kParallelDepth levels fork: a range is split on the thread that owns it, its right half goes to a new thread
+// and its left half stays, so level d runs 2^d splits at once and the critical path is n + n/2 + n/4 + the deepest
+// subtree.  Every range builds into its own node array and the arrays are spliced parent, left, right — the result does
+// not depend on thread timing.
 constexpr int kParallelDepth = 3;
 constexpr uint32_t kParallelMin = 2048;
 
+namespace detail {
+
+struct Built {
+    std::vector<DBvhNode> nodes;  // indices local to this array; leaf slots are item positions
+    Sub sub;
+    int depth = 0;
+};
+
+inline void build_range(std::vector<Item>& items, double pad, uint32_t begin, uint32_t end, int depth, Built& out) {
+    BvhBuilder b{items, out.nodes, pad};
+    if (depth >= kParallelDepth || end - begin < kParallelMin) {
+        out.sub = b.build(begin, end, depth);
+        out.depth = b.max_depth;
+        return;
+    }
+    Aabb box, cbox;
+    b.range_boxes(begin, end, box, cbox);
+    const uint32_t mid = b.split(begin, end, depth, cbox);
+    Built left, right;
+    std::thread other([&] { build_range(items, pad, mid, end, depth + 1, right); });
+    build_range(items, pad, begin, mid, depth + 1, left);
+    other.join();
+    out.nodes.reserve(1 + left.nodes.size() + right.nodes.size());
+    out.nodes.emplace_back();
+    auto append = [&](const Built& c) {
+        const int32_t base = (int32_t)out.nodes.size();
+        for (DBvhNode nd : c.nodes) {
+            if (nd.count0 == 0) nd.child0 += base;
+            if (nd.count1 == 0) nd.child1 += base;
+            out.nodes.push_back(nd);
+        }
+        Sub s = c.sub;
+        if (!s.leaf) s.index += base;
+        return s;
+    };
+    const Sub l = append(left);
+    const Sub r = append(right);
+    std::memset(&out.nodes[0], 0, sizeof(DBvhNode));
+    b.fill(out.nodes[0], l, r);
+    out.sub = Sub{false, 0, 0, box};
+    out.depth = std::max(left.depth, right.depth);
+}
+
+}  // namespace detail
+
 inline int32_t build_bvh(const std::vector<BvhTri>& tris, std::vector<DBvhNode>& nodes, int32_t tri_base,
-                         std::vector<uint32_t>& order, int* max_depth, double* max_abs_out = nullptr) {
+                         std::vector<uint32_t>& order, int* max_depth, double* max_abs_out = nullptr,
+                         double* phase_ms = nullptr) {  // phase_ms[3]: items, build, splice
     using namespace detail;
+    auto lap_from = std::chrono::steady_clock::now();
+    auto lap = [&](int k) {
+        const auto now = std::chrono::steady_clock::now();
+        if (phase_ms) phase_ms[k] += std::chrono::duration<double, std::milli>(now - lap_from).count();
+        lap_from = now;
+    };
     const uint32_t n = (uint32_t)tris.size();
     order.resize(n);
     for (uint32_t i = 0; i < n; i++) order[i] = i;
@@ -259,109 +314,22 @@ inline int32_t build_bvh(const std::vector<BvhTri>& tris, std::vector<DBvhNode>&
     if (max_abs_out) *max_abs_out = max_abs;
     if (n <= (uint32_t)kLeafMax) return -1;
     const double pad = kPadRel * std::max(max_abs, std::numeric_limits<double>::min());
-
-    // phase 1: split the top levels, remembering the open ranges
-    struct Open {
-        uint32_t begin, end;
-        int depth;
-        int32_t parent;  // node (in `top`) whose child slot this range fills, -1 for the root
-        int side;
-    };
-    std::vector<DBvhNode> top;
-    std::vector<Open> open, pending{{0, n, 0, -1, 0}};
-    BvhBuilder tb{items, top, pad};
-    int depth_seen = 0;
-    while (!pending.empty()) {
-        Open o = pending.back();
-        pending.pop_back();
-        const uint32_t cnt = o.end - o.begin;
-        if (o.depth >= kParallelDepth || cnt < kParallelMin) {
-            open.push_back(o);
-            continue;
-        }
-        Aabb box, cbox;
-        tb.range_boxes(o.begin, o.end, box, cbox);
-        const uint32_t mid = tb.split(o.begin, o.end, o.depth, cbox);
-        const int32_t me = (int32_t)top.size();
-        top.emplace_back();
-        std::memset(&top[me], 0, sizeof(DBvhNode));
-        if (o.parent >= 0) (o.side ? top[o.parent].child1 : top[o.parent].child0) = me;  // inner child: count stays 0
-        pending.push_back(Open{mid, o.end, o.depth + 1, me, 1});
-        pending.push_back(Open{o.begin, mid, o.depth + 1, me, 0});
-        depth_seen = std::max(depth_seen, o.depth);
-    }
-    // phase 2: the open ranges, concurrently, each into its own node array
-    struct Done {
-        std::vector<DBvhNode> nodes;
-        Sub sub;
-        int depth;
-    };
-    std::vector<Done> done(open.size());
-    auto work = [&](size_t k) {
-        BvhBuilder b{items, done[k].nodes, pad};
-        done[k].sub = b.build(open[k].begin, open[k].end, open[k].depth);
-        done[k].depth = b.max_depth;
-    };
-    if (open.size() > 1) {
-        std::vector<std::thread> th;
-        for (size_t k = 1; k < open.size(); k++) th.emplace_back(work, k);
-        work(0);
-        for (auto& t : th) t.join();
-    } else {
-        work(0);
-    }
-    // phase 3: splice.  Global node index = base of its array; leaf slots are item positions + tri_base.
-    const int32_t top_base = (int32_t)nodes.size();
-    std::vector<int32_t> base(open.size());
-    int32_t at = top_base + (int32_t)top.size();
-    for (size_t k = 0; k < open.size(); k++) {
-        base[k] = at;
-        at += (int32_t)done[k].nodes.size();
-        depth_seen = std::max(depth_seen, done[k].depth);
-    }
-    // boxes of the top nodes' children, bottom-up: children were created after their parents, so walk backwards
-    std::vector<Aabb> top_box(top.size());
-    std::vector<Sub> open_sub(open.size());
-    for (size_t k = 0; k < open.size(); k++) {
-        Sub s = done[k].sub;
-        if (s.leaf) s.index += tri_base;
-        else s.index += base[k];
-        open_sub[k] = s;
-    }
-    // child links of top nodes: inner links were stored as top-local indices; open ranges fill the rest
-    std::vector<Sub> child[2];
-    child[0].resize(top.size());
-    child[1].resize(top.size());
-    std::vector<char> have[2];
-    have[0].assign(top.size(), 0);
-    have[1].assign(top.size(), 0);
-    for (size_t k = 0; k < open.size(); k++)
-        if (open[k].parent >= 0) {
-            child[open[k].side][open[k].parent] = open_sub[k];
-            have[open[k].side][open[k].parent] = 1;
-        }
-    for (int32_t t = (int32_t)top.size() - 1; t >= 0; t--) {
-        for (int side = 0; side < 2; side++)
-            if (!have[side][t]) {  // an inner top node
-                const int32_t c = side ? top[t].child1 : top[t].child0;
-                child[side][t] = Sub{false, top_base + c, 0, top_box[c]};
-            }
-        top_box[t] = child[0][t].box;
-        top_box[t].grow(child[1][t].box);
-        tb.fill(top[t], child[0][t], child[1][t]);
-    }
-    nodes.insert(nodes.end(), top.begin(), top.end());
-    for (size_t k = 0; k < open.size(); k++) {
-        for (DBvhNode nd : done[k].nodes) {
-            if (nd.count0 > 0) nd.child0 += tri_base; else nd.child0 += base[k];
-            if (nd.count1 > 0) nd.child1 += tri_base; else nd.child1 += base[k];
-            nodes.push_back(nd);
-        }
+    lap(0);
+    Built root;
+    build_range(items, pad, 0, n, 0, root);
+    lap(1);
+    // global indices: nodes after the ones already in `nodes`, leaf slots after tri_base
+    const int32_t base = (int32_t)nodes.size();
+    nodes.reserve(nodes.size() + root.nodes.size());
+    for (DBvhNode nd : root.nodes) {
+        nd.child0 += nd.count0 > 0 ? tri_base : base;
+        nd.child1 += nd.count1 > 0 ? tri_base : base;
+        nodes.push_back(nd);
     }
     for (uint32_t i = 0; i < n; i++) order[i] = items[i].id;
-    if (max_depth) *max_depth = depth_seen + 1;
-    if (top.empty()) return open_sub[0].leaf ? -1 : open_sub[0].index;
-    return top_base;
+    if (max_depth) *max_depth = root.depth + 1;
+    lap(2);
+    return root.sub.leaf ? -1 : base + root.sub.index;
 }
 
 }  // namespace rtc

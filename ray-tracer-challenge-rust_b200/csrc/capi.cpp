@@ -3,6 +3,7 @@
 // API.  There is no CPU rendering path in this library: every render / color_at call needs a CUDA device and fails with
 // RTC_ERR_CUDA otherwise.
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <mutex>
 #include <sstream>
@@ -136,6 +137,16 @@ int rtc_device_count(void) {
     return n;
 }
 
+// RTC_B200_TRACE=1: where the host time of a scene build went (stderr, one line per call)
+static void trace_phases(const char* who, const FlatScene& flat) {
+    static const bool trace = std::getenv("RTC_B200_TRACE") != nullptr;
+    if (!trace) return;
+    const double* t = flat.phase_ms;
+    std::fprintf(stderr, "[rtc] %s: validate %.3f  group bounds %.3f  bvh items %.3f / build %.3f / splice %.3f  "
+                         "triangle tables %.3f  upload %.3f ms (%zu triangles, %zu bvh nodes)\n",
+                 who, t[0], t[1], t[2], t[3], t[4], t[5], t[6], flat.tris.size(), flat.bvh.size());
+}
+
 /* ---------------------------------------------------------------------------------------------- 1. CORE BOUNDARY */
 int rtc_scene_create(const rtc_scene_desc* desc, int device, rtc_scene** out) {
     if (!desc || !out) return set_err(RTC_ERR_INVALID, "null argument");
@@ -145,8 +156,11 @@ int rtc_scene_create(const rtc_scene_desc* desc, int device, rtc_scene** out) {
     int rc = flatten_scene(*desc, flat, &e);
     if (rc != RTC_OK) return set_err(rc, e);
     DeviceScene* dev = nullptr;
+    PhaseClock clock;
     rc = device_scene_create(flat, device, &dev, &e);
     if (rc != 0) return set_err(RTC_ERR_CUDA, e);
+    clock.lap(flat.phase_ms, FlatScene::T_UPLOAD);
+    trace_phases("rtc_scene_create", flat);
     rtc_scene* s = new rtc_scene();
     s->dev = dev;
     s->info[0] = flat.leaf_count;
@@ -444,6 +458,7 @@ int rtc_world_flatten_info(rtc_world* w, uint64_t n[8], double* gates_out, uint6
     std::string e;
     int rc = flatten_scene(m.desc, flat, &e);
     if (rc != RTC_OK) return set_err(rc, e);
+    trace_phases("rtc_world_flatten_info", flat);
     n[0] = flat.leaf_count;
     n[1] = flat.gates.size();
     n[2] = flat.meshes.size();

@@ -1,5 +1,6 @@
 // flat_scene.hpp — the flattened World as host vectors (output of flatten.hpp, input of the device upload).
 #pragma once
+#include <chrono>
 #include <cstdint>
 #include <vector>
 
@@ -24,6 +25,18 @@ struct FlatScene {
     float reject_extent = 0.f;
     int32_t merged_gates = 0;  // nested single-child groups whose identical box shares the parent's gate
     int bvh_max_depth = 0;
+    // where rtc_scene_create's host time went (ms), printed under RTC_B200_TRACE=1
+    enum { T_VALIDATE, T_BOUNDS, T_BVH_ITEMS, T_BVH_BUILD, T_BVH_SPLICE, T_TRIANGLES, T_UPLOAD, T_COUNT };
+    double phase_ms[T_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+};
+
+struct PhaseClock {  // adds the time since construction (or the last lap) to a FlatScene phase
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(double* phase_ms, int phase) {
+        const auto t1 = std::chrono::steady_clock::now();
+        phase_ms[phase] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+    }
 };
 
 }  // namespace rtc

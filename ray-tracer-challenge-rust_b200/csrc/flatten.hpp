@@ -14,6 +14,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rtc.h"
@@ -49,6 +50,7 @@ class Flattener {
         check(d_.transform_count == 0 || d_.transforms, "transforms is NULL");
         check(d_.material_count == 0 || d_.materials, "materials is NULL");
         check(d_.triangle_count == 0 || d_.triangles, "triangles is NULL");
+        PhaseClock clock;
         // subtree extents of the pre-order walk
         end_.assign(d_.shape_count, 0);
         uint32_t pos = 0;
@@ -60,6 +62,7 @@ class Flattener {
             out_.light_pos[k] = d_.light_position[k];
             out_.light_int[k] = d_.light_intensity[k];
         }
+        clock.lap(out_.phase_ms, FlatScene::T_VALIDATE);
         emit_children(0, d_.shape_count);  // World.objects in order (world.rs:46-50)
         out_.leaf_count = next_leaf_;
         if (!out_.meshes.empty()) out_.feature_mask |= 32;
@@ -152,8 +155,24 @@ class Flattener {
     static void add(Box4& b, const Vec4& p) {  // bounds.rs:142-151
         if (!(p.w == 1.0)) fail(RTC_ERR_PANIC, "assertion failed: point.is_point() (src/bounds.rs:143) — a group holds a "
                                                "shape with an unbounded box (uncapped cylinder/cone)");
-        b.min.x = std::fmin(b.min.x, p.x); b.min.y = std::fmin(b.min.y, p.y); b.min.z = std::fmin(b.min.z, p.z);
-        b.max.x = std::fmax(b.max.x, p.x); b.max.y = std::fmax(b.max.y, p.y); b.max.z = std::fmax(b.max.z, p.z);
+        b.min.x = min_(b.min.x, p.x); b.min.y = min_(b.min.y, p.y); b.min.z = min_(b.min.z, p.z);
+        b.max.x = max_(b.max.x, p.x); b.max.y = max_(b.max.y, p.y); b.max.z = max_(b.max.z, p.z);
+    }
+    // f64::min / f64::max (a NaN operand loses), inline: libm's fmin/fmax calls were half of a mesh group's box time.
+    // On a +0 / -0 tie either may come back (as with f64::min); no comparison a gate makes can tell them apart.
+    static double min_(double a, double b) { return a != a ? b : (b < a ? b : a); }
+    static double max_(double a, double b) { return a != a ? b : (b > a ? b : a); }
+    void fold_child(Box4& out, uint32_t c) {  // bounds.rs:52-124: the child's box, eight corners through its transform
+        const Box4 pb = bounds_of(c);
+        const Mat4 tr = Mat4::from(d_.transforms[d_.shapes[c].transform].transform);
+        add(out, mul(tr, point(pb.min.x, pb.min.y, pb.min.z)));
+        add(out, mul(tr, point(pb.min.x, pb.min.y, pb.max.z)));
+        add(out, mul(tr, point(pb.min.x, pb.max.y, pb.min.z)));
+        add(out, mul(tr, point(pb.min.x, pb.max.y, pb.max.z)));
+        add(out, mul(tr, point(pb.max.x, pb.min.y, pb.min.z)));
+        add(out, mul(tr, point(pb.max.x, pb.min.y, pb.max.z)));
+        add(out, mul(tr, point(pb.max.x, pb.max.y, pb.min.z)));
+        add(out, mul(tr, pb.max));
     }
     Box4 bounds_of(uint32_t i) {
         const rtc_shape_desc& s = d_.shapes[i];
@@ -178,18 +197,38 @@ class Flattener {
                 auto hit = group_bounds_.find(i);
                 if (hit != group_bounds_.end()) return hit->second;
                 Box4 out{point(0., 0., 0.), point(0., 0., 0.)};
-                for (uint32_t c = i + 1; c < end_[i]; c = end_[c]) {
-                    Box4 pb = bounds_of(c);
-                    Mat4 tr = Mat4::from(d_.transforms[d_.shapes[c].transform].transform);
-                    add(out, mul(tr, point(pb.min.x, pb.min.y, pb.min.z)));
-                    add(out, mul(tr, point(pb.min.x, pb.min.y, pb.max.z)));
-                    add(out, mul(tr, point(pb.min.x, pb.max.y, pb.min.z)));
-                    add(out, mul(tr, point(pb.min.x, pb.max.y, pb.max.z)));
-                    add(out, mul(tr, point(pb.max.x, pb.min.y, pb.min.z)));
-                    add(out, mul(tr, point(pb.max.x, pb.min.y, pb.max.z)));
-                    add(out, mul(tr, point(pb.max.x, pb.max.y, pb.min.z)));
-                    add(out, mul(tr, pb.max));
+                const uint32_t first = i + 1, last = end_[i];
+                bool folded = false;
+                if ((uint32_t)s.child_count >= kParallelMin * 2 && last - first == (uint32_t)s.child_count) {
+                    // a long run of leaves (an OBJ mesh): slices fold on their own threads, each from the origin seed the
+                    // whole fold starts from, and min/max merge them — the same box.  A slice that would panic leaves
+                    // the serial loop below to raise it at the right child.
+                    const uint32_t slices = std::min<uint32_t>(8, std::max(1u, std::thread::hardware_concurrency()));
+                    std::vector<Box4> part(slices, out);
+                    std::vector<char> ok(slices, 1);
+                    std::vector<std::thread> th;
+                    auto run = [&](uint32_t k) {
+                        const uint32_t a = first + (uint64_t)(last - first) * k / slices;
+                        const uint32_t b = first + (uint64_t)(last - first) * (k + 1) / slices;
+                        try {
+                            for (uint32_t c = a; c < b; c++) fold_child(part[k], c);
+                        } catch (const FlattenError&) {
+                            ok[k] = 0;
+                        }
+                    };
+                    for (uint32_t k = 1; k < slices; k++) th.emplace_back(run, k);
+                    run(0);
+                    for (auto& t : th) t.join();
+                    folded = true;
+                    for (uint32_t k = 0; k < slices; k++) folded = folded && ok[k];
+                    if (folded)
+                        for (const Box4& p : part) {
+                            add(out, p.min);
+                            add(out, p.max);
+                        }
                 }
+                if (!folded)
+                    for (uint32_t c = first; c < last; c = end_[c]) fold_child(out, c);
                 group_bounds_.emplace(i, out);
                 return out;
             }
@@ -309,7 +348,9 @@ class Flattener {
         Mat4 id = Mat4::identity();
         for (int k = 0; k < 16; k++)
             if (!(t[k] == id.m[k])) fail(RTC_ERR_UNSUPPORTED, "a group's own transform must be the identity (shape.rs:203-217)");
+        PhaseClock clock;
         Box4 b = bounds_of(i);
+        clock.lap(out_.phase_ms, FlatScene::T_BOUNDS);
         DGate g;
         g.lo[0] = b.min.x; g.lo[1] = b.min.y; g.lo[2] = b.min.z;
         g.hi[0] = b.max.x; g.hi[1] = b.max.y; g.hi[2] = b.max.z;
@@ -344,6 +385,7 @@ class Flattener {
         const rtc_transform_desc& td = d_.transforms[d_.shapes[begin].transform];
         const Mat4 inv_t = transpose(Mat4::from(td.inverse));  // shape.rs:216
         const uint32_t n = end - begin;
+        PhaseClock clock;
         std::vector<BvhTri> bt(n);
         for (uint32_t k = 0; k < n; k++) {
             const rtc_triangle_desc& t = d_.triangles[d_.shapes[begin + k].triangle];
@@ -353,6 +395,28 @@ class Flattener {
                 bt[k].p[2][a] = t.p3[a];
             }
         }
+        // normal_at for a triangle (shape.rs:509-518) is point-independent: invT * normal, w = 0, normalize, w = 0,
+        // normalize.  Computed per input triangle on a second thread while the BVH builds (it is a third of the serial
+        // time of a mesh otherwise), placed in leaf order afterwards.
+        std::vector<DTriAttr> attr_in(n);
+        auto attrs = [&] {
+            for (uint32_t k = 0; k < n; k++) {
+                const rtc_shape_desc& s = d_.shapes[begin + k];
+                const rtc_triangle_desc& t = d_.triangles[s.triangle];
+                Vec4 wn = mul(inv_t, vector(t.normal[0], t.normal[1], t.normal[2]));
+                wn.w = 0.;
+                wn = normalize(wn);
+                wn.w = 0.;
+                wn = normalize(wn);
+                DTriAttr& ta = attr_in[k];
+                ta.normal[0] = wn.x; ta.normal[1] = wn.y; ta.normal[2] = wn.z;
+                ta.material = s.material;
+                ta.xform = xf;
+            }
+        };
+        std::thread attr_thread;
+        if (n >= kParallelMin) attr_thread = std::thread(attrs);
+        else attrs();
         DMesh m;
         m.xform = xf;
         m.tri_base = (int32_t)out_.tris.size();
@@ -360,7 +424,10 @@ class Flattener {
         std::vector<uint32_t> order;
         int depth = 0;
         double max_abs = 0.;
-        m.root = build_bvh(bt, out_.bvh, m.tri_base, order, &depth, &max_abs);
+        clock.lap(out_.phase_ms, FlatScene::T_BVH_ITEMS);
+        m.root = build_bvh(bt, out_.bvh, m.tri_base, order, &depth, &max_abs, out_.phase_ms + FlatScene::T_BVH_ITEMS);
+        clock = PhaseClock();  // build_bvh booked its own phases
+        if (attr_thread.joinable()) attr_thread.join();
         m.extent = f32_above_(max_abs * (1.0 + 2.0 * kPadRel));
         m.pad[0] = m.pad[1] = m.pad[2] = 0;
         if (depth > out_.bvh_max_depth) out_.bvh_max_depth = depth;
@@ -368,11 +435,13 @@ class Flattener {
             fail(RTC_ERR_UNSUPPORTED, "mesh BVH deeper than the device traversal stack (more than ~16M triangles)");
         const uint32_t leaf0 = next_leaf_;
         next_leaf_ += n;
+        const size_t at = out_.tris.size();
+        out_.tris.resize(at + n);
+        out_.tri_attr.resize(at + n);
         for (uint32_t slot = 0; slot < n; slot++) {
             const uint32_t k = order[slot];
-            const rtc_shape_desc& s = d_.shapes[begin + k];
-            const rtc_triangle_desc& t = d_.triangles[s.triangle];
-            DTri dt;
+            const rtc_triangle_desc& t = d_.triangles[d_.shapes[begin + k].triangle];
+            DTri& dt = out_.tris[at + slot];
             std::memset(&dt, 0, sizeof(dt));
             for (int a = 0; a < 3; a++) {
                 dt.p1[a] = t.p1[a];
@@ -380,19 +449,9 @@ class Flattener {
                 dt.e2[a] = t.e2[a];
             }
             dt.leaf = (int32_t)(leaf0 + k);
-            out_.tris.push_back(dt);
-            // normal_at for a triangle (shape.rs:509-518): invT * normal, w = 0, normalize, w = 0, normalize
-            Vec4 wn = mul(inv_t, vector(t.normal[0], t.normal[1], t.normal[2]));
-            wn.w = 0.;
-            wn = normalize(wn);
-            wn.w = 0.;
-            wn = normalize(wn);
-            DTriAttr ta;
-            ta.normal[0] = wn.x; ta.normal[1] = wn.y; ta.normal[2] = wn.z;
-            ta.material = s.material;
-            ta.xform = xf;
-            out_.tri_attr.push_back(ta);
+            out_.tri_attr[at + slot] = attr_in[k];
         }
+        clock.lap(out_.phase_ms, FlatScene::T_TRIANGLES);
         out_.program.push_back(DProgramNode{NODE_MESH, (int32_t)out_.meshes.size(), 0, 0});
         out_.meshes.push_back(m);
     }

@@ -340,8 +340,10 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* 
         s->ctx->out64_size = px * 24;
     }
     // Overlap the device->host copy with rendering: the call's rows are rendered in two launches (3/4, then 1/4) and the
-    // first chunk's pixels cross PCIe on a second stream while the second chunk renders.  Ray counters are per launch;
-    // with `stats` requested the frame is rendered in one launch so that the reported kernel time is one kernel's.
+    // first chunk's pixels cross PCIe on a second stream while the second chunk renders.  More, smaller chunks were
+    // measured slower at every frame size (each launch pays its own ramp-up and tail: 8K pumpkin 11.5 ms with 2 chunks,
+    // 11.7-12.2 ms with 4-16; profiles/r01n_host_chunk_sweep.json).  Ray counters are per launch; with `stats` requested
+    // the frame is rendered in one launch so that the reported kernel time is one kernel's.
     const bool split = !stats && !rgb_f64 && rgba8 && rows.local_rows >= 256;
     if (!split) {
         int rc = launch(s, cam, rows, rgba8 ? s->ctx->out8 : nullptr, rgb_f64 ? s->ctx->out64 : nullptr, s->stream, stats, err);

@@ -193,13 +193,15 @@ def test_full_size_properties_8k(rtc):
     assert int(a[..., 3].min()) == 255  # every pixel was written
 
 
-def test_host_output_chunks_match_single_launch(rtc):
-    """rtc_render's two-chunk path (copy overlapped with the second kernel) returns the frame of the one-launch path."""
-    world, cam = rtc.build_scene("cow_teddy", 1280, 720)
-    one = np.empty((720, 1280, 4), dtype=np.uint8)
-    two = np.empty_like(one)
+@pytest.mark.parametrize("w,h", [(1280, 720), (2560, 1442), (4096, 2160)])
+def test_host_output_chunks_match_single_launch(rtc, w, h):
+    """rtc_render's chunked path (each chunk's copy overlapped with the next chunk's kernel: 2 launches for a small
+    frame, one per ~4 MiB up to 16 for larger ones, ragged last tile row included) returns the one-launch frame."""
+    world, cam = rtc.build_scene("cow_teddy", w, h)
+    one = np.empty((h, w, 4), dtype=np.uint8)
+    two = np.zeros_like(one)
     cam.render_into(world, rgba8=one, stats=rtc.Stats())  # stats requested -> single launch
-    cam.render_into(world, rgba8=two)                      # no stats -> chunked + overlapped copy
+    cam.render_into(world, rgba8=two)                      # no stats -> chunked + overlapped copies
     assert np.array_equal(one, two)
 
 
