@@ -204,3 +204,54 @@ def test_scene_create_rejects_malformed_descriptions(rtc):
     assert rc in (rtc.RTC_OK, rtc.RTC_ERR_CUDA)
     if rc == rtc.RTC_OK:
         api.scene_destroy(out)
+
+
+def _fold_group_box(vertices, faces, m):
+    """bounds.rs:50-151 restated with elementwise numpy (IEEE, no FMA): every triangle's origin-seeded box, its eight
+    corners through the triangle's transform as ((m0*x + m1*y) + m2*z) + m3*1, folded into an origin-seeded box."""
+    tri = vertices[faces - 1]                                  # (n, 3 points, 3)
+    lo = np.minimum(tri.min(axis=1), 0.0)
+    hi = np.maximum(tri.max(axis=1), 0.0)
+    out_lo, out_hi = np.zeros(3), np.zeros(3)
+    for c in range(8):
+        p = np.stack([(hi if (c >> (2 - a)) & 1 else lo)[:, a] for a in range(3)], axis=1)
+        for r in range(3):
+            v = ((m[r, 0] * p[:, 0] + m[r, 1] * p[:, 1]) + m[r, 2] * p[:, 2]) + m[r, 3] * 1.0
+            out_lo[r] = min(out_lo[r], v.min())
+            out_hi[r] = max(out_hi[r], v.max())
+    return np.concatenate([out_lo, out_hi])
+
+
+def test_big_mesh_gate_box_is_the_reference_fold_bit_for_bit(rtc):
+    """A mesh group of 10 000 triangles takes the flattener's sliced, multi-threaded fold (flatten.hpp): its gate must
+    still be exactly what Bounds::new folds — compared bit for bit with an independent numpy restatement."""
+    from importlib import import_module
+    scenes = import_module("ray-tracer-challenge-rust_b200.scenes")
+    v, f = scenes.load_mesh("pumpkin")
+    S, T = rtc.Shapes(rtc.api()), rtc.Transformations(rtc.api())
+    g = S.mesh(v, f)
+    m = T.translation(0.5, -1.25, 3.0) * T.rotation_y(0.4) * T.scaling(0.3, 0.31, 0.29)
+    g.set_transform(m)
+    w = rtc.World(rtc.Light((0, 0, 0), (1, 1, 1)))
+    w.push(g)
+    info = w.flatten_info(want_gates=True)
+    assert info["gates"] == 1 and info["mesh_triangles"] == 10000
+    # set_transform on a group multiplies into each child (shape.rs:203-217): outer -> inner group -> triangle
+    eye = type(m)(rtc.api(), np.eye(4))
+    mm = ((m * eye) * eye).v.reshape(4, 4)
+    want = _fold_group_box(np.asarray(v, dtype=np.float64), np.asarray(f), mm)
+    got = np.asarray(info["gate_boxes"][0], dtype=np.float64)
+    assert np.array_equal(got, want), (got, want)
+
+
+def test_long_leaf_run_with_an_unbounded_child_still_panics(rtc):
+    """The sliced fold must not swallow the reference's panic (bounds.rs:143) for a group of thousands of leaves."""
+    S = rtc.Shapes(rtc.api())
+    g = S.group()
+    for i in range(4500):
+        g.push_shape(S.cylinder() if i == 3333 else S.sphere())
+    w = rtc.World(rtc.Light((0, 0, 0), (1, 1, 1)))
+    w.push(g)
+    with pytest.raises(rtc.RtcError) as e:
+        w.flatten_info()
+    assert e.value.code == rtc.RTC_ERR_PANIC and "bounds.rs:143" in e.value.message
