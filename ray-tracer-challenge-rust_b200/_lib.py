@@ -19,12 +19,25 @@ class RtcError(RuntimeError):
         self.code, self.message = code, message
 
 
+def _load(path):
+    """dlopen with a short retry: on a freshly provisioned box the snapshot copy of a 70 MB library has been seen still
+    in flight when the first ranks start ("file too short")."""
+    import time
+    for attempt in range(10):
+        try:
+            return C.CDLL(path)
+        except OSError as e:
+            if "too short" not in str(e) and "truncated" not in str(e) or attempt == 9:
+                raise
+            time.sleep(1.0)
+
+
 class RtcApi(BuilderApi):
     def __init__(self, path=LIB_PATH):
         if not os.path.exists(path):
             raise ImportError(f"{path} is missing: build it with `python ray-tracer-challenge-rust_b200/build.py` "
                               "(there is no CPU fallback)")
-        super().__init__(C.CDLL(path), "rtc_")
+        super().__init__(_load(path), "rtc_")
         self.path = path
         f, vp = self._fn, C.c_void_p
         u8p = C.POINTER(C.c_uint8)
