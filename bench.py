@@ -45,6 +45,9 @@ def parse_args():
     p.add_argument("--band-rows", type=int, default=8)
     p.add_argument("--exchange", default="auto", choices=["auto", "peer", "gather"],
                    help="N > 1: how bands reach rank 0 (peer = direct NVLink stores, gather = NCCL gather)")
+    p.add_argument("--e2e-build", default="device", choices=["device", "host"],
+                   help="mesh build of the per-step scene in the e2e loop: GPU linear BVH (RTC_BUILD_DEVICE_LBVH) or the "
+                        "host SAH build the device-resident loop uses")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the informative per-config table")
     return p.parse_args()
@@ -276,9 +279,13 @@ def run_b200(args):
     cdesc = cam.desc()
     stream = torch.cuda.current_stream().cuda_stream
 
+    e2e_flags = rtc.RTC_BUILD_DEVICE_LBVH if args.e2e_build == "device" else rtc.RTC_BUILD_HOST_SAH
+    e2e_h2d = [0]
+
     def e2e_step():
         scene = C.c_void_p()
-        api.check(api.scene_create(desc, local_rank, C.byref(scene)))
+        api.check(api.scene_create_ex(desc, local_rank, e2e_flags, C.byref(scene)))
+        e2e_h2d[0] = int(api.scene_upload_bytes(scene))
         if world_size == 1:
             # the drop-in call itself: rtc_render with a HOST (pinned) output buffer — it renders in two chunks and
             # overlaps the first chunk's device->host copy with the second chunk's kernel
@@ -354,13 +361,15 @@ def run_b200(args):
         "sustained": {"frames": n_sustain, "frame_ms": sustained_ms, "mrays_s": total_rays / sustained_ms / 1e3,
                       "what": "back-to-back frames for about a second, no L2 flush, one device timing around all"},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "frame_ms": e2e_s / args.steps * 1e3,
-                "h2d_bytes_per_step": int(info["device_bytes"]), "d2h_bytes_per_step": int(4 * w * h),
-                "what": ("per step: rtc_scene_create (flatten + BVH + upload) -> rtc_render into a pinned host RGBA8 frame "
-                         "(two chunks, copy overlapped with the second kernel) -> rtc_scene_destroy; wall clock"
+                "h2d_bytes_per_step": e2e_h2d[0], "d2h_bytes_per_step": int(4 * w * h),
+                "build": ("RTC_BUILD_DEVICE_LBVH: meshes built on the GPU per step (csrc/lbvh.cu)" if args.e2e_build == "device"
+                          else "RTC_BUILD_HOST_SAH: binned SAH on the host per step"),
+                "what": ("per step: rtc_scene_create_ex (flatten + mesh build + upload) -> rtc_render into a pinned host "
+                         "RGBA8 frame (two chunks, copy overlapped with the second kernel) -> rtc_scene_destroy; wall clock"
                          if world_size == 1 else
-                         "per step: rtc_scene_create (flatten + BVH + upload) -> rtc_render_device (stores into rank 0's "
-                         "frame) -> barrier -> RGBA8 frame to pinned host memory -> rtc_scene_destroy; wall clock, max "
-                         "over ranks")},
+                         "per step: rtc_scene_create_ex (flatten + mesh build + upload) -> rtc_render_device (stores into "
+                         "rank 0's frame) -> barrier -> RGBA8 frame to pinned host memory -> rtc_scene_destroy; wall "
+                         "clock, max over ranks")},
         "gpu_launches": args.steps * 1,  # timed (device-resident) region: one render_kernel launch per frame
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",

@@ -133,10 +133,22 @@ typedef struct rtc_scene rtc_scene;
  * Fails with RTC_ERR_PANIC where the reference would panic while rendering this world (e.g. an uncapped cylinder inside
  * a group: bounds.rs:143), RTC_ERR_UNSUPPORTED for non-affine transforms. */
 int rtc_scene_create(const rtc_scene_desc* desc, int device, rtc_scene** out);
+/* The same with a choice of mesh build.  Both produce the same pixels (a BVH only decides which exact triangle tests
+ * run); they trade build time against traversal work:
+ *   RTC_BUILD_HOST_SAH    (rtc_scene_create) binned-SAH BVH built on the host: milliseconds per 10 k triangles, the fewest
+ *                         box tests per ray — for scenes that are rendered many times;
+ *   RTC_BUILD_DEVICE_LBVH meshes of >= 256 triangles are built on the GPU (Morton order, Karras hierarchy, csrc/lbvh.cuh):
+ *                         triangle normals, triangle tables and BVH never touch the host; 8-20 % more box tests per ray
+ *                         — for scenes that are built, rendered once and dropped (obj_file.rs -> Camera::render). */
+#define RTC_BUILD_HOST_SAH 0u
+#define RTC_BUILD_DEVICE_LBVH 1u
+int rtc_scene_create_ex(const rtc_scene_desc* desc, int device, uint32_t flags, rtc_scene** out);
 void rtc_scene_destroy(rtc_scene* scene);
 /* Flattened-scene facts for reports: n[0]=leaves, [1]=gates, [2]=meshes, [3]=mesh triangles, [4]=bvh nodes,
  * [5]=device bytes. */
 int rtc_scene_info(const rtc_scene* scene, uint64_t n[6]);
+/* Host->device bytes rtc_scene_create(_ex) copied for this scene (tables; for a device build the triangle inputs). */
+uint64_t rtc_scene_upload_bytes(const rtc_scene* scene);
 
 /* Camera::render (src/camera.rs:67-79) with HOST output buffers (either may be NULL):
  *   rgba8_out  : rows*hsize*4 bytes, each channel quantised as canvas.rs:61-63 does at PPM time, alpha = 255
@@ -231,6 +243,8 @@ int rtc_world_push(rtc_world* w, rtc_shape* s); /* World.objects.push; consumes 
 int rtc_world_color_at(rtc_world* w, const double* rays, uint64_t n, double* rgb_out);
 /* The layer-1 scene handle this world marshals into (created on first use on `device`); owned by the world. */
 int rtc_world_scene(rtc_world* w, int device, rtc_scene** out);
+/* Which mesh build rtc_world_scene / rtc_camera_render use for this world (RTC_BUILD_*; drops a scene built otherwise). */
+int rtc_world_set_build(rtc_world* w, uint32_t flags);
 
 /* The layer-1 description of this world: what rtc_world_scene passes to rtc_scene_create, and what the Rust-side
  * Camera::render patch builds from its &World.  The rtc_scene_desc borrows from the rtc_marshalled. */

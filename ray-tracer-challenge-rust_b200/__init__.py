@@ -14,7 +14,7 @@ import numpy as np
 
 from . import scenes  # noqa: F401
 from ._capi import BuilderApi, CameraDesc, Rows, Stats, as_f64, dptr
-from ._lib import (LIB_PATH, RTC_ERR_CUDA, RTC_ERR_INVALID, RTC_ERR_PANIC, RTC_ERR_UNSUPPORTED, RTC_OK, RtcError,
+from ._lib import (LIB_PATH, RTC_BUILD_DEVICE_LBVH, RTC_BUILD_HOST_SAH, RTC_ERR_CUDA, RTC_ERR_INVALID, RTC_ERR_PANIC, RTC_ERR_UNSUPPORTED, RTC_OK, RtcError,
                    api)
 from .scene_api import (BLACK, BLUE, GREEN, RED, WHITE, CameraHandle, Light, Material, Matrix, Pattern, Shape, Shapes,
                         Transformations, WorldHandle)
@@ -122,6 +122,12 @@ class World(WorldHandle):
         out = np.empty((r.shape[0], 3))
         self.api.check(self.api.world_color_at(self.h, dptr(r), r.shape[0], dptr(out)))
         return out
+
+    def set_build(self, build):
+        """Mesh build of this world's scene: "host" (binned SAH, the default — best for many frames of one scene) or
+        "device" (linear BVH built on the GPU — best when a scene is built, rendered once and dropped)."""
+        flags = {"host": RTC_BUILD_HOST_SAH, "device": RTC_BUILD_DEVICE_LBVH}[build]
+        self.api.check(self.api.world_set_build(self.h, flags))
 
     def scene(self, device=0):
         """The layer-1 rtc_scene handle (flattened + uploaded on first use; owned by the world)."""

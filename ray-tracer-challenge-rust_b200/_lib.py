@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # RTC_B200_LIB selects a tuning variant built by tools/tune_variants.py (same sources, other launch shape)
 LIB_PATH = os.environ.get("RTC_B200_LIB") or os.path.join(HERE, "librtc_b200.so")
 
+RTC_BUILD_HOST_SAH, RTC_BUILD_DEVICE_LBVH = 0, 1
 RTC_OK, RTC_ERR_INVALID, RTC_ERR_PANIC, RTC_ERR_CUDA, RTC_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 
 
@@ -47,8 +48,10 @@ class RtcApi(BuilderApi):
         f("frame_share_open", C.c_int, C.c_int, C.c_char_p, C.POINTER(vp))
         f("frame_share_close", C.c_int, C.c_int, vp, C.c_int)
         f("scene_create", C.c_int, vp, C.c_int, C.POINTER(vp))
+        f("scene_create_ex", C.c_int, vp, C.c_int, C.c_uint32, C.POINTER(vp))
         f("scene_destroy", None, vp)
         f("scene_info", C.c_int, vp, c_u64_p)
+        f("scene_upload_bytes", C.c_uint64, vp)
         f("render", C.c_int, vp, C.POINTER(CameraDesc), C.POINTER(Rows), vp, vp, C.POINTER(Stats))
         f("render_device", C.c_int, vp, C.POINTER(CameraDesc), C.POINTER(Rows), vp, vp, vp, C.c_int, C.POINTER(Stats))
         f("rows_count", C.c_uint32, C.POINTER(CameraDesc), C.POINTER(Rows))
@@ -56,6 +59,7 @@ class RtcApi(BuilderApi):
         f("measure_fp64_peak", C.c_int, C.c_int, c_double_p, c_double_p)
         f("world_color_at", C.c_int, vp, c_double_p, C.c_uint64, c_double_p)
         f("world_scene", C.c_int, vp, C.c_int, C.POINTER(vp))
+        f("world_set_build", C.c_int, vp, C.c_uint32)
         f("world_describe", C.c_int, vp, c_u64_p)
         f("world_flatten_info", C.c_int, vp, c_u64_p, c_double_p, C.c_uint64)
         f("world_marshal", C.c_int, vp, C.POINTER(vp))

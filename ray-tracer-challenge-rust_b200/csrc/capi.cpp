@@ -90,6 +90,7 @@ struct rtc_shape {
 struct rtc_world {
     HWorld w;
     rtc_scene* scene = nullptr;  // marshalled + uploaded on first use; dropped when the world changes
+    uint32_t build_flags = RTC_BUILD_HOST_SAH;
     std::mutex mu;
 };
 struct rtc_camera {
@@ -149,34 +150,46 @@ static void trace_phases(const char* who, const FlatScene& flat) {
 
 /* ---------------------------------------------------------------------------------------------- 1. CORE BOUNDARY */
 int rtc_scene_create(const rtc_scene_desc* desc, int device, rtc_scene** out) {
+    return rtc_scene_create_ex(desc, device, RTC_BUILD_HOST_SAH, out);
+}
+int rtc_scene_create_ex(const rtc_scene_desc* desc, int device, uint32_t flags, rtc_scene** out) {
     if (!desc || !out) return set_err(RTC_ERR_INVALID, "null argument");
+    if (flags & ~(uint32_t)RTC_BUILD_DEVICE_LBVH) return set_err(RTC_ERR_INVALID, "unknown build flag");
     *out = nullptr;
-    FlatScene flat;
-    std::string e;
-    int rc = flatten_scene(*desc, flat, &e);
-    if (rc != RTC_OK) return set_err(rc, e);
-    DeviceScene* dev = nullptr;
-    PhaseClock clock;
-    rc = device_scene_create(flat, device, &dev, &e);
-    if (rc != 0) return set_err(RTC_ERR_CUDA, e);
-    clock.lap(flat.phase_ms, FlatScene::T_UPLOAD);
-    trace_phases("rtc_scene_create", flat);
-    rtc_scene* s = new rtc_scene();
-    s->dev = dev;
-    s->info[0] = flat.leaf_count;
-    s->info[1] = flat.gates.size();
-    s->info[2] = flat.meshes.size();
-    s->info[3] = flat.tris.size();
-    s->info[4] = flat.bvh.size();
-    s->info[5] = device_scene_bytes(dev);
-    *out = s;
-    return RTC_OK;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        FlatScene flat;
+        std::string e;
+        FlattenOptions opts;
+        opts.device_mesh_build = (flags & RTC_BUILD_DEVICE_LBVH) && attempt == 0;
+        int rc = flatten_scene(*desc, flat, &e, opts);
+        if (rc != RTC_OK) return set_err(rc, e);
+        DeviceScene* dev = nullptr;
+        PhaseClock clock;
+        int built_depth = 0;
+        rc = device_scene_create(flat, device, &dev, &e, &built_depth);
+        if (rc == kDeviceBuildTooDeep && attempt == 0) continue;  // rebuild this scene's meshes on the host
+        if (rc != 0) return set_err(RTC_ERR_CUDA, e);
+        clock.lap(flat.phase_ms, FlatScene::T_UPLOAD);
+        trace_phases("rtc_scene_create", flat);
+        rtc_scene* s = new rtc_scene();
+        s->dev = dev;
+        s->info[0] = flat.leaf_count;
+        s->info[1] = flat.gates.size();
+        s->info[2] = flat.meshes.size();
+        s->info[3] = flat.tris.size() + flat.device_tris;
+        s->info[4] = flat.bvh.size() + flat.device_nodes;
+        s->info[5] = device_scene_bytes(dev);
+        *out = s;
+        return RTC_OK;
+    }
+    return set_err(RTC_ERR_CUDA, "scene build failed");
 }
 void rtc_scene_destroy(rtc_scene* scene) {
     if (!scene) return;
     device_scene_destroy(scene->dev);
     delete scene;
 }
+uint64_t rtc_scene_upload_bytes(const rtc_scene* scene) { return scene ? device_scene_upload_bytes(scene->dev) : 0; }
 int rtc_scene_info(const rtc_scene* scene, uint64_t n[6]) {
     if (!scene || !n) return set_err(RTC_ERR_INVALID, "null argument");
     std::memcpy(n, scene->info, sizeof(scene->info));
@@ -417,10 +430,21 @@ int rtc_world_scene(rtc_world* w, int device, rtc_scene** out) {
     if (!w->scene) {
         Marshalled m;
         marshal_world(w->w, m);
-        int rc = rtc_scene_create(&m.desc, device, &w->scene);
+        int rc = rtc_scene_create_ex(&m.desc, device, w->build_flags, &w->scene);
         if (rc != RTC_OK) return rc;
     }
     *out = w->scene;
+    return RTC_OK;
+}
+int rtc_world_set_build(rtc_world* w, uint32_t flags) {
+    if (!w) return set_err(RTC_ERR_INVALID, "null argument");
+    if (flags & ~(uint32_t)RTC_BUILD_DEVICE_LBVH) return set_err(RTC_ERR_INVALID, "unknown build flag");
+    std::lock_guard<std::mutex> lk(w->mu);
+    if (flags != w->build_flags && w->scene) {
+        rtc_scene_destroy(w->scene);
+        w->scene = nullptr;
+    }
+    w->build_flags = flags;
     return RTC_OK;
 }
 // The layer-1 description of a world — exactly what rtc_world_scene hands to rtc_scene_create, and what the Rust-side

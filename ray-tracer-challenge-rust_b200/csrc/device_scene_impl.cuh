@@ -45,6 +45,7 @@ struct DeviceScene {
     int sm_count = 0;
     void* slab = nullptr;           // all tables, one stream-ordered allocation
     size_t slab_size = 0;
+    size_t upload_bytes = 0;        // host->device bytes the create call copied (tables, device-build inputs)
     DScene view{};
     int feature_mask = 0;           // FEAT_* bits of what the flattened world contains (picks the kernel instantiation)
     cudaStream_t stream = nullptr;  // == ctx->stream

@@ -4,9 +4,21 @@
 #include <cstdint>
 #include <vector>
 
+#include "../../include/rtc.h"
 #include "device_scene.h"
 
 namespace rtc {
+
+// A mesh left for the device to build (lbvh.cuh): its input triangles, and where its slots and nodes go — after the
+// host-built entries of the tris / tri_attr / bvh tables.
+struct PendingMesh {
+    int32_t mesh_index;  // into FlatScene::meshes
+    uint32_t n;
+    int32_t xform, leaf0;
+    int32_t tri_base, node_base;  // assigned when flattening ends
+    double inv_t[16];             // transpose of the transform's inverse (shape.rs:216)
+    size_t input_offset;          // first triangle in pending_tri / pending_material
+};
 
 struct FlatScene {
     std::vector<DProgramNode> program;
@@ -25,6 +37,11 @@ struct FlatScene {
     float reject_extent = 0.f;
     int32_t merged_gates = 0;  // nested single-child groups whose identical box shares the parent's gate
     int bvh_max_depth = 0;
+    // device-built meshes (flatten option device_mesh_build)
+    std::vector<PendingMesh> pending;
+    std::vector<rtc_triangle_desc> pending_tri;
+    std::vector<int32_t> pending_material;
+    uint32_t device_tris = 0, device_nodes = 0;  // table entries appended after the host-built ones
     // where rtc_scene_create's host time went (ms), printed under RTC_B200_TRACE=1
     enum { T_VALIDATE, T_BOUNDS, T_BVH_ITEMS, T_BVH_BUILD, T_BVH_SPLICE, T_TRIANGLES, T_UPLOAD, T_COUNT };
     double phase_ms[T_COUNT] = {0, 0, 0, 0, 0, 0, 0};

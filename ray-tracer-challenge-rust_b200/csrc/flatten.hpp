@@ -30,6 +30,11 @@ struct FlattenError {
     std::string message;
 };
 
+struct FlattenOptions {
+    bool device_mesh_build = false;  // leave meshes of >= kDeviceBuildMin triangles to the device build (lbvh.cuh)
+};
+constexpr uint32_t kDeviceBuildMin = 256;
+
 namespace detail {
 
 struct XKey {
@@ -43,7 +48,7 @@ struct Box4 {
 
 class Flattener {
   public:
-    Flattener(const rtc_scene_desc& d, FlatScene& out) : d_(d), out_(out) {}
+    Flattener(const rtc_scene_desc& d, FlatScene& out, const FlattenOptions& o = {}) : d_(d), out_(out), opts_(o) {}
 
     void run() {
         check(d_.shape_count == 0 || d_.shapes, "shapes is NULL");
@@ -65,6 +70,14 @@ class Flattener {
         clock.lap(out_.phase_ms, FlatScene::T_VALIDATE);
         emit_children(0, d_.shape_count);  // World.objects in order (world.rs:46-50)
         out_.leaf_count = next_leaf_;
+        // device-built meshes take the table entries after the host-built ones
+        for (PendingMesh& p : out_.pending) {
+            p.tri_base = (int32_t)(out_.tris.size() + out_.device_tris);
+            p.node_base = (int32_t)(out_.bvh.size() + out_.device_nodes);
+            out_.meshes[p.mesh_index].tri_base = p.tri_base;
+            out_.device_tris += p.n;
+            out_.device_nodes += p.n - 1;
+        }
         if (!out_.meshes.empty()) out_.feature_mask |= 32;
         if (!out_.gates.empty()) out_.feature_mask |= 64;
         for (const DMaterial& m : out_.materials)
@@ -74,6 +87,7 @@ class Flattener {
   private:
     const rtc_scene_desc& d_;
     FlatScene& out_;
+    const FlattenOptions opts_;
     std::vector<uint32_t> end_;  // end_[i] = index just past shape i's subtree
     std::map<XKey, int32_t> xform_ids_;
     std::map<uint32_t, Box4> group_bounds_;
@@ -386,6 +400,36 @@ class Flattener {
         const Mat4 inv_t = transpose(Mat4::from(td.inverse));  // shape.rs:216
         const uint32_t n = end - begin;
         PhaseClock clock;
+        if (opts_.device_mesh_build && n >= kDeviceBuildMin) {
+            PendingMesh p;
+            p.mesh_index = (int32_t)out_.meshes.size();
+            p.n = n;
+            p.xform = xf;
+            p.leaf0 = (int32_t)next_leaf_;
+            p.tri_base = p.node_base = -1;
+            std::memcpy(p.inv_t, inv_t.m, sizeof(p.inv_t));
+            p.input_offset = out_.pending_tri.size();
+            out_.pending_tri.resize(p.input_offset + n);
+            out_.pending_material.resize(p.input_offset + n);
+            for (uint32_t k = 0; k < n; k++) {
+                const rtc_shape_desc& s = d_.shapes[begin + k];
+                out_.pending_tri[p.input_offset + k] = d_.triangles[s.triangle];
+                out_.pending_material[p.input_offset + k] = s.material;
+            }
+            next_leaf_ += n;
+            DMesh m;
+            m.xform = xf;
+            m.root = -1;  // written by the device build, like extent
+            m.tri_base = -1;
+            m.tri_count = (int32_t)n;
+            m.extent = 0.f;
+            m.pad[0] = m.pad[1] = m.pad[2] = 0;
+            out_.pending.push_back(p);
+            out_.program.push_back(DProgramNode{NODE_MESH, (int32_t)out_.meshes.size(), 0, 0});
+            out_.meshes.push_back(m);
+            clock.lap(out_.phase_ms, FlatScene::T_TRIANGLES);
+            return;
+        }
         std::vector<BvhTri> bt(n);
         for (uint32_t k = 0; k < n; k++) {
             const rtc_triangle_desc& t = d_.triangles[d_.shapes[begin + k].triangle];
@@ -460,9 +504,9 @@ class Flattener {
 }  // namespace detail
 
 // Returns RTC_OK or a negative code with *err set.
-inline int flatten_scene(const rtc_scene_desc& desc, FlatScene& out, std::string* err) {
+inline int flatten_scene(const rtc_scene_desc& desc, FlatScene& out, std::string* err, const FlattenOptions& opts = {}) {
     try {
-        detail::Flattener f(desc, out);
+        detail::Flattener f(desc, out, opts);
         f.run();
         return RTC_OK;
     } catch (const FlattenError& e) {

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "flat_scene.hpp"
+#include "lbvh_launch.cuh"
 #include "render.cuh"
 #include "device_scene_impl.cuh"
 #include "render_launch.cuh"
@@ -177,22 +178,29 @@ static DeviceContext* context_for(int device, std::string* err) {
     return c;
 }
 
-int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::string* err) {
+int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::string* err, int* built_depth) {
     DeviceContext* ctx = context_for(device, err);
     if (!ctx) return -3;
     std::lock_guard<std::mutex> lk(ctx->mu);
     RTC_CUDA(cudaSetDevice(device));
+    // device-built meshes (lbvh.cu) own the table entries after the host-built ones: allocated here, never uploaded
+    const auto with_extra = [](size_t raw_bytes, size_t extra_bytes) { return (raw_bytes + extra_bytes + 255) & ~(size_t)255; };
     const size_t sizes[9] = {slab_bytes(f.program), slab_bytes(f.xforms),   slab_bytes(f.prims),
-                             slab_bytes(f.gates),   slab_bytes(f.meshes),   slab_bytes(f.bvh),
-                             slab_bytes(f.tris),    slab_bytes(f.tri_attr), slab_bytes(f.materials)};
+                             slab_bytes(f.gates),   slab_bytes(f.meshes),
+                             with_extra(f.bvh.size() * sizeof(DBvhNode), (size_t)f.device_nodes * sizeof(DBvhNode)),
+                             with_extra(f.tris.size() * sizeof(DTri), (size_t)f.device_tris * sizeof(DTri)),
+                             with_extra(f.tri_attr.size() * sizeof(DTriAttr), (size_t)f.device_tris * sizeof(DTriAttr)),
+                             slab_bytes(f.materials)};
     size_t total = 256;
     for (size_t b : sizes) total += b;
-    if (ctx->staging_size < total) {
+    // pinned staging mirrors the slab's layout (one copy when nothing is device-built), followed by the device build's inputs
+    const size_t staging_need = total + lbvh_staging_bytes(f) + 256;
+    if (ctx->staging_size < staging_need) {
         if (ctx->staging) cudaFreeHost(ctx->staging);
         ctx->staging = nullptr;
         ctx->staging_size = 0;
-        RTC_CUDA(cudaHostAlloc(&ctx->staging, total * 2, cudaHostAllocDefault));
-        ctx->staging_size = total * 2;
+        RTC_CUDA(cudaHostAlloc(&ctx->staging, staging_need * 2, cudaHostAllocDefault));
+        ctx->staging_size = staging_need * 2;
     }
     unsigned char* host = (unsigned char*)ctx->staging;
     size_t off[9], at = 0;
@@ -210,8 +218,32 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     }
     void* slab = nullptr;
     RTC_CUDA(cudaMallocAsync(&slab, total, ctx->stream));
-    cudaError_t e = cudaMemcpyAsync(slab, host, at, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the tables are now visible to every stream
+    cudaError_t e = cudaSuccess;
+    if (f.pending.empty()) {
+        e = cudaMemcpyAsync(slab, host, at, cudaMemcpyHostToDevice, ctx->stream);
+    } else {  // the tails of the bvh / tris / tri_attr tables are written by the device build: copy host-built bytes only
+        for (int k = 0; k < 9 && e == cudaSuccess; k++)
+            if (raw[k])
+                e = cudaMemcpyAsync((unsigned char*)slab + off[k], host + off[k], raw[k], cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e == cudaSuccess && !f.pending.empty()) {
+        unsigned char* base = (unsigned char*)slab;
+        int depth = 0;
+        const int rc = lbvh_build_device(f, host + ((at + 255) & ~(size_t)255), (DBvhNode*)(base + off[5]), (DTri*)(base + off[6]),
+                                         (DTriAttr*)(base + off[7]), (DMesh*)(base + off[4]), ctx->stream, &depth, err);
+        if (rc != 0) {
+            cudaFreeAsync(slab, ctx->stream);
+            return rc;
+        }
+        if (depth + 2 > kBvhStackDepth) {  // a pathological key distribution: the caller rebuilds on the host
+            cudaFreeAsync(slab, ctx->stream);
+            if (err) *err = "device-built BVH deeper than the traversal stack";
+            return kDeviceBuildTooDeep;
+        }
+        if (built_depth) *built_depth = depth;
+    } else if (e == cudaSuccess) {
+        e = cudaStreamSynchronize(ctx->stream);  // the tables are now visible to every stream
+    }
     if (e != cudaSuccess) {
         cudaFreeAsync(slab, ctx->stream);
         if (err) *err = cuda_err("uploading the scene", e);
@@ -224,6 +256,11 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->stream = ctx->stream;
     s->slab = slab;
     s->slab_size = total;
+    s->upload_bytes = at;
+    if (!f.pending.empty()) {
+        s->upload_bytes = f.pending_tri.size() * (sizeof(rtc_triangle_desc) + sizeof(int32_t));
+        for (size_t b : raw) s->upload_bytes += b;
+    }
     unsigned char* base = (unsigned char*)s->slab;
     s->view.program = (const DProgramNode*)(base + off[0]);
     s->view.xforms = (const DXform*)(base + off[1]);
@@ -262,6 +299,7 @@ void device_scene_destroy(DeviceScene* s) {
     delete s;
 }
 uint64_t device_scene_bytes(const DeviceScene* s) { return s->slab_size; }
+uint64_t device_scene_upload_bytes(const DeviceScene* s) { return s->upload_bytes; }
 int device_scene_device(const DeviceScene* s) { return s->device; }
 
 static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d8, void* d64, cudaStream_t st,

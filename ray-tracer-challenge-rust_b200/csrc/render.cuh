@@ -24,9 +24,13 @@ int enable_peer_access(int device, int peer, std::string* err);
 int frame_share_create(int device, uint64_t bytes, void** d_ptr, unsigned char* handle64, std::string* err);
 int frame_share_open(int device, const unsigned char* handle64, void** d_ptr, std::string* err);
 int frame_share_close(int device, void* d_ptr, int owner, std::string* err);
-int device_scene_create(const FlatScene& flat, int device, DeviceScene** out, std::string* err);
+// -3: CUDA error; kDeviceBuildTooDeep: a device-built mesh came out deeper than the traversal stack (rebuild on the host).
+// *built_depth (optional): depth of the deepest device-built BVH.
+constexpr int kDeviceBuildTooDeep = -5;
+int device_scene_create(const FlatScene& flat, int device, DeviceScene** out, std::string* err, int* built_depth = nullptr);
 void device_scene_destroy(DeviceScene* s);
 uint64_t device_scene_bytes(const DeviceScene* s);
+uint64_t device_scene_upload_bytes(const DeviceScene* s);
 int device_scene_device(const DeviceScene* s);
 
 // Camera::render for the rows selected by `rows` into device buffers (either may be null), asynchronously on `stream`.

@@ -101,29 +101,41 @@ class HostSim:
         vp = C.c_void_p
         self.lib.sim_last_error.restype = C.c_char_p
         self.lib.sim_scene_create.argtypes = [vp, C.POINTER(vp)]
+        self.lib.sim_scene_create_ex.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]
+        self.lib.sim_scene_tables.argtypes = [vp, _capi.c_u64_p]
         self.lib.sim_scene_destroy.argtypes = [vp]
         self.lib.sim_render.argtypes = [vp, C.POINTER(_capi.CameraDesc), C.POINTER(C.c_uint32), C.c_uint64, C.c_int,
                                         _capi.c_double_p, C.POINTER(C.c_uint8), _capi.c_u64_p]
         self.lib.sim_color_at.argtypes = [vp, _capi.c_double_p, C.c_uint64, _capi.c_double_p]
 
-    def scene(self, world):
-        """Marshal a product World exactly as rtc_world_scene does and flatten it for the simulation."""
+    def scene(self, world, device_build=False):
+        """Marshal a product World exactly as rtc_world_scene does and flatten it for the simulation.  device_build:
+        meshes go through the simulated device build (csrc/lbvh.cuh run as loops) instead of the host SAH builder."""
         api = world.api
         m = C.c_void_p()
         api.check(api.world_marshal(world.h, C.byref(m)))
         try:
             s = C.c_void_p()
-            rc = self.lib.sim_scene_create(api.marshalled_desc(m), C.byref(s))
+            depth = C.c_int(0)
+            rc = self.lib.sim_scene_create_ex(api.marshalled_desc(m), int(device_build), C.byref(s), C.byref(depth))
             if rc != 0:
                 raise RuntimeError(f"hostsim {rc}: " + self.lib.sim_last_error().decode())
         finally:
             api.marshalled_free(m)
-        return SimScene(self, s)
+        sc = SimScene(self, s)
+        sc.bvh_depth = depth.value
+        return sc
 
 
 class SimScene:
     def __init__(self, sim, handle):
         self.sim, self.h = sim, handle
+
+    def tables(self):
+        """(bvh nodes, triangles, meshes, content hash of the mesh tables)."""
+        n = (C.c_uint64 * 4)()
+        self.sim.lib.sim_scene_tables(self.h, n)
+        return tuple(n)
 
     def render(self, cam, pixels=None, nthreads=None):
         d = cam.desc()

@@ -13,6 +13,7 @@
 #include "../../include/rtc.h"
 #include "../../ray-tracer-challenge-rust_b200/csrc/flatten.hpp"
 #include "../../ray-tracer-challenge-rust_b200/csrc/rt_core.cuh"
+#include "lbvh_sim.hpp"
 
 using namespace rtc;
 using namespace rtc::core;
@@ -28,15 +29,20 @@ struct Sim {
 extern "C" {
 const char* sim_last_error() { return g_err.c_str(); }
 
-int sim_scene_create(const rtc_scene_desc* desc, void** out) {
+// device_build != 0: meshes go through the simulated device build (lbvh_sim.hpp) instead of the host SAH builder
+int sim_scene_create_ex(const rtc_scene_desc* desc, int device_build, void** out, int* depth_out) {
     Sim* s = new Sim();
     std::string e;
-    int rc = flatten_scene(*desc, s->flat, &e);
+    FlattenOptions opts;
+    opts.device_mesh_build = device_build != 0;
+    int rc = flatten_scene(*desc, s->flat, &e, opts);
     if (rc != RTC_OK) {
         g_err = e;
         delete s;
         return rc;
     }
+    const int depth = lbvh_build_sim(s->flat);
+    if (depth_out) *depth_out = device_build ? depth : s->flat.bvh_max_depth;
     DScene& v = s->view;
     v.program = s->flat.program.data();
     v.xforms = s->flat.xforms.data();
@@ -57,7 +63,24 @@ int sim_scene_create(const rtc_scene_desc* desc, void** out) {
     *out = s;
     return 0;
 }
+int sim_scene_create(const rtc_scene_desc* desc, void** out) { return sim_scene_create_ex(desc, 0, out, nullptr); }
 void sim_scene_destroy(void* s) { delete (Sim*)s; }
+// table sizes and a content hash of the mesh tables (FNV-1a over bvh, tris, tri_attr), to compare builds
+void sim_scene_tables(void* scene, uint64_t n[4]) {
+    Sim* s = (Sim*)scene;
+    n[0] = s->flat.bvh.size();
+    n[1] = s->flat.tris.size();
+    n[2] = s->flat.meshes.size();
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t bytes) {
+        const unsigned char* b = (const unsigned char*)p;
+        for (size_t i = 0; i < bytes; i++) h = (h ^ b[i]) * 1099511628211ull;
+    };
+    mix(s->flat.bvh.data(), s->flat.bvh.size() * sizeof(DBvhNode));
+    mix(s->flat.tris.data(), s->flat.tris.size() * sizeof(DTri));
+    mix(s->flat.tri_attr.data(), s->flat.tri_attr.size() * sizeof(DTriAttr));
+    n[3] = h;
+}
 
 // pixel_xy == NULL: whole frame.  out_rgb: 3 f64 per pixel; counters[4] = primary, shadow, reflect, refract.
 int sim_render(void* scene, const rtc_camera_desc* cam, const uint32_t* pixel_xy, uint64_t npixels, int nthreads,

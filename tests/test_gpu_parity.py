@@ -256,3 +256,40 @@ def test_empty_world_is_black(rtc):
     w = rtc.World(rtc.Light((0, 10, 0), (1, 1, 1)))
     c = rtc.Camera(16, 8, 1.0)
     assert not c.render(w).pixels_f64().any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,w,h", [("teapot", 640, 360), ("cow_teddy", 960, 540), ("pumpkin", 1280, 720)])
+def test_device_mesh_build_renders_the_same_frame(rtc, oracle, name, w, h):
+    """RTC_BUILD_DEVICE_LBVH: triangle tables, normals and BVH built by csrc/lbvh.cu on the GPU.  Another tree, the same
+    frame and the same exact ray counts as the host-built scene, and the oracle's pixels on a subset."""
+    world, cam = rtc.build_scene(name, w, h)
+    host = np.empty((h, w, 4), dtype=np.uint8)
+    st_h = rtc.Stats()
+    cam.render_into(world, rgba8=host, stats=st_h)
+    info_h = world.scene_info()
+    world.set_build("device")
+    dev = np.zeros_like(host)
+    st_d = rtc.Stats()
+    cam.render_into(world, rgba8=dev, stats=st_d)
+    info_d = world.scene_info()
+    assert info_d["mesh_triangles"] == info_h["mesh_triangles"] and info_d["meshes"] == info_h["meshes"]
+    assert np.array_equal(host, dev)
+    assert (st_h.shadow_rays, st_h.reflect_rays, st_h.refract_rays) == (st_d.shadow_rays, st_d.reflect_rays, st_d.refract_rays)
+    # f64 colours: the two builds agree bit for bit (same device arithmetic, only the set of boxes tested differs) ...
+    rgb_d = np.empty((h, w, 3))
+    cam.render_into(world, rgb_f64=rgb_d)
+    world.set_build("host")
+    rgb_h = np.empty((h, w, 3))
+    cam.render_into(world, rgb_f64=rgb_h)
+    assert np.array_equal(rgb_d.view(np.uint64), rgb_h.view(np.uint64))
+    # ... and the oracle's pixels on a subset, to the usual bar
+    px = helpers.subset_pixels(w, h, 32, 16)
+    ow, oc = helpers.scenes.build(oracle, name, w, h)
+    ref, _ = oracle.render(ow, oc, mode=oracle.CACHED, pixels=px)
+    _check(ref, np.ascontiguousarray(rgb_d[px[:, 1], px[:, 0]]), oracle.quantise_rgba8(ref), dev[px[:, 1], px[:, 0]])
+    # rebuilt from scratch, the device build is deterministic
+    world.set_build("device")
+    again = np.zeros_like(host)
+    cam.render_into(world, rgba8=again)
+    assert np.array_equal(dev, again)

@@ -89,3 +89,50 @@ def test_explicit_rays_and_ties(rtc, oracle, hostsim):
         rays.append(np.concatenate([origin, d / np.linalg.norm(d)]))
     rays = np.array(rays)
     assert _bits_equal(oracle.color_at(ow, rays), hostsim.scene(world).color_at(rays))
+
+
+@pytest.mark.parametrize("name,w,h", [("teapot", 64, 36), ("cow", 64, 32), ("cow_teddy", 64, 36), ("pumpkin", 64, 36)])
+def test_device_mesh_build_bit_exact(rtc, oracle, hostsim, name, w, h):
+    """RTC_BUILD_DEVICE_LBVH (csrc/lbvh.cuh: Morton order, Karras hierarchy, fitted boxes), its kernel bodies run as loops
+    by tests/hostsim: another tree, the same pixels and ray counts as the oracle — bit for bit."""
+    world, cam = rtc.build_scene(name, w, h)
+    ow, oc = helpers.scenes.build(oracle, name, w, h)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    scene = hostsim.scene(world, device_build=True)
+    rgb, rgba, scnt = scene.render(cam)
+    assert _bits_equal(ref, rgb)
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+    assert 0 < scene.bvh_depth <= 46  # fits the device traversal stack (kBvhStackDepth - 2)
+    host = hostsim.scene(world)
+    assert scene.tables()[1] == host.tables()[1] and scene.tables()[3] != host.tables()[3]  # same triangles, other tree
+
+
+def test_device_mesh_build_degenerate_meshes(rtc, oracle, hostsim):
+    """Keys that collide: a mesh whose triangles all share one centroid (a fan of coincident copies) and a flat strip on
+    one axis — the hierarchy must still split (equal keys are told apart by sorted position) and stay shallow."""
+    n = 600
+    verts = [(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0)]
+    faces = [(1, 2, 3)] * n                                   # n coincident triangles
+    for i in range(n):                                          # a strip along x, all centroids on one line
+        verts += [(2.0 + i, 0.0, 0.0), (3.0 + i, 0.0, 0.0), (2.5 + i, 0.0, 1.0)]
+        faces.append((3 * i + 4, 3 * i + 5, 3 * i + 6))
+    v, f = np.asarray(verts, dtype=np.float64), np.asarray(faces, dtype=np.int32)
+
+    def build(api_like, mod):
+        Sx, Tx = mod.Shapes(api_like), mod.Transformations(api_like)
+        g = Sx.mesh(v, f)
+        g.set_transform(Tx.scaling(0.01, 1.0, 1.0))
+        w = mod.WorldHandle(api_like, mod.Light((0.0, 5.0, -5.0), (1.0, 1.0, 1.0)))
+        w.push(g)
+        cam = mod.CameraHandle(api_like, 48, 24, 0.9)
+        cam.set_transform(Tx.view_transform((3.0, 2.0, -6.0), (3.0, 0.0, 0.0), (0.0, 1.0, 0.0)))
+        return w, cam
+
+    world, cam = _wrap(rtc, *build(rtc.api(), helpers.scenes))
+    ow, oc = build(oracle, helpers.scenes)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    scene = hostsim.scene(world, device_build=True)
+    rgb, _, scnt = scene.render(cam)
+    assert _bits_equal(ref, rgb)
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+    assert scene.bvh_depth <= 46

@@ -48,15 +48,29 @@ def main():
             api.check(api.scene_create(desc, 0, C.byref(sc)))
             api.scene_destroy(sc)
 
+        def create_destroy_device():
+            sc = C.c_void_p()
+            api.check(api.scene_create_ex(desc, 0, rtc.RTC_BUILD_DEVICE_LBVH, C.byref(sc)))
+            api.scene_destroy(sc)
+
+        dscene = C.c_void_p()
+        api.check(api.scene_create_ex(desc, 0, rtc.RTC_BUILD_DEVICE_LBVH, C.byref(dscene)))
+
+        def render_device_built():
+            api.check(api.render(dscene, C.byref(cdesc), None, C.c_void_p(frame.data_ptr()), None, None))
+
         def render():
             api.check(api.render(scene, C.byref(cdesc), None, C.c_void_p(frame.data_ptr()), None, None))
 
         for _ in range(3):
-            create_destroy(); render()
+            create_destroy(); render(); create_destroy_device(); render_device_built()
         out[name] = {"marshal_ms": med(marshal), "flatten_only_ms": med(lambda: api.world_flatten_info(world.h, n8, None, 0)),
                      "scene_create_destroy_ms": med(create_destroy), "render_host_ms": med(render),
+                     "scene_create_destroy_device_build_ms": med(create_destroy_device),
+                     "render_host_device_built_ms": med(render_device_built),
                      "chunk_mib": os.environ.get("RTC_HOST_CHUNK_MIB", "default")}
         api.scene_destroy(scene)
+        api.scene_destroy(dscene)
         api.marshalled_free(m)
     print(json.dumps(out, indent=1))
 
