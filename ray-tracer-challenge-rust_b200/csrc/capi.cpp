@@ -161,6 +161,23 @@ int rtc_scene_create_ex(const rtc_scene_desc* desc, int device, uint32_t flags, 
         std::string e;
         FlattenOptions opts;
         opts.device_mesh_build = (flags & RTC_BUILD_DEVICE_LBVH) && attempt == 0;
+        // the device build's input arrays are megabytes: keep their pages across calls on this thread instead of
+        // faulting fresh ones in every time (a third of the gather time of a 10 k-triangle mesh)
+        thread_local std::vector<rtc_triangle_desc> keep_tri;
+        thread_local std::vector<int32_t> keep_mat;
+        struct Lend {
+            FlatScene& f;
+            Lend(FlatScene& fs) : f(fs) {
+                f.pending_tri.swap(keep_tri);
+                f.pending_material.swap(keep_mat);
+                f.pending_tri.clear();
+                f.pending_material.clear();
+            }
+            ~Lend() {
+                f.pending_tri.swap(keep_tri);
+                f.pending_material.swap(keep_mat);
+            }
+        } lend(flat);
         int rc = flatten_scene(*desc, flat, &e, opts);
         if (rc != RTC_OK) return set_err(rc, e);
         DeviceScene* dev = nullptr;

@@ -17,7 +17,10 @@ struct PendingMesh {
     int32_t xform, leaf0;
     int32_t tri_base, node_base;  // assigned when flattening ends
     double inv_t[16];             // transpose of the transform's inverse (shape.rs:216)
-    size_t input_offset;          // first triangle in pending_tri / pending_material
+    size_t input_offset;          // first entry in pending_material (and in pending_tri when `direct` is null)
+    // the run's triangles where they lie in the caller's description, when their indices are consecutive (the usual
+    // case: Parser::obj_to_group pushes them in order) — borrowed for the duration of rtc_scene_create, saves a gather
+    const rtc_triangle_desc* direct;
 };
 
 struct FlatScene {

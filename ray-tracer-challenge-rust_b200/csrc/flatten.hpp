@@ -408,13 +408,20 @@ class Flattener {
             p.leaf0 = (int32_t)next_leaf_;
             p.tri_base = p.node_base = -1;
             std::memcpy(p.inv_t, inv_t.m, sizeof(p.inv_t));
-            p.input_offset = out_.pending_tri.size();
-            out_.pending_tri.resize(p.input_offset + n);
+            p.input_offset = out_.pending_material.size();
             out_.pending_material.resize(p.input_offset + n);
+            const int32_t t0 = d_.shapes[begin].triangle;
+            bool consecutive = true;
             for (uint32_t k = 0; k < n; k++) {
                 const rtc_shape_desc& s = d_.shapes[begin + k];
-                out_.pending_tri[p.input_offset + k] = d_.triangles[s.triangle];
                 out_.pending_material[p.input_offset + k] = s.material;
+                consecutive = consecutive && s.triangle == t0 + (int32_t)k;
+            }
+            p.direct = consecutive ? d_.triangles + t0 : nullptr;
+            if (!consecutive) {  // gathered copy, index-aligned with pending_material
+                out_.pending_tri.resize(p.input_offset + n);
+                for (uint32_t k = 0; k < n; k++)
+                    out_.pending_tri[p.input_offset + k] = d_.triangles[d_.shapes[begin + k].triangle];
             }
             next_leaf_ += n;
             DMesh m;

@@ -79,7 +79,7 @@ inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
     } while (0)
 
 size_t lbvh_staging_bytes(const FlatScene& f) {
-    return align_up(f.pending_tri.size() * sizeof(rtc_triangle_desc)) + align_up(f.pending_material.size() * sizeof(int32_t));
+    return align_up(f.pending_material.size() * sizeof(rtc_triangle_desc)) + align_up(f.pending_material.size() * sizeof(int32_t));
 }
 
 int lbvh_build_device(const FlatScene& f, unsigned char* pinned, DBvhNode* d_nodes, DTri* d_tris, DTriAttr* d_attr,
@@ -89,7 +89,7 @@ int lbvh_build_device(const FlatScene& f, unsigned char* pinned, DBvhNode* d_nod
     if (f.pending.empty()) return 0;
     uint32_t nmax = 0;
     for (const PendingMesh& p : f.pending) nmax = std::max(nmax, p.n);
-    const size_t total_in = f.pending_tri.size();
+    const size_t total_in = f.pending_material.size();
 
     size_t cub_bytes = 0;
     LBVH_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
@@ -113,7 +113,9 @@ int lbvh_build_device(const FlatScene& f, unsigned char* pinned, DBvhNode* d_nod
 
     // inputs: pageable vectors -> pinned staging -> device
     const size_t tri_bytes = total_in * sizeof(rtc_triangle_desc), mat_bytes = total_in * sizeof(int32_t);
-    std::memcpy(pinned, f.pending_tri.data(), tri_bytes);
+    for (const PendingMesh& p : f.pending)
+        std::memcpy(pinned + p.input_offset * sizeof(rtc_triangle_desc),
+                    p.direct ? p.direct : f.pending_tri.data() + p.input_offset, (size_t)p.n * sizeof(rtc_triangle_desc));
     std::memcpy(pinned + align_up(tri_bytes), f.pending_material.data(), mat_bytes);
     LBVH_CUDA(cudaMemcpyAsync(base + o_tri, pinned, tri_bytes, cudaMemcpyHostToDevice, st));
     LBVH_CUDA(cudaMemcpyAsync(base + o_mat, pinned + align_up(tri_bytes), mat_bytes, cudaMemcpyHostToDevice, st));

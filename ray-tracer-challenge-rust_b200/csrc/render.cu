@@ -258,7 +258,7 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->slab_size = total;
     s->upload_bytes = at;
     if (!f.pending.empty()) {
-        s->upload_bytes = f.pending_tri.size() * (sizeof(rtc_triangle_desc) + sizeof(int32_t));
+        s->upload_bytes = f.pending_material.size() * (sizeof(rtc_triangle_desc) + sizeof(int32_t));
         for (size_t b : raw) s->upload_bytes += b;
     }
     unsigned char* base = (unsigned char*)s->slab;

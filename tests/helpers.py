@@ -164,6 +164,36 @@ class SimScene:
             self.h = None
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def scattered_description(world, seed=5):
+    """(desc, scattered): the marshalled rtc_scene_desc of a product World and a copy whose triangle payloads are stored
+    in a random order (shape.triangle indices follow) — the same world, described differently."""
+    api = world.api
+    m = C.c_void_p()
+    api.check(api.world_marshal(world.h, C.byref(m)))
+    try:
+        desc = C.cast(api.marshalled_desc(m), C.POINTER(_capi.SceneDesc)).contents
+        nt, ns = desc.triangle_count, desc.shape_count
+        perm = np.random.default_rng(seed).permutation(nt)  # new position of each payload
+        tris = (_capi.TriangleDesc * nt)()
+        for old in range(nt):
+            tris[int(perm[old])] = desc.triangles[old]
+        shapes = (_capi.ShapeDesc * ns)()
+        for i in range(ns):
+            shapes[i] = desc.shapes[i]
+            if shapes[i].kind == 6:
+                shapes[i].triangle = int(perm[shapes[i].triangle])
+        d2 = _capi.SceneDesc()
+        C.memmove(C.byref(d2), C.byref(desc), C.sizeof(_capi.SceneDesc))
+        d2.triangles, d2.shapes = tris, shapes
+        yield desc, d2
+    finally:
+        api.marshalled_free(m)
+
+
 def load_hostsim():
     csrc = os.path.join(ROOT, "ray-tracer-challenge-rust_b200", "csrc")
     srcs = [SIM_SRC, os.path.join(ROOT, "include", "rtc.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc)]

@@ -23,7 +23,7 @@ inline int lbvh_build_sim(FlatScene& f) {
     for (const PendingMesh& p : f.pending) {
         const uint32_t n = p.n;
         lbvh::Work w{};
-        w.tri = f.pending_tri.data() + p.input_offset;
+        w.tri = p.direct ? p.direct : f.pending_tri.data() + p.input_offset;
         w.material = f.pending_material.data() + p.input_offset;
         w.n = n;
         w.xform = p.xform;

@@ -293,3 +293,24 @@ def test_device_mesh_build_renders_the_same_frame(rtc, oracle, name, w, h):
     again = np.zeros_like(host)
     cam.render_into(world, rgba8=again)
     assert np.array_equal(dev, again)
+
+
+@pytest.mark.gpu
+def test_device_mesh_build_gathers_scattered_triangles(rtc):
+    """Triangle payloads stored out of shape order: the device build gathers its input instead of reading the caller's
+    array in place; both builds of both descriptions render one frame."""
+    world, cam = rtc.build_scene("teapot", 320, 180)
+    api = rtc.api()
+    cdesc = cam.desc()
+    frames = []
+    with helpers.scattered_description(world) as (desc, scattered):
+        for d in (desc, scattered):
+            for flags in (rtc.RTC_BUILD_HOST_SAH, rtc.RTC_BUILD_DEVICE_LBVH):
+                scene = C.c_void_p()
+                api.check(api.scene_create_ex(C.cast(C.byref(d), C.c_void_p), 0, flags, C.byref(scene)))
+                out = np.zeros((180, 320, 4), dtype=np.uint8)
+                api.check(api.render(scene, C.byref(cdesc), None, out.ctypes.data_as(C.c_void_p), None, None))
+                api.scene_destroy(scene)
+                frames.append(out)
+    for f in frames[1:]:
+        assert np.array_equal(frames[0], f)

@@ -136,3 +136,17 @@ def test_device_mesh_build_degenerate_meshes(rtc, oracle, hostsim):
     assert _bits_equal(ref, rgb)
     assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
     assert scene.bvh_depth <= 46
+
+
+def test_device_mesh_build_gathers_scattered_triangles(rtc, hostsim):
+    """A description whose triangle payloads are NOT stored in shape order (the boundary allows any indices) takes the
+    gather path of the device build's input; the frame is the one of the in-order description."""
+    import ctypes as C
+    world, cam = rtc.build_scene("teapot", 48, 27)
+    with helpers.scattered_description(world) as (desc, scattered):
+        frames = []
+        for d in (desc, scattered):
+            s, depth = C.c_void_p(), C.c_int(0)
+            assert hostsim.lib.sim_scene_create_ex(C.cast(C.byref(d), C.c_void_p), 1, C.byref(s), C.byref(depth)) == 0
+            frames.append(helpers.SimScene(hostsim, s).render(cam)[0])
+        assert _bits_equal(frames[0], frames[1])
