@@ -145,7 +145,8 @@ static void trace_phases(const char* who, const FlatScene& flat) {
     const double* t = flat.phase_ms;
     std::fprintf(stderr, "[rtc] %s: validate %.3f  group bounds %.3f  bvh items %.3f / build %.3f / splice %.3f  "
                          "triangle tables %.3f  upload %.3f ms (%zu triangles, %zu bvh nodes)\n",
-                 who, t[0], t[1], t[2], t[3], t[4], t[5], t[6], flat.tris.size(), flat.bvh.size());
+                 who, t[0], t[1], t[2], t[3], t[4], t[5], t[6], flat.tris.size() + flat.device_tris,
+                 flat.bvh.size() + flat.device_nodes);
 }
 
 /* ---------------------------------------------------------------------------------------------- 1. CORE BOUNDARY */
