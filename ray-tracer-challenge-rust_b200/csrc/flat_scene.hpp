@@ -21,6 +21,10 @@ struct PendingMesh {
     // the run's triangles where they lie in the caller's description, when their indices are consecutive (the usual
     // case: Parser::obj_to_group pushes them in order) — borrowed for the duration of rtc_scene_create, saves a gather
     const rtc_triangle_desc* direct;
+    // >= 0: this run is all its group holds and the group is a World object (or the only child of one): the device folds
+    // the group's gate box too (bounds.rs:50-151) into gates[gate_index], through the children's `transform`
+    int32_t gate_index;
+    double transform[16];
 };
 
 struct FlatScene {

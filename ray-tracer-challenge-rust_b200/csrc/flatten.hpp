@@ -94,6 +94,8 @@ class Flattener {
     uint32_t next_leaf_ = 0;
     int32_t parent_gate_ = -1;  // gate of the group being emitted, if this node is its ONLY child
     bool only_child_ = false;
+    int group_depth_ = 0;        // 0 while emitting World.objects themselves
+    int32_t pending_gate_ = -1;  // gate the next device-built mesh run folds (see device_gate_run)
 
     [[noreturn]] static void fail(int code, const std::string& m) { throw FlattenError{code, m}; }
     static void check(bool c, const char* m) {
@@ -355,13 +357,54 @@ class Flattener {
         }
     }
 
-    void emit_group(uint32_t i) {
+    void require_identity(uint32_t i) const {
         // the reference intersects a group in the space of its own transform, which set_transform never changes from
         // the identity (shape.rs:203-217); anything else has no reference behaviour to match
         const double* t = d_.transforms[d_.shapes[i].transform].transform;
         Mat4 id = Mat4::identity();
         for (int k = 0; k < 16; k++)
             if (!(t[k] == id.m[k])) fail(RTC_ERR_UNSUPPORTED, "a group's own transform must be the identity (shape.rs:203-217)");
+    }
+    // group g holds nothing but one run of >= kDeviceBuildMin triangles that share one transform entry
+    bool device_gate_run(uint32_t g) const {
+        const rtc_shape_desc& s = d_.shapes[g];
+        if (s.kind != RTC_GROUP || (uint32_t)s.child_count < kDeviceBuildMin || end_[g] - g - 1 != (uint32_t)s.child_count)
+            return false;
+        const int32_t tr = d_.shapes[g + 1].transform;
+        for (uint32_t c = g + 1; c < end_[g]; c++)
+            if (d_.shapes[c].kind != RTC_TRIANGLE || d_.shapes[c].transform != tr) return false;
+        return true;
+    }
+
+    void emit_group(uint32_t i) {
+        require_identity(i);
+        if (opts_.device_mesh_build && group_depth_ == 0) {
+            // A World object that is a mesh — group{ triangles } or, as Parser::obj_to_group builds it,
+            // group{ default_group{ triangles } } — leaves its gate box to the device build along with the mesh: the fold
+            // over 8 corners per triangle is the largest host cost left (bounds.rs:50-151).  The outer group's box is
+            // the inner one's (identity child transform, both origin-seeded), so one gate stands for both, as below.
+            uint32_t g = i;
+            const bool nested = d_.shapes[i].child_count == 1 && d_.shapes[i + 1].kind == RTC_GROUP;
+            if (nested) g = i + 1;
+            if (device_gate_run(g)) {
+                if (nested) {
+                    require_identity(g);
+                    out_.merged_gates++;
+                }
+                const size_t at = out_.program.size();
+                out_.program.push_back(DProgramNode{NODE_GATE, (int32_t)out_.gates.size(), 0, 0});
+                DGate zero;
+                std::memset(&zero, 0, sizeof(zero));
+                out_.gates.push_back(zero);
+                pending_gate_ = (int32_t)out_.gates.size() - 1;
+                group_depth_++;
+                emit_children(g + 1, end_[g]);  // one run -> one pending mesh, which takes pending_gate_
+                group_depth_--;
+                if (pending_gate_ != -1) fail(RTC_ERR_INVALID, "internal: device gate not taken by its mesh");
+                out_.program[at].skip = (int32_t)out_.program.size();
+                return;
+            }
+        }
         PhaseClock clock;
         Box4 b = bounds_of(i);
         clock.lap(out_.phase_ms, FlatScene::T_BOUNDS);
@@ -375,7 +418,9 @@ class Flattener {
             const int32_t saved_parent = parent_gate_;
             const bool saved_only = only_child_;
             only_child_ = (d_.shapes[i].child_count == 1);
+            group_depth_++;
             emit_children(i + 1, end_[i]);
+            group_depth_--;
             parent_gate_ = saved_parent;
             only_child_ = saved_only;
             out_.merged_gates++;
@@ -388,7 +433,9 @@ class Flattener {
         const bool saved_only = only_child_;
         parent_gate_ = (int32_t)out_.gates.size() - 1;
         only_child_ = (d_.shapes[i].child_count == 1);
+        group_depth_++;
         emit_children(i + 1, end_[i]);
+        group_depth_--;
         parent_gate_ = saved_parent;
         only_child_ = saved_only;
         out_.program[at].skip = (int32_t)out_.program.size();
@@ -418,6 +465,9 @@ class Flattener {
                 consecutive = consecutive && s.triangle == t0 + (int32_t)k;
             }
             p.direct = consecutive ? d_.triangles + t0 : nullptr;
+            p.gate_index = pending_gate_;
+            pending_gate_ = -1;
+            std::memcpy(p.transform, td.transform, sizeof(p.transform));
             if (!consecutive) {  // gathered copy, index-aligned with pending_material
                 out_.pending_tri.resize(p.input_offset + n);
                 for (uint32_t k = 0; k < n; k++)

@@ -27,24 +27,28 @@ __global__ void k_init(lbvh::Work w) {
 // per-triangle values are reduced across the warp first: seven atomics per warp instead of seven per thread
 __global__ void k_bounds(lbvh::Work w) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long v[7];
+    unsigned long long v[13];  // 7 of tri_bounds, 6 of the gate fold
+    bool ok = true;
+    for (int a = 0; a < 13; a++) v[a] = (a < 3 || (a >= 7 && a < 10)) ? ~0ull : 0ull;
     if (k < w.n) {
         lbvh::tri_bounds_values(w, k, v);
-    } else {
-        for (int a = 0; a < 3; a++) {
-            v[a] = ~0ull;
-            v[3 + a] = 0ull;
-        }
-        v[6] = 0ull;
+        if (w.gate_out) lbvh::gate_values(w, k, v + 7, &ok);
     }
+    const int count = w.gate_out ? 13 : 7;
     for (int off = 16; off > 0; off >>= 1)
-        for (int a = 0; a < 7; a++) {
+        for (int a = 0; a < count; a++) {
             const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[a], off);
-            v[a] = a < 3 ? (o < v[a] ? o : v[a]) : (o > v[a] ? o : v[a]);
+            const bool is_min = a < 3 || (a >= 7 && a < 10);
+            v[a] = is_min ? (o < v[a] ? o : v[a]) : (o > v[a] ? o : v[a]);
         }
+    if (!ok) *w.error = 1;
     if ((threadIdx.x & 31) == 0) {
         for (int a = 0; a < 3; a++) atomicMin(w.gbox + a, v[a]);
         for (int a = 3; a < 7; a++) atomicMax(w.gbox + a, v[a]);
+        if (w.gate_out) {
+            for (int a = 0; a < 3; a++) atomicMin(w.gate_acc + a, v[7 + a]);
+            for (int a = 3; a < 6; a++) atomicMax(w.gate_acc + a, v[7 + a]);
+        }
     }
 }
 __global__ void k_morton(lbvh::Work w) {
@@ -83,7 +87,8 @@ size_t lbvh_staging_bytes(const FlatScene& f) {
 }
 
 int lbvh_build_device(const FlatScene& f, unsigned char* pinned, DBvhNode* d_nodes, DTri* d_tris, DTriAttr* d_attr,
-                      DMesh* d_meshes, cudaStream_t st, int* max_depth, std::string* err) {
+                      DMesh* d_meshes, DGate* d_gates, cudaStream_t st, int* max_depth, bool* would_panic,
+                      std::string* err) {
     void* scratch = nullptr;
     if (max_depth) *max_depth = 0;
     if (f.pending.empty()) return 0;
@@ -103,7 +108,7 @@ int lbvh_build_device(const FlatScene& f, unsigned char* pinned, DBvhNode* d_nod
         return o;
     };
     const size_t o_tri = take(total_in * sizeof(rtc_triangle_desc)), o_mat = take(total_in * sizeof(int32_t));
-    const size_t o_gbox = take(8 * sizeof(unsigned long long)), o_depth = take(sizeof(int32_t));
+    const size_t o_gbox = take(16 * sizeof(unsigned long long)), o_depth = take(2 * sizeof(int32_t));  // + gate_acc; + error
     const size_t o_keys0 = take(nmax * 8), o_keys1 = take(nmax * 8), o_ord0 = take(nmax * 4), o_ord1 = take(nmax * 4);
     const size_t o_left = take(nmax * 4), o_right = take(nmax * 4), o_parent = take(nmax * 4), o_first = take(nmax * 4),
                  o_last = take(nmax * 4), o_leafp = take(nmax * 4), o_arrive = take(nmax * 4);
@@ -119,7 +124,7 @@ int lbvh_build_device(const FlatScene& f, unsigned char* pinned, DBvhNode* d_nod
     std::memcpy(pinned + align_up(tri_bytes), f.pending_material.data(), mat_bytes);
     LBVH_CUDA(cudaMemcpyAsync(base + o_tri, pinned, tri_bytes, cudaMemcpyHostToDevice, st));
     LBVH_CUDA(cudaMemcpyAsync(base + o_mat, pinned + align_up(tri_bytes), mat_bytes, cudaMemcpyHostToDevice, st));
-    LBVH_CUDA(cudaMemsetAsync(base + o_depth, 0, sizeof(int32_t), st));
+    LBVH_CUDA(cudaMemsetAsync(base + o_depth, 0, 2 * sizeof(int32_t), st));
 
     for (const PendingMesh& p : f.pending) {
         lbvh::Work w{};
@@ -144,6 +149,10 @@ int lbvh_build_device(const FlatScene& f, unsigned char* pinned, DBvhNode* d_nod
         w.box = (double*)(base + o_box);
         w.leaf_box = (double*)(base + o_lbox);
         w.depth_max = (int32_t*)(base + o_depth);
+        w.error = (int32_t*)(base + o_depth) + 1;
+        w.gate_acc = (unsigned long long*)(base + o_gbox) + 8;
+        w.gate_out = p.gate_index >= 0 ? d_gates + p.gate_index : nullptr;
+        std::memcpy(w.tr, p.transform, sizeof(w.tr));
         w.nodes = d_nodes;
         w.tris = d_tris;
         w.attr = d_attr;
@@ -165,11 +174,12 @@ int lbvh_build_device(const FlatScene& f, unsigned char* pinned, DBvhNode* d_nod
         k_emit<<<blocks_for(p.n - 1), kThreads, 0, st>>>(w);
         LBVH_CUDA(cudaGetLastError());
     }
-    int32_t depth = 0;
-    LBVH_CUDA(cudaMemcpyAsync(&depth, base + o_depth, sizeof(depth), cudaMemcpyDeviceToHost, st));
+    int32_t result[2] = {0, 0};  // deepest tree, "the reference would panic"
+    LBVH_CUDA(cudaMemcpyAsync(result, base + o_depth, sizeof(result), cudaMemcpyDeviceToHost, st));
     LBVH_CUDA(cudaStreamSynchronize(st));
     LBVH_CUDA(cudaFreeAsync(scratch, st));
-    if (max_depth) *max_depth = depth;
+    if (max_depth) *max_depth = result[0];
+    if (would_panic) *would_panic = result[1] != 0;
     return 0;
 }
 

@@ -7,7 +7,8 @@
 //
 // Each step is a plain function of a thread index so that the same code runs as CUDA kernels (lbvh.cu) and, for the CPU
 // tests, as loops (tests/hostsim — test infrastructure only):
-//   1. tri_bounds   per triangle: box and centroid; mesh-wide centroid box and max |coordinate| (atomic min/max)
+//   1. tri_bounds   per triangle: box and centroid; mesh-wide centroid box and max |coordinate| (atomic min/max);
+//      gate_fold    and, when the mesh is all its group holds, the group's gate box exactly as Bounds::new folds it
 //   2. tri_morton   per triangle: 63-bit Morton key of the centroid (21 bits per axis)
 //      sort         (key, triangle) pairs by key — cub::DeviceRadixSort on the device, std::stable_sort in the simulation
 //   3. hierarchy    per inner node (n-1 of them): range and split by longest common key prefix (Karras 2012), equal keys
@@ -48,6 +49,7 @@ struct Work {
     int32_t xform, leaf0;
     int32_t tri_base, node_base;  // where this mesh's slots / nodes start in the scene tables
     double inv_t[16];             // transpose of the mesh transform's inverse (shape.rs:216)
+    double tr[16];                // the triangles' transform (gate fold)
     // scratch
     unsigned long long* gbox;  // [7] order-preserving encodings: centroid min xyz, centroid max xyz, max |coordinate|
     unsigned long long* keys;  // n Morton keys (sorted with `order`)
@@ -58,11 +60,14 @@ struct Work {
     double* box;                                    // (n-1) x 6: lo xyz, hi xyz
     double* leaf_box;                               // n x 6, by slot
     int32_t* depth_max;                             // 1, zeroed
+    unsigned long long* gate_acc;                   // [6] ordered bits of the group box being folded: lo xyz, hi xyz
+    int32_t* error;                                 // 1, zeroed; set when the reference would panic (bounds.rs:143)
     // output (scene tables)
     DBvhNode* nodes;  // n-1 entries at node_base, zeroed beforehand
     DTri* tris;       // n entries at tri_base
     DTriAttr* attr;
     DMesh* mesh;
+    DGate* gate_out;  // null: the mesh's group box was folded on the host
 };
 
 // ---- atomics: CUDA on the device, plain on the (single-threaded) simulation ------------------------------------------
@@ -133,6 +138,42 @@ LBVH_HD void gbox_init(const Work& w) {
         w.gbox[3 + a] = 0ull;
     }
     w.gbox[6] = 0ull;
+    for (int a = 0; a < 6; a++) w.gate_acc[a] = order_bits(0.0);  // Bounds::new seeds a group's box with the origin
+}
+// The gate box of the mesh's group (bounds.rs:50-151), this triangle's share: its origin-seeded box (bounds.rs:126-137),
+// the eight corners through the triangle's transform with the sums of matrix.rs:207-227 (left to right, w row included),
+// folded with f64::min / f64::max.  v[0..2] minima, v[3..5] maxima as ordered bits; *ok = false where Bounds::add would
+// panic (w != 1: a non-finite coordinate).
+LBVH_HD void gate_values(const Work& w, uint32_t k, unsigned long long v[6], bool* ok) {
+    double lo[3], hi[3];
+    tri_box(w.tri[k], lo, hi);
+    for (int a = 0; a < 3; a++) {
+        lo[a] = fmin(lo[a], 0.0);
+        hi[a] = fmax(hi[a], 0.0);
+    }
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int c = 0; c < 8; c++) {
+        const double x = (c & 4) ? hi[0] : lo[0], y = (c & 2) ? hi[1] : lo[1], z = (c & 1) ? hi[2] : lo[2];
+        const double wv = w.tr[12] * x + w.tr[13] * y + w.tr[14] * z + w.tr[15] * 1.0;
+        if (!(wv == 1.0)) *ok = false;
+        for (int r = 0; r < 3; r++) {
+            const double p = w.tr[4 * r] * x + w.tr[4 * r + 1] * y + w.tr[4 * r + 2] * z + w.tr[4 * r + 3] * 1.0;
+            mn[r] = fmin(mn[r], p);
+            mx[r] = fmax(mx[r], p);
+        }
+    }
+    for (int r = 0; r < 3; r++) {
+        v[r] = mn[r] == mn[r] ? order_bits(mn[r]) : ~0ull;
+        v[3 + r] = mx[r] == mx[r] ? order_bits(mx[r]) : 0ull;
+    }
+}
+LBVH_HD void gate_fold(const Work& w, uint32_t k) {
+    unsigned long long v[6];
+    bool ok = true;
+    gate_values(w, k, v, &ok);
+    for (int a = 0; a < 3; a++) atomic_min_u64(w.gate_acc + a, v[a]);
+    for (int a = 3; a < 6; a++) atomic_max_u64(w.gate_acc + a, v[a]);
+    if (!ok) *w.error = 1;
 }
 // v[0..2] centroid (for the min), v[3..5] centroid (for the max), v[6] max |coordinate|, as ordered bits
 LBVH_HD void tri_bounds_values(const Work& w, uint32_t k, unsigned long long v[7]) {
@@ -346,6 +387,11 @@ LBVH_HD void emit(const Work& w, uint32_t node) {
     if (i == 0) {
         w.mesh->root = w.node_base;
         w.mesh->extent = f32_above(max_abs * (1.0 + 2.0 * kPad));
+        if (w.gate_out)
+            for (int a = 0; a < 3; a++) {
+                w.gate_out->lo[a] = order_value(w.gate_acc[a]);
+                w.gate_out->hi[a] = order_value(w.gate_acc[3 + a]);
+            }
     }
 }
 

@@ -229,15 +229,18 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     if (e == cudaSuccess && !f.pending.empty()) {
         unsigned char* base = (unsigned char*)slab;
         int depth = 0;
+        bool would_panic = false;
         const int rc = lbvh_build_device(f, host + ((at + 255) & ~(size_t)255), (DBvhNode*)(base + off[5]), (DTri*)(base + off[6]),
-                                         (DTriAttr*)(base + off[7]), (DMesh*)(base + off[4]), ctx->stream, &depth, err);
+                                         (DTriAttr*)(base + off[7]), (DMesh*)(base + off[4]), (DGate*)(base + off[3]),
+                                         ctx->stream, &depth, &would_panic, err);
         if (rc != 0) {
             cudaFreeAsync(slab, ctx->stream);
             return rc;
         }
-        if (depth + 2 > kBvhStackDepth) {  // a pathological key distribution: the caller rebuilds on the host
+        // a pathological key distribution, or a coordinate the reference panics on: the caller rebuilds on the host
+        if (depth + 2 > kBvhStackDepth || would_panic) {
             cudaFreeAsync(slab, ctx->stream);
-            if (err) *err = "device-built BVH deeper than the traversal stack";
+            if (err) *err = would_panic ? "device gate fold met a non-finite coordinate" : "device-built BVH deeper than the traversal stack";
             return kDeviceBuildTooDeep;
         }
         if (built_depth) *built_depth = depth;

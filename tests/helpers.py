@@ -103,6 +103,8 @@ class HostSim:
         self.lib.sim_scene_create.argtypes = [vp, C.POINTER(vp)]
         self.lib.sim_scene_create_ex.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]
         self.lib.sim_scene_tables.argtypes = [vp, _capi.c_u64_p]
+        self.lib.sim_scene_gates.argtypes = [vp, _capi.c_double_p, C.c_uint64]
+        self.lib.sim_scene_gates.restype = C.c_uint64
         self.lib.sim_scene_destroy.argtypes = [vp]
         self.lib.sim_render.argtypes = [vp, C.POINTER(_capi.CameraDesc), C.POINTER(C.c_uint32), C.c_uint64, C.c_int,
                                         _capi.c_double_p, C.POINTER(C.c_uint8), _capi.c_u64_p]
@@ -130,6 +132,12 @@ class HostSim:
 class SimScene:
     def __init__(self, sim, handle):
         self.sim, self.h = sim, handle
+
+    def gates(self):
+        """(n, 6) gate boxes: lo xyz, hi xyz."""
+        buf = np.zeros((64, 6))
+        n = self.sim.lib.sim_scene_gates(self.h, buf.ctypes.data_as(_capi.c_double_p), 64)
+        return buf[:n]
 
     def tables(self):
         """(bvh nodes, triangles, meshes, content hash of the mesh tables)."""

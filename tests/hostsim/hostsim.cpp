@@ -65,6 +65,15 @@ int sim_scene_create_ex(const rtc_scene_desc* desc, int device_build, void** out
 }
 int sim_scene_create(const rtc_scene_desc* desc, void** out) { return sim_scene_create_ex(desc, 0, out, nullptr); }
 void sim_scene_destroy(void* s) { delete (Sim*)s; }
+// the gate boxes (6 doubles each: lo xyz, hi xyz); returns how many the scene has
+uint64_t sim_scene_gates(void* scene, double* out, uint64_t cap) {
+    Sim* s = (Sim*)scene;
+    for (uint64_t i = 0; i < s->flat.gates.size() && i < cap; i++) {
+        std::memcpy(out + 6 * i, s->flat.gates[i].lo, 24);
+        std::memcpy(out + 6 * i + 3, s->flat.gates[i].hi, 24);
+    }
+    return s->flat.gates.size();
+}
 // table sizes and a content hash of the mesh tables (FNV-1a over bvh, tris, tri_attr), to compare builds
 void sim_scene_tables(void* scene, uint64_t n[4]) {
     Sim* s = (Sim*)scene;

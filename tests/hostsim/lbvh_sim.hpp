@@ -35,13 +35,20 @@ inline int lbvh_build_sim(FlatScene& f) {
         std::vector<uint32_t> order(n), arrive(n - 1, 0);
         std::vector<int32_t> left(n - 1), right(n - 1), parent(n - 1), first(n - 1), last(n - 1), leaf_parent(n);
         std::vector<double> box(6 * (size_t)(n - 1)), leaf_box(6 * (size_t)n);
-        int32_t depth_max = 0;
+        int32_t depth_max = 0, error = 0;
+        unsigned long long gate_acc[6];
+        w.gate_acc = gate_acc;
+        w.error = &error;
+        w.gate_out = p.gate_index >= 0 ? &f.gates[p.gate_index] : nullptr;
+        std::memcpy(w.tr, p.transform, sizeof(w.tr));
         w.gbox = gbox.data(); w.keys = keys.data(); w.order = order.data(); w.left = left.data(); w.right = right.data();
         w.parent = parent.data(); w.first = first.data(); w.last = last.data(); w.leaf_parent = leaf_parent.data();
         w.arrive = arrive.data(); w.box = box.data(); w.leaf_box = leaf_box.data(); w.depth_max = &depth_max;
         w.nodes = f.bvh.data(); w.tris = f.tris.data(); w.attr = f.tri_attr.data(); w.mesh = &f.meshes[p.mesh_index];
         lbvh::gbox_init(w);
         for (uint32_t k = 0; k < n; k++) lbvh::tri_bounds(w, k);
+        if (w.gate_out)
+            for (uint32_t k = 0; k < n; k++) lbvh::gate_fold(w, k);
         for (uint32_t k = 0; k < n; k++) lbvh::tri_morton(w, k);
         std::vector<uint32_t> perm(n);
         std::iota(perm.begin(), perm.end(), 0u);
@@ -57,6 +64,7 @@ inline int lbvh_build_sim(FlatScene& f) {
         for (uint32_t s = 0; s < n; s++) lbvh::fit(w, s);
         for (uint32_t i = 0; i + 1 < n; i++) lbvh::emit(w, i);
         if (depth_max > depth_all) depth_all = depth_max;
+        if (error) depth_all = 1 << 20;  // "rebuild on the host", as the product does
     }
     f.pending.clear();
     f.device_tris = f.device_nodes = 0;

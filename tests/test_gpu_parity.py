@@ -314,3 +314,21 @@ def test_device_mesh_build_gathers_scattered_triangles(rtc):
                 frames.append(out)
     for f in frames[1:]:
         assert np.array_equal(frames[0], f)
+
+
+@pytest.mark.gpu
+def test_device_build_falls_back_to_the_host_for_the_reference_panic(rtc):
+    """bounds.rs:143 for a mesh with a non-finite vertex: the device gate fold flags it, the library rebuilds on the host
+    and reports the reference's panic — the same error as the host build."""
+    v, f = helpers.scenes.load_mesh("teapot")
+    v = np.array(v, dtype=np.float64)
+    v[17, 1] = np.inf
+    for build in ("host", "device"):
+        S = rtc.Shapes(rtc.api())
+        w = rtc.World(rtc.Light((0, 5, -5), (1, 1, 1)))
+        w.push(S.mesh(v, f))
+        w.set_build(build)
+        cam = rtc.Camera(32, 16, 0.8)
+        with pytest.raises(rtc.RtcError) as e:
+            cam.render(w)
+        assert e.value.code == rtc.RTC_ERR_PANIC and "bounds.rs:143" in e.value.message

@@ -105,6 +105,9 @@ def test_device_mesh_build_bit_exact(rtc, oracle, hostsim, name, w, h):
     assert 0 < scene.bvh_depth <= 46  # fits the device traversal stack (kBvhStackDepth - 2)
     host = hostsim.scene(world)
     assert scene.tables()[1] == host.tables()[1] and scene.tables()[3] != host.tables()[3]  # same triangles, other tree
+    # the mesh groups' gate boxes were folded by the (simulated) device too: the values of the host fold (bounds.rs:50-151)
+    assert scene.gates().shape == host.gates().shape and len(scene.gates()) >= 1
+    assert np.array_equal(scene.gates(), host.gates())
 
 
 def test_device_mesh_build_degenerate_meshes(rtc, oracle, hostsim):
@@ -150,3 +153,18 @@ def test_device_mesh_build_gathers_scattered_triangles(rtc, hostsim):
             assert hostsim.lib.sim_scene_create_ex(C.cast(C.byref(d), C.c_void_p), 1, C.byref(s), C.byref(depth)) == 0
             frames.append(helpers.SimScene(hostsim, s).render(cam)[0])
         assert _bits_equal(frames[0], frames[1])
+
+
+def test_device_gate_fold_leaves_the_panic_to_the_host_build(rtc, hostsim):
+    """A non-finite vertex makes Bounds::add panic in the reference (bounds.rs:143).  The device fold only flags it; the
+    product then rebuilds on the host, which raises the reference's panic."""
+    v, f = helpers.scenes.load_mesh("teapot")
+    v = np.array(v, dtype=np.float64)
+    v[17, 1] = np.inf
+    S = rtc.Shapes(rtc.api())
+    w = rtc.World(rtc.Light((0, 5, -5), (1, 1, 1)))
+    w.push(S.mesh(v, f))
+    scene = hostsim.scene(w, device_build=True)
+    assert scene.bvh_depth >= 1 << 20          # the simulated device build says "rebuild on the host"
+    with pytest.raises(RuntimeError, match="bounds.rs:143"):
+        hostsim.scene(w)                        # ... and the host build panics like the reference
