@@ -255,3 +255,20 @@ def test_long_leaf_run_with_an_unbounded_child_still_panics(rtc):
     with pytest.raises(rtc.RtcError) as e:
         w.flatten_info()
     assert e.value.code == rtc.RTC_ERR_PANIC and "bounds.rs:143" in e.value.message
+
+
+def test_build_flags_are_validated_before_any_device_work(rtc):
+    api = rtc.api()
+    w = rtc.World(rtc.Light((0, 0, 0), (1, 1, 1)))
+    assert api.world_set_build(w.h, 7) == rtc.RTC_ERR_INVALID and "build flag" in api.error()
+    assert api.world_set_build(w.h, rtc.RTC_BUILD_DEVICE_LBVH) == rtc.RTC_OK
+    assert api.world_set_build(w.h, rtc.RTC_BUILD_HOST_SAH) == rtc.RTC_OK
+    with pytest.raises(KeyError):
+        w.set_build("fastest")
+    m = C.c_void_p()
+    api.check(api.world_marshal(w.h, C.byref(m)))
+    try:
+        out = C.c_void_p()
+        assert api.scene_create_ex(api.marshalled_desc(m), 0, 0x10, C.byref(out)) == rtc.RTC_ERR_INVALID
+    finally:
+        api.marshalled_free(m)
