@@ -332,3 +332,30 @@ def test_device_build_falls_back_to_the_host_for_the_reference_panic(rtc):
         with pytest.raises(rtc.RtcError) as e:
             cam.render(w)
         assert e.value.code == rtc.RTC_ERR_PANIC and "bounds.rs:143" in e.value.message
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(3))
+def test_random_triangle_soups_under_both_builds(rtc, oracle, seed):
+    """Glass and mirror triangle soups with duplicate and degenerate triangles (worldgen.random_soup_world): the host SAH
+    scene and the device-built scene render the same frame with the same ray counts, which is the oracle's."""
+    import worldgen
+    w, c = worldgen.random_soup_world(rtc.api(), seed, 160, 112)
+    world = rtc.World(_handle=w.h)
+    w.h = None
+    cam = rtc.Camera.__new__(rtc.Camera)
+    cam.api, cam.hsize, cam.vsize, cam.field_of_view, cam.h = c.api, c.hsize, c.vsize, c.field_of_view, c.h
+    c.h = None
+    ow, oc = worldgen.random_soup_world(oracle, seed, 160, 112)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    frames = []
+    for build in ("host", "device"):
+        world.set_build(build)
+        st = rtc.Stats()
+        rgba = np.zeros((112, 160, 4), dtype=np.uint8)
+        rgb = np.zeros((112, 160, 3))
+        cam.render_into(world, rgba8=rgba, rgb_f64=rgb, stats=st)
+        _check(ref, rgb.reshape(-1, 3), oracle.quantise_rgba8(ref), rgba.reshape(-1, 4))
+        assert st.total_rays == cnt.total_rays
+        frames.append(rgb)
+    assert np.array_equal(frames[0].view(np.uint64), frames[1].view(np.uint64))

@@ -168,3 +168,19 @@ def test_device_gate_fold_leaves_the_panic_to_the_host_build(rtc, hostsim):
     assert scene.bvh_depth >= 1 << 20          # the simulated device build says "rebuild on the host"
     with pytest.raises(RuntimeError, match="bounds.rs:143"):
         hostsim.scene(w)                        # ... and the host build panics like the reference
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_triangle_soups_bit_exact_under_both_builds(rtc, oracle, hostsim, seed):
+    """Glass and mirror triangle soups with duplicate and degenerate triangles: the host SAH build and the simulated
+    device build visit triangles in different orders and must both give the oracle's frame and ray counts."""
+    world, cam = _wrap(rtc, *worldgen.random_soup_world(rtc.api(), seed))
+    ow, oc = worldgen.random_soup_world(oracle, seed)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    for device_build in (False, True):
+        scene = hostsim.scene(world, device_build=device_build)
+        rgb, _, scnt = scene.render(cam)
+        assert _bits_equal(ref, rgb), f"seed {seed} device_build={device_build}: " \
+                                      f"{np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
+        assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+        assert cnt.refract > 0

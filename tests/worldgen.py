@@ -130,3 +130,66 @@ def random_world(api, seed, hsize=48, vsize=32, nobjects=10, groups=True):
             leaf.material = _rand_material(T, rng)
             world.push(leaf)
     return world, cam
+
+
+def random_soup_world(api, seed, hsize=40, vsize=28):
+    """-> (world, camera).  Triangle soups big enough for the device mesh build (>= 256 triangles each): a lumpy closed
+    shell with shared vertices and edges, exact duplicates of some of its triangles (equal-t hits: the tie goes to the
+    lower DFS leaf whatever order a BVH visits them in), slivers, one soup of glass (the n1/n2 container walk crosses
+    every triangle up to the hit), reflective floor, a few primitives in front and behind."""
+    rng = np.random.default_rng(1000 + seed)
+    T, S = sa.Transformations(api), sa.Shapes(api)
+    cam = sa.CameraHandle(api, hsize, vsize, rng.uniform(0.7, 1.0))
+    cam.set_transform(T.view_transform((rng.uniform(-2, 2), rng.uniform(1, 3), -7.0), (0.0, 0.3, 0.0), (0.0, 1.0, 0.0)))
+    world = sa.WorldHandle(api, sa.Light((rng.uniform(-5, 5), 7.0, -6.0), (1.0, 1.0, 0.95)))
+
+    floor = S.plane()
+    floor.set_transform(T.translation(0, -1.6, 0))
+    fm = sa.Material()
+    fm.reflective = 0.35
+    fm.pattern = sa.Pattern.checkers((0.2, 0.2, 0.2), (0.9, 0.9, 0.9))
+    floor.material = fm
+    world.push(floor)
+
+    def shell(nu, nv, radius, lump):
+        us = np.linspace(0, 2 * math.pi, nu, endpoint=False)
+        vs = np.linspace(0.15, math.pi - 0.15, nv)
+        verts = []
+        for v in vs:
+            for u in us:
+                r = radius * (1 + lump * math.sin(3 * u) * math.sin(2 * v))
+                verts.append((r * math.sin(v) * math.cos(u), r * math.cos(v), r * math.sin(v) * math.sin(u)))
+        faces = []
+        for j in range(nv - 1):
+            for i in range(nu):
+                a, b = j * nu + i, j * nu + (i + 1) % nu
+                c, d = a + nu, b + nu
+                faces += [(a + 1, b + 1, c + 1), (b + 1, d + 1, c + 1)]
+        return np.array(verts, dtype=np.float64), np.array(faces, dtype=np.int32)
+
+    for k in range(2):
+        v, f = shell(int(rng.integers(12, 18)), int(rng.integers(10, 14)), rng.uniform(0.8, 1.3), rng.uniform(0.0, 0.3))
+        v = v + rng.normal(0, 0.01, v.shape)
+        dup = f[rng.integers(0, len(f), 24)]                       # exact duplicates of existing triangles
+        sliver = f[rng.integers(0, len(f), 8)].copy()
+        sliver[:, 2] = sliver[:, 1]                                 # degenerate (zero-area) triangles
+        f = np.concatenate([f, dup, sliver]).astype(np.int32)
+        g = S.mesh(v, f)
+        m = sa.Material()
+        m.color = tuple(rng.uniform(0.2, 1.0, 3))
+        if k == 0:
+            m.transparency, m.refractive_index, m.reflective = 0.8, 1.5, 0.3
+            m.diffuse, m.ambient = 0.2, 0.05
+        else:
+            m.reflective = rng.uniform(0.0, 0.5)
+        g.set_material(m)
+        g.set_transform(T.translation(-1.4 + 2.8 * k, rng.uniform(-0.2, 0.4), rng.uniform(-0.5, 0.5)) *
+                        T.rotation_y(rng.uniform(0, 3)) * T.scaling(1.0, rng.uniform(0.7, 1.2), 1.0))
+        world.push(g)
+
+    for _ in range(3):
+        leaf, _k = _rand_leaf(S, T, rng, force_capped=True)
+        leaf.set_transform(_rand_transform(T, rng, scale=(0.3, 0.7), spread=2.5))
+        leaf.material = _rand_material(T, rng)
+        world.push(leaf)
+    return world, cam
