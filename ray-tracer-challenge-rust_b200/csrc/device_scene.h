@@ -32,7 +32,8 @@ struct DXform {
 // reject: 0 = always run the exact test; 1 = a ray that misses the padded world box [blo,bhi] cannot intersect the
 // leaf; 2 = same, but valid only when every object-space direction component is clearly >= EPSILON (the cube's
 // check_axis treats smaller ones as parallel, shape.rs:593-599), decided in f32 with m32 (rows of the inverse's 3x3) and
-// the per-row rounding slack k.
+// the per-row rounding slack k; 3 = a cube whose inverse's 3x3 is diagonal: the same decision from m32[0..2] (the diagonal)
+// with one product per axis.
 struct alignas(16) DPrim {
     int32_t kind, material, xform, capped;
     double minimum, maximum;

@@ -32,6 +32,7 @@ struct FlattenError {
 
 struct FlattenOptions {
     bool device_mesh_build = false;  // leave meshes of >= kDeviceBuildMin triangles to the device build (lbvh.cuh)
+    bool diagonal_cubes = false;     // reject mode 3 for cubes without rotation or shear (one product per axis)
 };
 constexpr uint32_t kDeviceBuildMin = 256;
 
@@ -296,14 +297,23 @@ class Flattener {
             out_.reject_extent = std::fmax(out_.reject_extent, std::fmax(std::fabs(p.blo[a]), std::fabs(p.bhi[a])));
         }
         p.reject = (s.kind == RTC_CUBE) ? 2 : 1;
+        bool diagonal = true;
         for (int a = 0; a < 3; a++) {
             double l1 = 0.;
             for (int c = 0; c < 3; c++) {
                 p.m32[a * 3 + c] = (float)td.inverse[a * 4 + c];
                 l1 += std::fabs(td.inverse[a * 4 + c]);
+                if (a != c && td.inverse[a * 4 + c] != 0.0) diagonal = false;
             }
             // |f32 dot - exact dot| <= ~4 * 2^-24 * l1 * max|d|; k carries an 8x margin on top (2^-19)
             p.k[a] = f32_above_(l1 * 1.9073486328125e-06);
+        }
+        if (opts_.diagonal_cubes && s.kind == RTC_CUBE && diagonal) {
+            // object-space direction component a is inverse[a][a] * d[a] exactly: the same bound with a single product
+            p.reject = 3;
+            const float d0 = p.m32[0], d1 = p.m32[4], d2 = p.m32[8];
+            for (int c = 0; c < 9; c++) p.m32[c] = 0.f;
+            p.m32[0] = d0; p.m32[1] = d1; p.m32[2] = d2;
         }
     }
 

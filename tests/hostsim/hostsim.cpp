@@ -34,7 +34,8 @@ int sim_scene_create_ex(const rtc_scene_desc* desc, int device_build, void** out
     Sim* s = new Sim();
     std::string e;
     FlattenOptions opts;
-    opts.device_mesh_build = device_build != 0;
+    opts.device_mesh_build = (device_build & 1) != 0;
+    opts.diagonal_cubes = (device_build & 2) != 0;  // bit 1: reject mode 3 for axis-aligned cubes
     int rc = flatten_scene(*desc, s->flat, &e, opts);
     if (rc != RTC_OK) {
         g_err = e;
@@ -42,7 +43,7 @@ int sim_scene_create_ex(const rtc_scene_desc* desc, int device_build, void** out
         return rc;
     }
     const int depth = lbvh_build_sim(s->flat);
-    if (depth_out) *depth_out = device_build ? depth : s->flat.bvh_max_depth;
+    if (depth_out) *depth_out = (device_build & 1) ? depth : s->flat.bvh_max_depth;
     DScene& v = s->view;
     v.program = s->flat.program.data();
     v.xforms = s->flat.xforms.data();

@@ -184,3 +184,25 @@ def test_random_triangle_soups_bit_exact_under_both_builds(rtc, oracle, hostsim,
                                       f"{np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
         assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
         assert cnt.refract > 0
+
+
+@pytest.mark.parametrize("name,w,h", [("table", 160, 90), ("hexagon", 100, 50)])
+def test_diagonal_cube_precheck_bit_exact(rtc, oracle, hostsim, name, w, h):
+    """Reject mode 3 (cubes without rotation or shear decide the EPSILON pre-check with one product per axis) — an
+    experiment switch (RTC_B200_DIAG_CUBE) — must not change a pixel or a ray count."""
+    world, cam = rtc.build_scene(name, w, h)
+    ow, oc = helpers.scenes.build(oracle, name, w, h)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    rgb, _, scnt = hostsim.scene(world, diagonal_cubes=True).render(cam)
+    assert _bits_equal(ref, rgb)
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_worlds_bit_exact_with_diagonal_cubes(rtc, oracle, hostsim, seed):
+    world, cam = _wrap(rtc, *worldgen.random_world(rtc.api(), seed))
+    ow, oc = worldgen.random_world(oracle, seed)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    rgb, _, scnt = hostsim.scene(world, diagonal_cubes=True).render(cam)
+    assert _bits_equal(ref, rgb), f"seed {seed}: {np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
