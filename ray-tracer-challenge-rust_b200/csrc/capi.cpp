@@ -162,8 +162,8 @@ int rtc_scene_create_ex(const rtc_scene_desc* desc, int device, uint32_t flags, 
         std::string e;
         FlattenOptions opts;
         opts.device_mesh_build = (flags & RTC_BUILD_DEVICE_LBVH) && attempt == 0;
-        static const bool diag = std::getenv("RTC_B200_DIAG_CUBE") != nullptr;  // experiment switch
-        opts.diagonal_cubes = diag;
+        static const bool no_diag = std::getenv("RTC_B200_NO_DIAG_CUBE") != nullptr;  // A/B switch (profiles/r01r)
+        opts.diagonal_cubes = !no_diag;
         // the device build's input arrays are megabytes: keep their pages across calls on this thread instead of
         // faulting fresh ones in every time (a third of the gather time of a 10 k-triangle mesh)
         thread_local std::vector<rtc_triangle_desc> keep_tri;

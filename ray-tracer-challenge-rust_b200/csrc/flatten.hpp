@@ -32,7 +32,7 @@ struct FlattenError {
 
 struct FlattenOptions {
     bool device_mesh_build = false;  // leave meshes of >= kDeviceBuildMin triangles to the device build (lbvh.cuh)
-    bool diagonal_cubes = false;     // reject mode 3 for cubes without rotation or shear (one product per axis)
+    bool diagonal_cubes = true;      // reject mode 3 for cubes without rotation or shear (one product per axis)
 };
 constexpr uint32_t kDeviceBuildMin = 256;
 

@@ -35,7 +35,7 @@ int sim_scene_create_ex(const rtc_scene_desc* desc, int device_build, void** out
     std::string e;
     FlattenOptions opts;
     opts.device_mesh_build = (device_build & 1) != 0;
-    opts.diagonal_cubes = (device_build & 2) != 0;  // bit 1: reject mode 3 for axis-aligned cubes
+    opts.diagonal_cubes = (device_build & 2) == 0;  // bit 1: turn reject mode 3 (axis-aligned cubes) OFF
     int rc = flatten_scene(*desc, s->flat, &e, opts);
     if (rc != RTC_OK) {
         g_err = e;

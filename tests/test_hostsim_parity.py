@@ -187,22 +187,22 @@ def test_random_triangle_soups_bit_exact_under_both_builds(rtc, oracle, hostsim,
 
 
 @pytest.mark.parametrize("name,w,h", [("table", 160, 90), ("hexagon", 100, 50)])
-def test_diagonal_cube_precheck_bit_exact(rtc, oracle, hostsim, name, w, h):
-    """Reject mode 3 (cubes without rotation or shear decide the EPSILON pre-check with one product per axis) — an
-    experiment switch (RTC_B200_DIAG_CUBE) — must not change a pixel or a ray count."""
+def test_general_cube_precheck_bit_exact(rtc, oracle, hostsim, name, w, h):
+    """With reject mode 3 switched off (RTC_B200_NO_DIAG_CUBE: every cube takes the nine-product EPSILON pre-check, as
+    rotated ones always do) not a pixel or a ray count changes."""
     world, cam = rtc.build_scene(name, w, h)
     ow, oc = helpers.scenes.build(oracle, name, w, h)
     ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
-    rgb, _, scnt = hostsim.scene(world, diagonal_cubes=True).render(cam)
+    rgb, _, scnt = hostsim.scene(world, diagonal_cubes=False).render(cam)
     assert _bits_equal(ref, rgb)
     assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
 
 
 @pytest.mark.parametrize("seed", range(12))
-def test_random_worlds_bit_exact_with_diagonal_cubes(rtc, oracle, hostsim, seed):
+def test_random_worlds_bit_exact_without_diagonal_cubes(rtc, oracle, hostsim, seed):
     world, cam = _wrap(rtc, *worldgen.random_world(rtc.api(), seed))
     ow, oc = worldgen.random_world(oracle, seed)
     ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
-    rgb, _, scnt = hostsim.scene(world, diagonal_cubes=True).render(cam)
+    rgb, _, scnt = hostsim.scene(world, diagonal_cubes=False).render(cam)
     assert _bits_equal(ref, rgb), f"seed {seed}: {np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
     assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
