@@ -206,3 +206,37 @@ def test_random_worlds_bit_exact_without_diagonal_cubes(rtc, oracle, hostsim, se
     rgb, _, scnt = hostsim.scene(world, diagonal_cubes=False).render(cam)
     assert _bits_equal(ref, rgb), f"seed {seed}: {np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
     assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+
+
+@pytest.mark.parametrize("ntri", [255, 256, 257, 511])
+def test_device_mesh_build_threshold_sizes(rtc, oracle, hostsim, ntri):
+    """Meshes just below and above the device build's threshold (256 triangles): below it the host builds the mesh even
+    when the device build is requested; the frames are the oracle's either way."""
+    rng = np.random.default_rng(ntri)
+    nv = ntri + 2
+    ang = np.linspace(0, 4 * np.pi, nv)
+    v = np.stack([np.cos(ang) * (1 + 0.2 * np.arange(nv) / nv), np.linspace(-1, 1, nv) + rng.normal(0, 0.02, nv),
+                  np.sin(ang) * (1 + 0.2 * np.arange(nv) / nv)], axis=1)
+    f = np.array([(i + 1, i + 2, i + 3) for i in range(ntri)], dtype=np.int32)  # a ribbon spiralling upwards
+
+    def build(api_like, mod):
+        Sx, Tx = mod.Shapes(api_like), mod.Transformations(api_like)
+        g = Sx.mesh(v, f)
+        g.set_transform(Tx.rotation_x(0.3))
+        w = mod.WorldHandle(api_like, mod.Light((2.0, 5.0, -5.0), (1.0, 1.0, 1.0)))
+        w.push(g)
+        cam = mod.CameraHandle(api_like, 40, 30, 0.9)
+        cam.set_transform(Tx.view_transform((0.0, 1.0, -5.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0)))
+        return w, cam
+
+    world, cam = _wrap(rtc, *build(rtc.api(), helpers.scenes))
+    ow, oc = build(oracle, helpers.scenes)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    host = hostsim.scene(world)
+    dev = hostsim.scene(world, device_build=True)
+    for scene in (host, dev):
+        rgb, _, scnt = scene.render(cam)
+        assert _bits_equal(ref, rgb)
+        assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+    same_tables = host.tables()[3] == dev.tables()[3]
+    assert same_tables == (ntri < 256)  # below the threshold the request is served by the host build
