@@ -124,8 +124,38 @@ struct ObjResult {
 
 namespace detail {
 inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\f' || c == '\v'; }
-// str::parse::<f64>: decimal/exponent forms, inf/infinity/nan; no hex floats, no trailing junk
-inline double parse_f64(const char* b, const char* e, const char* what, const std::string& line) {
+// [+-]digits[.digits], at most 15 digits in all, no exponent: the digit string as an integer and the power of ten are both
+// exact doubles, so one correctly rounded division gives the correctly rounded value (Clinger's fast path) — what
+// str::parse::<f64> and strtod return, without strtod's cost.  Anything else: false, the caller takes the general path.
+inline bool parse_f64_fast(const char* b, const char* e, double* out) {
+    static const double p10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+    const char* p = b;
+    bool neg = false;
+    if (p < e && (*p == '-' || *p == '+')) neg = *p++ == '-';
+    uint64_t m = 0;
+    int digits = 0, frac = 0;
+    bool dot = false;
+    for (; p < e; p++) {
+        if (*p >= '0' && *p <= '9') {
+            if (++digits > 15) return false;
+            m = m * 10 + (uint64_t)(*p - '0');
+            if (dot) frac++;
+        } else if (*p == '.' && !dot) {
+            dot = true;
+        } else {
+            return false;
+        }
+    }
+    if (digits == 0) return false;
+    const double v = frac ? (double)m / p10[frac] : (double)m;
+    *out = neg ? -v : v;
+    return true;
+}
+// str::parse::<f64>: decimal/exponent forms, inf/infinity/nan; no hex floats, no trailing junk.  (lb, le) is the line,
+// quoted in the panic message only.
+inline double parse_f64(const char* b, const char* e, const char* what, const char* lb, const char* le) {
+    double fast;
+    if (parse_f64_fast(b, e, &fast)) return fast;
     std::string tok(b, e);
     bool bad = tok.empty();
     for (char c : tok)
@@ -133,11 +163,11 @@ inline double parse_f64(const char* b, const char* e, const char* what, const st
     char* end = nullptr;
     double v = bad ? 0. : std::strtod(tok.c_str(), &end);
     if (bad || end != tok.c_str() + tok.size())
-        throw HostPanic(std::string("vertex ") + what + " should be an f64 in \"" + line + "\" (src/obj_file.rs:42-55)");
+        throw HostPanic(std::string("vertex ") + what + " should be an f64 in \"" + std::string(lb, le) + "\" (src/obj_file.rs:42-55)");
     return v;
 }
 // str::parse::<usize>: optional '+', then decimal digits only
-inline uint64_t parse_usize(const char* b, const char* e, const char* what, const std::string& line) {
+inline uint64_t parse_usize(const char* b, const char* e, const char* what, const char* lb, const char* le) {
     const char* p = b;
     if (p < e && *p == '+') p++;
     bool ok = p < e;
@@ -146,7 +176,7 @@ inline uint64_t parse_usize(const char* b, const char* e, const char* what, cons
         if (*p < '0' || *p > '9') { ok = false; break; }
         v = v * 10 + (uint64_t)(*p - '0');
     }
-    if (!ok) throw HostPanic(std::string("face ") + what + " should be a usize in \"" + line + "\" (src/obj_file.rs:57-74)");
+    if (!ok) throw HostPanic(std::string("face ") + what + " should be a usize in \"" + std::string(lb, le) + "\" (src/obj_file.rs:57-74)");
     return v;
 }
 }  // namespace detail
@@ -187,16 +217,16 @@ inline ObjResult obj_parse(const char* text, size_t len) {
             for (int k = 0; k < 3; k++) {
                 if (tok.size() < (size_t)k + 2)
                     throw HostPanic(std::string("vertex token to have a ") + names[k] + " in \"" + line() + "\"");
-                xyz[k] = detail::parse_f64(tok[k + 1].first, tok[k + 1].second, names[k], line());
+                xyz[k] = detail::parse_f64(tok[k + 1].first, tok[k + 1].second, names[k], lb, le);
             }
             verts.insert(verts.end(), xyz, xyz + 3);
         } else if (tl == 1 && *tok[0].first == 'f') {
             if (tok.size() < 2) throw HostPanic("face should have a v1 in \"" + line() + "\"");
-            uint64_t v1 = detail::parse_usize(tok[1].first, tok[1].second, "v1", line());
+            uint64_t v1 = detail::parse_usize(tok[1].first, tok[1].second, "v1", lb, le);
             if (tok.size() < 3) throw HostPanic("face should have a v2 in \"" + line() + "\"");
-            uint64_t v2 = detail::parse_usize(tok[2].first, tok[2].second, "v2", line());
+            uint64_t v2 = detail::parse_usize(tok[2].first, tok[2].second, "v2", lb, le);
             for (size_t k = 3; k < tok.size(); k++) {  // fan triangulation, obj_file.rs:70-94
-                uint64_t v3 = detail::parse_usize(tok[k].first, tok[k].second, "v3", line());
+                uint64_t v3 = detail::parse_usize(tok[k].first, tok[k].second, "v3", lb, le);
                 double p1[3], p2[3], p3[3];
                 vertex(v1, p1);
                 vertex(v2, p2);

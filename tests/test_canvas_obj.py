@@ -142,3 +142,48 @@ def test_obj_matches_mesh_from_arrays_and_oracle(rtc, oracle, hostsim, tmp_path)
     assert outs[0].any()
     for o in outs[1:]:
         assert np.array_equal(o.view(np.uint64), outs[0].view(np.uint64))
+
+
+def test_obj_numbers_are_correctly_rounded(rtc):
+    """Vertex coordinates parse like str::parse::<f64> (correctly rounded): the short-decimal fast path (<= 15 digits, no
+    exponent) and the general path (long mantissas, exponents, inf) both give Python's float() bit for bit."""
+    import ctypes as C
+    import importlib
+    capi = importlib.import_module("ray-tracer-challenge-rust_b200._capi")
+    rng = np.random.default_rng(11)
+    toks = ["0", "-0", "-0.000000", "+1", "1.", ".5", "-.25", "007.500", "123456789012345", "0.000000000000001",
+            "1234567.12345678", "9007199254740993", "0.1234567890123456789", "1e-3", "-2.5E+2", "1e22", "1e23",
+            "179769313486231570000000000000000000000", "4.9e-324", "inf", "-Infinity", "3.141592653589793"]
+    for _ in range(400):
+        nd = int(rng.integers(1, 19))
+        digits = "".join(str(int(d)) for d in rng.integers(0, 10, nd))
+        cut = int(rng.integers(0, nd + 1))
+        t = digits[:cut] + ("." + digits[cut:] if rng.random() < 0.8 else digits[cut:])
+        if t in (".", ""):
+            t = "1"
+        if rng.random() < 0.5:
+            t = "-" + t
+        if rng.random() < 0.1:
+            t += "e" + str(int(rng.integers(-30, 30)))
+        toks.append(t)
+    while len(toks) % 3:
+        toks.append("1")
+    lines = [f"v {toks[i]} {toks[i + 1]} {toks[i + 2]}" for i in range(0, len(toks), 3)]
+    nv = len(lines)
+    lines += [f"f {i + 1} {(i + 1) % nv + 1} {(i + 2) % nv + 1}" for i in range(nv)]
+    S = rtc.Shapes(rtc.api())
+    g = S.obj_str("\n".join(lines) + "\n")
+    w = rtc.World(rtc.Light((0, 0, 0), (1, 1, 1)))
+    w.push(g)
+    api = rtc.api()
+    m = C.c_void_p()
+    api.check(api.world_marshal(w.h, C.byref(m)))
+    try:
+        desc = C.cast(api.marshalled_desc(m), C.POINTER(capi.SceneDesc)).contents
+        assert desc.triangle_count == nv
+        for i in range(nv):  # triangle i starts at vertex i
+            got = np.array(list(desc.triangles[i].p1))
+            want = np.array([float(toks[3 * i]), float(toks[3 * i + 1]), float(toks[3 * i + 2])])
+            assert got.tobytes() == want.tobytes(), (lines[i], got, want)
+    finally:
+        api.marshalled_free(m)
