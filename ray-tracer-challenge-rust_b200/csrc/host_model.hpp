@@ -277,26 +277,31 @@ struct Bytes {
 struct Marshaller {
     Marshalled& m;
     std::map<Bytes, int32_t> xf, mat;
+    // the triangles of a mesh share one transform and one material: remember the last entry and compare bytes before
+    // building a map key (a 256-byte string per shape otherwise — most of the marshalling time of a 10 k-triangle world)
+    int32_t last_xf = -1, last_mat = -1;
     int32_t transform_id(const HShape* s) {
         rtc_transform_desc t;
         std::memcpy(t.transform, s->transform.m, sizeof(t.transform));
         std::memcpy(t.inverse, s->inverse.m, sizeof(t.inverse));
+        if (last_xf >= 0 && std::memcmp(&m.transforms[last_xf], &t, sizeof(t)) == 0) return last_xf;
         Bytes k{std::string((const char*)&t, sizeof(t))};
         auto it = xf.find(k);
-        if (it != xf.end()) return it->second;
+        if (it != xf.end()) return last_xf = it->second;
         int32_t id = (int32_t)m.transforms.size();
         m.transforms.push_back(t);
         xf.emplace(std::move(k), id);
-        return id;
+        return last_xf = id;
     }
     int32_t material_id(const rtc_material& mm) {
+        if (last_mat >= 0 && std::memcmp(&m.materials[last_mat], &mm, sizeof(mm)) == 0) return last_mat;
         Bytes k{std::string((const char*)&mm, sizeof(mm))};
         auto it = mat.find(k);
-        if (it != mat.end()) return it->second;
+        if (it != mat.end()) return last_mat = it->second;
         int32_t id = (int32_t)m.materials.size();
         m.materials.push_back(mm);
         mat.emplace(std::move(k), id);
-        return id;
+        return last_mat = id;
     }
     void walk(const HShape* s) {
         rtc_shape_desc d;
@@ -332,6 +337,10 @@ struct HWorld {  // world.rs:13-16
 
 inline void marshal_world(const HWorld& w, Marshalled& out) {
     detail::Marshaller mm{out, {}, {}};
+    size_t leaves = 0;
+    for (auto& o : w.objects) leaves += shape_leaf_count(o.get());
+    out.shapes.reserve(leaves + 16);
+    out.triangles.reserve(leaves);
     for (auto& o : w.objects) mm.walk(o.get());
     rtc_scene_desc& d = out.desc;
     d.shapes = out.shapes.data();
