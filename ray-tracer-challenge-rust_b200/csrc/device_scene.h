@@ -21,10 +21,10 @@ namespace rtc {
 enum : int32_t { NODE_GATE = 0, NODE_PRIM = 1, NODE_MESH = 2 };
 
 struct DProgramNode {
-    int32_t type;   // NODE_*
-    int32_t index;  // into gates / prims / meshes
-    int32_t skip;   // GATE: program index just past the group's subtree
-    int32_t pad;
+    int32_t type;    // NODE_*
+    int32_t index;   // into gates / prims / meshes
+    int32_t skip;    // GATE: program index just past the group's subtree
+    int32_t parent;  // program index of the enclosing GATE entry, -1 at World level (the class pass of the n1/n2 walk)
 };
 struct DXform {
     double m[12];  // inverse, rows 0..2
@@ -42,8 +42,10 @@ struct alignas(16) DPrim {
     float k[3];
     float m32[9];
     float blo[3], bhi[3];  // padded world box, f32 rounded outward (tested like a BVH box)
+    int32_t cls;           // >= 0: member of a class of value-equal leaves (shape.rs:638-646), see DClassMember
+    int32_t pad2[3];
 };
-static_assert(sizeof(DPrim) == 112, "DPrim layout: read with 16-byte loads");
+static_assert(sizeof(DPrim) == 128, "DPrim layout: read with 16-byte loads");
 struct DGate {
     double lo[3], hi[3];
 };
@@ -60,7 +62,15 @@ struct alignas(64) DBvhNode {
 struct alignas(16) DTri {
     double p1[3], e1[3], e2[3];
     int32_t leaf;
-    int32_t pad;
+    int32_t cls;  // >= 0: member of a class of value-equal leaves, else -1
+};
+// Leaves the reference's Shape equality (shape.rs:638-646: kind payload, transform and material, 1e-5 tolerance on
+// tuples / matrices / colours) cannot tell apart form a CLASS; the n1/n2 container walk (intersection.rs:29-62) treats a
+// class as ONE container.  Only classes of two or more leaves are listed: members of class c are
+// class_members[class_offsets[c] .. class_offsets[c + 1]).
+struct DClassMember {
+    int32_t node;  // program index of the member's PRIM entry, or of the MESH entry its triangle belongs to
+    int32_t slot;  // prims[] index, or tris[] slot
 };
 struct alignas(16) DTriAttr {
     double normal[3];
@@ -85,6 +95,10 @@ struct DScene {
     const DTri* tris;
     const DTriAttr* tri_attr;
     const DMaterial* materials;
+    const int32_t* class_offsets;
+    const DClassMember* class_members;
+    int32_t n_classes;
+    int32_t pad1;
     int32_t program_count;
     int32_t reject_prims;  // how many prims carry a reject box (0: the walker skips the per-ray set-up for them)
     float reject_extent;   // max |coordinate| over those boxes (f32 slab error bound)

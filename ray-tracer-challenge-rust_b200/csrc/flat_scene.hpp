@@ -37,6 +37,8 @@ struct FlatScene {
     std::vector<DTri> tris;
     std::vector<DTriAttr> tri_attr;
     std::vector<DMaterial> materials;
+    std::vector<int32_t> class_offsets;        // n_classes + 1 entries (empty: no class of value-equal leaves)
+    std::vector<DClassMember> class_members;
     double light_pos[3] = {0, 0, 0}, light_int[3] = {0, 0, 0};
     uint64_t leaf_count = 0;
     int32_t feature_mask = 0;  // bit k: leaves of ShapeKind k; 32 meshes; 64 gates; 128 a transparent material

@@ -10,9 +10,13 @@
 //
 // Compiled with -ffp-contract=off: gate boxes and triangle normals reach pixels.
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <map>
+#include <numeric>
 #include <string>
 #include <thread>
 #include <vector>
@@ -29,6 +33,10 @@ struct FlattenError {
     int code;
     std::string message;
 };
+
+// internal: a class of value-equal leaves reaches into a device-built mesh (triangle slots unknown on the host) — flatten
+// again with the host build
+constexpr int kFlattenNeedsHostBuild = -100;
 
 struct FlattenOptions {
     bool device_mesh_build = false;  // leave meshes of >= kDeviceBuildMin triangles to the device build (lbvh.cuh)
@@ -68,6 +76,8 @@ class Flattener {
             out_.light_pos[k] = d_.light_position[k];
             out_.light_int[k] = d_.light_intensity[k];
         }
+        for (const DMaterial& m : out_.materials)
+            if (m.transparency != 0.0) want_classes_ = true;
         clock.lap(out_.phase_ms, FlatScene::T_VALIDATE);
         emit_children(0, d_.shape_count);  // World.objects in order (world.rs:46-50)
         out_.leaf_count = next_leaf_;
@@ -83,6 +93,12 @@ class Flattener {
         if (!out_.gates.empty()) out_.feature_mask |= 64;
         for (const DMaterial& m : out_.materials)
             if (m.transparency != 0.0) out_.feature_mask |= 128;
+        // n1/n2 are only observable with a transparent material in the scene (world.rs:137-139): no classes otherwise
+        if (want_classes_) {
+            PhaseClock cc;
+            build_classes();
+            cc.lap(out_.phase_ms, FlatScene::T_VALIDATE);
+        }
     }
 
   private:
@@ -97,6 +113,15 @@ class Flattener {
     bool only_child_ = false;
     int group_depth_ = 0;        // 0 while emitting World.objects themselves
     int32_t pending_gate_ = -1;  // gate the next device-built mesh run folds (see device_gate_run)
+    int32_t gate_node_ = -1;     // program index of the GATE entry enclosing what is being emitted (-1: World level)
+    // where each DFS leaf went: its shape in the description, its program entry and its prims[] index / tris[] slot
+    // (slot -1: a triangle of a device-built mesh, placed by the device)
+    struct LeafSite {
+        uint32_t shape;
+        int32_t node, slot;
+    };
+    std::vector<LeafSite> sites_;
+    bool want_classes_ = false;  // some material is transparent: n1/n2 are observable (world.rs:137-139)
 
     [[noreturn]] static void fail(int code, const std::string& m) { throw FlattenError{code, m}; }
     static void check(bool c, const char* m) {
@@ -325,6 +350,121 @@ class Flattener {
         return n;
     }
 
+    // ---- classes of value-equal leaves (shape.rs:638-646) -------------------------------------------------------------
+    // Shape == compares kind (derived: payload included), transform and material; tuples, matrices and colours compare with
+    // is_almost_equal (|a - b| < 1e-5: utils.rs:4-6, tuple.rs:93-100, matrix.rs:174-185, color.rs:47-53), plain f64 fields
+    // exactly (material.rs:3, shape.rs:13).  prepare_computations finds its containers with it (intersection.rs:33,42).
+    static bool almost(double a, double b) { return std::fabs(a - b) < 0.00001; }
+    template <int N>
+    static bool almost_n(const double* a, const double* b) {
+        for (int k = 0; k < N; k++)
+            if (!almost(a[k], b[k])) return false;
+        return true;
+    }
+    static bool material_eq(const rtc_material& a, const rtc_material& b) {
+        if (!almost_n<3>(a.color, b.color)) return false;
+        if (!(a.ambient == b.ambient && a.diffuse == b.diffuse && a.specular == b.specular && a.shininess == b.shininess &&
+              a.reflective == b.reflective && a.transparency == b.transparency && a.refractive_index == b.refractive_index))
+            return false;
+        const bool pa = a.pattern_kind >= 0, pb = b.pattern_kind >= 0;
+        if (pa != pb) return false;
+        if (!pa) return true;
+        if (a.pattern_kind != b.pattern_kind) return false;
+        if (a.pattern_kind != RTC_PATTERN_TEST && !(almost_n<3>(a.pattern_a, b.pattern_a) && almost_n<3>(a.pattern_b, b.pattern_b)))
+            return false;
+        return almost_n<16>(a.pattern_transform, b.pattern_transform) && almost_n<16>(a.pattern_inverse, b.pattern_inverse);
+    }
+    bool leaf_eq(uint32_t ia, uint32_t ib) const {
+        const rtc_shape_desc& a = d_.shapes[ia];
+        const rtc_shape_desc& b = d_.shapes[ib];
+        if (a.kind != b.kind) return false;
+        if (a.kind == RTC_CYLINDER || a.kind == RTC_CONE) {
+            if (!(a.minimum == b.minimum && a.maximum == b.maximum && (a.capped != 0) == (b.capped != 0))) return false;
+        } else if (a.kind == RTC_TRIANGLE) {
+            const rtc_triangle_desc& x = d_.triangles[a.triangle];
+            const rtc_triangle_desc& y = d_.triangles[b.triangle];
+            if (!(almost_n<3>(x.p1, y.p1) && almost_n<3>(x.p2, y.p2) && almost_n<3>(x.p3, y.p3) && almost_n<3>(x.e1, y.e1) &&
+                  almost_n<3>(x.e2, y.e2) && almost_n<3>(x.normal, y.normal)))
+                return false;
+        }
+        if (a.transform != b.transform &&
+            !almost_n<16>(d_.transforms[a.transform].transform, d_.transforms[b.transform].transform))
+            return false;
+        return a.material == b.material || material_eq(d_.materials[a.material], d_.materials[b.material]);
+    }
+    // Equal leaves can only be found among leaves of one kind whose first compared coordinate (a triangle's p1.x, any other
+    // leaf's x translation) lies within 1e-5: sort by (kind, that coordinate) and compare inside the window.
+    void build_classes() {
+        const uint32_t n = (uint32_t)sites_.size();
+        if (n < 2) return;
+        std::vector<double> key(n);
+        std::vector<uint32_t> idx(n);
+        for (uint32_t l = 0; l < n; l++) {
+            const rtc_shape_desc& s = d_.shapes[sites_[l].shape];
+            const double c = s.kind == RTC_TRIANGLE ? d_.triangles[s.triangle].p1[0] : d_.transforms[s.transform].transform[3];
+            // kinds are 1e6 apart on the key axis only if coordinates are small; compare kinds explicitly in the window
+            key[l] = c;
+            idx[l] = l;
+        }
+        std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b] || (key[a] == key[b] && a < b); });
+        std::vector<uint32_t> parent(n);
+        std::iota(parent.begin(), parent.end(), 0u);
+        auto find = [&](uint32_t x) {
+            while (parent[x] != x) x = parent[x] = parent[parent[x]];
+            return x;
+        };
+        std::vector<std::pair<uint32_t, uint32_t>> edges;
+        for (uint32_t a = 0; a < n; a++) {
+            const uint32_t la = idx[a];
+            if (!(key[la] == key[la])) continue;  // NaN: equal to nothing, not even itself
+            for (uint32_t b = a + 1; b < n && key[idx[b]] - key[la] < 0.00001; b++) {
+                const uint32_t lb = idx[b];
+                if (leaf_eq(sites_[la].shape, sites_[lb].shape)) {
+                    edges.emplace_back(la, lb);
+                    const uint32_t ra = find(la), rb = find(lb);
+                    if (ra != rb) parent[ra < rb ? rb : ra] = ra < rb ? ra : rb;  // root = lowest leaf
+                }
+            }
+        }
+        if (edges.empty()) return;
+        // == must be an equivalence on this scene's leaves for "one container per class" to be what the reference's
+        // containers.position(|o| o == i.object) does; with a chain a == b == c, a != c the reference's answer depends on
+        // which of them happens to sit in the list — no fixed class structure reproduces that
+        std::vector<uint32_t> size(n, 0), links(n, 0);
+        for (uint32_t l = 0; l < n; l++) size[find(l)]++;
+        for (const auto& e : edges) links[find(e.first)]++;
+        for (uint32_t l = 0; l < n; l++)
+            if (size[l] > 1 && (uint64_t)links[l] * 2 != (uint64_t)size[l] * (size[l] - 1))
+                fail(RTC_ERR_UNSUPPORTED, "shapes that equal a common shape within 1e-5 but not each other (shape.rs:638-646): "
+                                          "the reference's n1/n2 for this world depend on intersection order");
+        std::vector<int32_t> cls(n, -1);
+        for (uint32_t l = 0; l < n; l++) {  // classes numbered by their lowest leaf; members in leaf order
+            const uint32_t r = find(l);
+            if (size[r] < 2) continue;
+            if (sites_[l].slot < 0) fail(kFlattenNeedsHostBuild, "a class of value-equal leaves inside a device-built mesh");
+            if (cls[r] < 0) {
+                cls[r] = (int32_t)out_.class_offsets.size();
+                out_.class_offsets.push_back(0);
+            }
+            cls[l] = cls[r];
+        }
+        const size_t nc = out_.class_offsets.size();
+        std::vector<int32_t> count(nc, 0);
+        for (uint32_t l = 0; l < n; l++)
+            if (cls[l] >= 0) count[cls[l]]++;
+        out_.class_offsets.assign(nc + 1, 0);
+        for (size_t c = 0; c < nc; c++) out_.class_offsets[c + 1] = out_.class_offsets[c] + count[c];
+        out_.class_members.resize(out_.class_offsets[nc]);
+        std::vector<int32_t> fill(out_.class_offsets.begin(), out_.class_offsets.end() - 1);
+        for (uint32_t l = 0; l < n; l++) {
+            if (cls[l] < 0) continue;
+            const LeafSite& st = sites_[l];
+            out_.class_members[fill[cls[l]]++] = DClassMember{st.node, st.slot};
+            if (out_.program[st.node].type == NODE_PRIM) out_.prims[st.slot].cls = cls[l];
+            else out_.tris[st.slot].cls = cls[l];
+        }
+    }
+
     // ---- emission ---------------------------------------------------------------------------------------------------
     bool same_inverse(uint32_t a, uint32_t b) const {
         return std::memcmp(d_.transforms[d_.shapes[a].transform].inverse, d_.transforms[d_.shapes[b].transform].inverse,
@@ -360,7 +500,9 @@ class Flattener {
                 // hexagon scene: 12 leaves in 6 two-leaf groups — boxes cost 12 %)
                 if (boxes_pay) reject_box(s, p);
                 if (p.reject) out_.reject_prims++;
-                out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, 0});
+                p.cls = -1;
+                if (want_classes_) sites_.push_back(LeafSite{i, (int32_t)out_.program.size(), (int32_t)out_.prims.size()});
+                out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, gate_node_});
                 out_.prims.push_back(p);
                 i++;
             }
@@ -402,14 +544,17 @@ class Flattener {
                     out_.merged_gates++;
                 }
                 const size_t at = out_.program.size();
-                out_.program.push_back(DProgramNode{NODE_GATE, (int32_t)out_.gates.size(), 0, 0});
+                out_.program.push_back(DProgramNode{NODE_GATE, (int32_t)out_.gates.size(), 0, gate_node_});
                 DGate zero;
                 std::memset(&zero, 0, sizeof(zero));
                 out_.gates.push_back(zero);
                 pending_gate_ = (int32_t)out_.gates.size() - 1;
+                const int32_t saved_node = gate_node_;
+                gate_node_ = (int32_t)at;
                 group_depth_++;
                 emit_children(g + 1, end_[g]);  // one run -> one pending mesh, which takes pending_gate_
                 group_depth_--;
+                gate_node_ = saved_node;
                 if (pending_gate_ != -1) fail(RTC_ERR_INVALID, "internal: device gate not taken by its mesh");
                 out_.program[at].skip = (int32_t)out_.program.size();
                 return;
@@ -437,17 +582,20 @@ class Flattener {
             return;
         }
         size_t at = out_.program.size();
-        out_.program.push_back(DProgramNode{NODE_GATE, (int32_t)out_.gates.size(), 0, 0});
+        out_.program.push_back(DProgramNode{NODE_GATE, (int32_t)out_.gates.size(), 0, gate_node_});
         out_.gates.push_back(g);
         const int32_t saved_parent = parent_gate_;
         const bool saved_only = only_child_;
+        const int32_t saved_node = gate_node_;
         parent_gate_ = (int32_t)out_.gates.size() - 1;
         only_child_ = (d_.shapes[i].child_count == 1);
+        gate_node_ = (int32_t)at;
         group_depth_++;
         emit_children(i + 1, end_[i]);
         group_depth_--;
         parent_gate_ = saved_parent;
         only_child_ = saved_only;
+        gate_node_ = saved_node;
         out_.program[at].skip = (int32_t)out_.program.size();
     }
 
@@ -492,7 +640,9 @@ class Flattener {
             m.extent = 0.f;
             m.pad[0] = m.pad[1] = m.pad[2] = 0;
             out_.pending.push_back(p);
-            out_.program.push_back(DProgramNode{NODE_MESH, (int32_t)out_.meshes.size(), 0, 0});
+            if (want_classes_)
+                for (uint32_t k = 0; k < n; k++) sites_.push_back(LeafSite{begin + k, (int32_t)out_.program.size(), -1});
+            out_.program.push_back(DProgramNode{NODE_MESH, (int32_t)out_.meshes.size(), 0, gate_node_});
             out_.meshes.push_back(m);
             clock.lap(out_.phase_ms, FlatScene::T_TRIANGLES);
             return;
@@ -560,10 +710,17 @@ class Flattener {
                 dt.e2[a] = t.e2[a];
             }
             dt.leaf = (int32_t)(leaf0 + k);
+            dt.cls = -1;
             out_.tri_attr[at + slot] = attr_in[k];
         }
+        if (want_classes_) {
+            const size_t s0 = sites_.size();
+            sites_.resize(s0 + n);
+            for (uint32_t slot = 0; slot < n; slot++)
+                sites_[s0 + order[slot]] = LeafSite{begin + order[slot], (int32_t)out_.program.size(), (int32_t)(at + slot)};
+        }
         clock.lap(out_.phase_ms, FlatScene::T_TRIANGLES);
-        out_.program.push_back(DProgramNode{NODE_MESH, (int32_t)out_.meshes.size(), 0, 0});
+        out_.program.push_back(DProgramNode{NODE_MESH, (int32_t)out_.meshes.size(), 0, gate_node_});
         out_.meshes.push_back(m);
     }
 };
@@ -577,6 +734,12 @@ inline int flatten_scene(const rtc_scene_desc& desc, FlatScene& out, std::string
         f.run();
         return RTC_OK;
     } catch (const FlattenError& e) {
+        if (e.code == kFlattenNeedsHostBuild && opts.device_mesh_build) {
+            FlattenOptions host = opts;
+            host.device_mesh_build = false;
+            out = FlatScene();
+            return flatten_scene(desc, out, err, host);
+        }
         if (err) *err = e.message;
         return e.code;
     }

@@ -285,7 +285,7 @@ LBVH_HD void fit(const Work& w, uint32_t slot) {
         dt.e2[a] = t.e2[a];
     }
     dt.leaf = w.leaf0 + (int32_t)k;
-    dt.pad = 0;
+    dt.cls = -1;  // scenes with value-equal leaves inside a device-built mesh are rebuilt on the host (flatten.hpp)
     w.tris[w.tri_base + slot] = dt;
     // normal_at for a triangle (shape.rs:509-518): invT * normal (w = 0), w = 0, normalize, w = 0, normalize — the sums
     // run left to right and include the w terms, as in flatten.hpp / host_math.hpp

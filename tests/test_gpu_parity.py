@@ -85,6 +85,28 @@ def test_random_worlds_match_oracle(rtc, oracle, seed):
         (cnt.primary, cnt.shadow, cnt.reflect, cnt.refract)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("build", ["host", "device"])
+def test_value_equal_shapes_are_one_container(rtc, oracle, variant, build):
+    """shape.rs:638-646 / intersection.rs:33,42 on the GPU: twin glass shapes around the camera are ONE container of the
+    n1/n2 walk (classes of value-equal leaves, flatten.hpp:build_classes); an identity comparison renders other pixels."""
+    import worldgen
+    w, c = worldgen.duplicate_glass_world(rtc.api(), variant)
+    world = rtc.World(_handle=w.h)
+    w.h = None
+    cam = rtc.Camera.__new__(rtc.Camera)
+    cam.api, cam.hsize, cam.vsize, cam.field_of_view, cam.h = c.api, c.hsize, c.vsize, c.field_of_view, c.h
+    c.h = None
+    world.set_build(build)
+    st = rtc.Stats()
+    canvas = cam.render(world, stats=st)
+    ow, oc = worldgen.duplicate_glass_world(oracle, variant)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    _check(ref, canvas.pixels_f64().reshape(-1, 3), oracle.quantise_rgba8(ref), canvas.pixels_rgba8())
+    assert (st.primary_rays, st.shadow_rays, st.reflect_rays, st.refract_rays) == \
+        (cnt.primary, cnt.shadow, cnt.reflect, cnt.refract)
+
+
 def test_default_world_known_answers(rtc):
     """camera.rs:145-155 and world.rs:212-260 through the CUDA path."""
     import math

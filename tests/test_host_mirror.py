@@ -272,3 +272,15 @@ def test_build_flags_are_validated_before_any_device_work(rtc):
         assert api.scene_create_ex(api.marshalled_desc(m), 0, 0x10, C.byref(out)) == rtc.RTC_ERR_INVALID
     finally:
         api.marshalled_free(m)
+
+
+def test_non_transitive_shape_equality_is_refused(rtc):
+    """Three glass spheres a == b == c, a != c (shape.rs:638-646 with its 1e-5 tolerance): the reference's n1/n2 then
+    depend on which of them sits in the container list; the library says so instead of guessing."""
+    import worldgen
+    w, _ = worldgen.chained_equal_world(rtc.api())
+    world = rtc.World(_handle=w.h)
+    w.h = None
+    with pytest.raises(rtc.RtcError) as e:
+        world.flatten_info()
+    assert e.value.code == rtc.RTC_ERR_UNSUPPORTED and "not each other" in e.value.message

@@ -240,3 +240,23 @@ def test_device_mesh_build_threshold_sizes(rtc, oracle, hostsim, ntri):
         assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
     same_tables = host.tables()[3] == dev.tables()[3]
     assert same_tables == (ntri < 256)  # below the threshold the request is served by the host build
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_value_equal_shapes_are_one_container(rtc, oracle, hostsim, variant):
+    """shape.rs:638-646 + intersection.rs:33,42: the container walk finds its containers by VALUE.  With the camera inside
+    twin glass shapes an identity comparison gets other n1/n2 (and other pixels); the flattener groups value-equal leaves
+    into classes and the walk toggles one container per class."""
+    world, cam = _wrap(rtc, *worldgen.duplicate_glass_world(rtc.api(), variant))
+    ow, oc = worldgen.duplicate_glass_world(oracle, variant)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    for device_build in (False, True):  # a class inside a device-built mesh sends the scene back to the host build
+        rgb, _, scnt = hostsim.scene(world, device_build=device_build).render(cam)
+        assert _bits_equal(ref, rgb), f"{np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
+        assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+
+
+def test_non_transitive_equality_is_refused(rtc, hostsim):
+    world, cam = _wrap(rtc, *worldgen.chained_equal_world(rtc.api()))
+    with pytest.raises(RuntimeError, match="not each other"):
+        hostsim.scene(world)

@@ -193,3 +193,86 @@ def random_soup_world(api, seed, hsize=40, vsize=28):
         leaf.material = _rand_material(T, rng)
         world.push(leaf)
     return world, cam
+
+
+def duplicate_glass_world(api, variant=0, hsize=64, vsize=48):
+    """-> (world, camera).  The camera sits INSIDE shapes that the reference's Shape equality (shape.rs:638-646: kind,
+    transform and material, 1e-5 tolerance) cannot tell apart, so the n1/n2 container walk of prepare_computations
+    (intersection.rs:29-62) toggles ONE container where an identity comparison would see two:
+      variant 0  two bit-identical glass spheres around the camera, a smaller glass sphere and a wall ahead
+      variant 1  the twins differ by 3e-6 in their transforms (equal within EPSILON, different bits), one of them sits in
+                 a group (behind a gate), plus twin glass cubes
+      variant 2  a glass mesh around the camera whose OBJ lists some faces twice (value-equal triangles in one run)
+    """
+    T, S = sa.Transformations(api), sa.Shapes(api)
+    cam = sa.CameraHandle(api, hsize, vsize, 1.0)
+    cam.set_transform(T.view_transform((0.1, 0.2, -0.6), (0.0, 0.1, 4.0), (0.0, 1.0, 0.0)))
+    world = sa.WorldHandle(api, sa.Light((-3.0, 5.0, -4.0), (1.0, 1.0, 0.9)))
+
+    wall = S.plane()
+    wall.set_transform(T.translation(0, 0, 6.0) * T.rotation_x(math.pi / 2))
+    wm = sa.Material()
+    wm.pattern = sa.Pattern.checkers((0.1, 0.1, 0.1), (0.9, 0.9, 0.9))
+    wall.material = wm
+    world.push(wall)
+
+    def glass(shape, index, reflective=0.3, transparency=0.9):
+        shape.material.transparency, shape.material.refractive_index = transparency, index
+        shape.material.reflective = reflective
+        shape.material.diffuse, shape.material.ambient = 0.1, 0.05
+        return shape
+
+    if variant == 0:
+        for _ in range(2):
+            s = glass(S.sphere(), 1.5)
+            s.set_transform(T.scaling(2.0, 2.0, 2.0))
+            world.push(s)
+        inner = glass(S.sphere(), 2.0)
+        inner.set_transform(T.translation(0.2, 0.1, 1.0) * T.scaling(0.5, 0.5, 0.5))
+        world.push(inner)
+    elif variant == 1:
+        a = glass(S.sphere(), 1.5)
+        a.set_transform(T.scaling(2.0, 2.0, 2.0))
+        world.push(a)
+        g = S.group()
+        b = glass(S.sphere(), 1.5)
+        b.set_transform(T.translation(3e-6, -2e-6, 0.0) * T.scaling(2.0, 2.0, 2.0))
+        g.push_shape(b)
+        other = S.sphere()
+        other.set_transform(T.translation(2.5, 0.0, 3.0))
+        g.push_shape(other)
+        world.push(g)
+        for k in range(2):
+            c = glass(S.cube(), 1.33, reflective=0.0)
+            c.set_transform(T.translation(0.0, 0.0, 0.5 + 1e-6 * k) * T.rotation_y(0.3) * T.scaling(1.2, 1.2, 1.2))
+            world.push(c)
+        third = glass(S.cube(), 2.4)
+        third.set_transform(T.translation(-0.3, 0.0, 1.4) * T.scaling(0.3, 0.3, 0.3))
+        world.push(third)
+    else:
+        v = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=np.float64) * 1.8
+        f = [[1, 3, 5], [3, 2, 5], [2, 4, 5], [4, 1, 5], [3, 1, 6], [2, 3, 6], [4, 2, 6], [1, 4, 6]]
+        f = np.array(f + [f[4], f[5], f[6], f[7], f[4]], dtype=np.int32)  # back faces twice, one of them three times
+        m = S.mesh(v, f)
+        gm = sa.Material()
+        gm.transparency, gm.refractive_index, gm.reflective, gm.diffuse, gm.ambient = 0.9, 1.5, 0.3, 0.1, 0.05
+        m.set_material(gm)
+        world.push(m)
+        inner = glass(S.sphere(), 2.0)
+        inner.set_transform(T.translation(0.0, 0.1, 0.9) * T.scaling(0.4, 0.4, 0.4))
+        world.push(inner)
+    return world, cam
+
+
+def chained_equal_world(api):
+    """Three glass spheres a == b == c but a != c (x translations 0, 8e-6, 1.6e-5): Shape equality is not an
+    equivalence here, so no class structure reproduces the reference's container walk — the library must refuse it."""
+    T, S = sa.Transformations(api), sa.Shapes(api)
+    cam = sa.CameraHandle(api, 8, 8, 1.0)
+    cam.set_transform(T.view_transform((0.0, 0.0, -5.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0)))
+    world = sa.WorldHandle(api, sa.Light((-3.0, 5.0, -4.0), (1.0, 1.0, 1.0)))
+    for k in range(3):
+        s = S.glass_sphere()
+        s.set_transform(T.translation(8e-6 * k, 0.0, 0.0))
+        world.push(s)
+    return world, cam
