@@ -168,6 +168,30 @@ uint32_t rtc_rows_count(const rtc_camera_desc* camera, const rtc_rows* rows);
 /* World::color_at (src/world.rs:80-82) for `n` explicit rays (origin xyz, direction xyz; host pointers) -> rgb f64. */
 int rtc_color_at(const rtc_scene* scene, const double* rays, uint64_t n, double* rgb_out);
 
+/* Probes of the per-ray program, so the reference's own unit tests can be asked of the CUDA path (never on a frame's
+ * path).  A leaf is named by its index in the pre-order walk of the World's leaves (groups do not count).
+ *   rtc_intersect             World::intersect (src/world.rs:43-54): every intersection of each ray, in the order the
+ *                             reference's stable sorts leave them (t ascending; ties: pre-order of the leaves, then push
+ *                             order).  Ray i fills t_out / leaf_out [i*cap, i*cap + min(counts[i], cap)); counts[i] is the
+ *                             number found, which may exceed cap.
+ *   rtc_prepare_computations  Intersection::hit (src/intersection.rs:79-83) then prepare_computations
+ *                             (src/intersection.rs:17-77) and Computations::schlick (:107-128) for the hit of each ray.
+ *   rtc_normal_at             Shape::normal_at (src/shape.rs:466-519) of one leaf at n world points. */
+typedef struct rtc_computations {
+    int32_t hit;    /* 0: no intersection with t >= 0 (everything else is zero) */
+    int32_t leaf;   /* Computations.object */
+    int32_t inside;
+    int32_t _pad;
+    double t;
+    double point[3], eyev[3], normalv[3], reflectv[3], over_point[3], under_point[3];
+    double n1, n2;
+    double reflectance;
+} rtc_computations;
+int rtc_intersect(const rtc_scene* scene, const double* rays, uint64_t n, uint32_t cap, double* t_out, int32_t* leaf_out,
+                  uint32_t* counts);
+int rtc_prepare_computations(const rtc_scene* scene, const double* rays, uint64_t n, rtc_computations* out);
+int rtc_normal_at(const rtc_scene* scene, int32_t leaf, const double* points, uint64_t n, double* normals_out);
+
 /* Work tallies of one frame for the FP64 roofline: renders the rows with a counting build of the same per-ray program
  * (nothing is stored or timed) and fills counts[rtc_tally_count()] — how many ray transforms, gate tests, leaf tests by
  * kind, triangle tests by outcome, BVH box tests, shaded hits, pattern evaluations, pow calls, refraction set-ups,

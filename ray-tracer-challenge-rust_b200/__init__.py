@@ -123,6 +123,35 @@ class World(WorldHandle):
         self.api.check(self.api.world_color_at(self.h, dptr(r), r.shape[0], dptr(out)))
         return out
 
+    def intersect(self, rays, cap=16, device=0):
+        """World::intersect (world.rs:43-54) per ray -> list of [(t, leaf), ...] in the reference's sorted order."""
+        r = as_f64(rays).reshape(-1, 6)
+        n = r.shape[0]
+        t = np.empty((n, cap))
+        leaf = np.empty((n, cap), dtype=np.int32)
+        cnt = np.empty(n, dtype=np.uint32)
+        self.api.check(self.api.intersect(self.scene(device), dptr(r), n, cap, dptr(t),
+                                          leaf.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          cnt.ctypes.data_as(C.POINTER(C.c_uint32))))
+        if n and int(cnt.max()) > cap:
+            return self.intersect(rays, int(cnt.max()), device)
+        return [[(float(t[i, k]), int(leaf[i, k])) for k in range(int(cnt[i]))] for i in range(n)]
+
+    def prepare_computations(self, rays, device=0):
+        """Intersection::hit + prepare_computations + schlick (intersection.rs:17-128) for the hit of each ray."""
+        from ._capi import Computations
+        r = as_f64(rays).reshape(-1, 6)
+        out = (Computations * r.shape[0])()
+        self.api.check(self.api.prepare_computations(self.scene(device), dptr(r), r.shape[0], out))
+        return list(out)
+
+    def normal_at(self, leaf, points, device=0):
+        """Shape::normal_at (shape.rs:466-519) of the leaf-th leaf (pre-order) at world points -> (n, 3)."""
+        p = as_f64(points).reshape(-1, 3)
+        out = np.empty_like(p)
+        self.api.check(self.api.normal_at(self.scene(device), leaf, dptr(p), p.shape[0], dptr(out)))
+        return out
+
     def set_build(self, build):
         """Mesh build of this world's scene: "host" (binned SAH, the default — best for many frames of one scene) or
         "device" (linear BVH built on the GPU — best when a scene is built, rendered once and dropped)."""

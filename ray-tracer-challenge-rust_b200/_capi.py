@@ -49,6 +49,14 @@ class Stats(C.Structure):
         return self.primary_rays + self.shadow_rays + self.reflect_rays + self.refract_rays
 
 
+class Computations(C.Structure):
+    """rtc_computations == Computations (intersection.rs:88-100) + Computations::schlick of the hit of one ray"""
+    _fields_ = [("hit", C.c_int32), ("leaf", C.c_int32), ("inside", C.c_int32), ("_pad", C.c_int32), ("t", C.c_double),
+                ("point", C.c_double * 3), ("eyev", C.c_double * 3), ("normalv", C.c_double * 3),
+                ("reflectv", C.c_double * 3), ("over_point", C.c_double * 3), ("under_point", C.c_double * 3),
+                ("n1", C.c_double), ("n2", C.c_double), ("reflectance", C.c_double)]
+
+
 def as_f64(a, n=None):
     a = np.ascontiguousarray(a, dtype=np.float64)
     if n is not None and a.size != n:

@@ -2,7 +2,7 @@
 import ctypes as C
 import os
 
-from ._capi import BuilderApi, CameraDesc, Material, Rows, Stats, c_double_p, c_u64_p
+from ._capi import BuilderApi, CameraDesc, Computations, Material, Rows, Stats, c_double_p, c_u64_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 # RTC_B200_LIB selects a tuning variant built by tools/tune_variants.py (same sources, other launch shape)
@@ -56,6 +56,10 @@ class RtcApi(BuilderApi):
         f("render_device", C.c_int, vp, C.POINTER(CameraDesc), C.POINTER(Rows), vp, vp, vp, C.c_int, C.POINTER(Stats))
         f("rows_count", C.c_uint32, C.POINTER(CameraDesc), C.POINTER(Rows))
         f("color_at", C.c_int, vp, c_double_p, C.c_uint64, c_double_p)
+        f("intersect", C.c_int, vp, c_double_p, C.c_uint64, C.c_uint32, c_double_p, C.POINTER(C.c_int32),
+          C.POINTER(C.c_uint32))
+        f("prepare_computations", C.c_int, vp, c_double_p, C.c_uint64, C.POINTER(Computations))
+        f("normal_at", C.c_int, vp, C.c_int32, c_double_p, C.c_uint64, c_double_p)
         f("measure_fp64_peak", C.c_int, C.c_int, c_double_p, c_double_p)
         f("world_color_at", C.c_int, vp, c_double_p, C.c_uint64, c_double_p)
         f("world_scene", C.c_int, vp, C.c_int, C.POINTER(vp))

@@ -89,7 +89,7 @@ def build(force=False, verbose=False, defines=(), out=None):
         # the CUDA translation units in parallel: management + small kernels, the tally build, and render_kernel once
         # per feature mask (csrc/render_launch.cuh RTC_RENDER_INSTANCES)
         jobs = [("render.o", ["render.cu"], dflags), ("render_tally.o", ["render_tally.cu"], []),
-                ("ppm_encode.o", ["ppm_encode.cu"], []), ("lbvh.o", ["lbvh.cu"], [])]
+                ("ppm_encode.o", ["ppm_encode.cu"], []), ("lbvh.o", ["lbvh.cu"], []), ("probe.o", ["probe.cu"], [])]
         for mask in _instance_masks():
             jobs.append((f"render_inst_{mask}.o", ["render_inst.cu"], dflags + [f"-DRTC_INST_MASK={mask}"]))
         from concurrent.futures import ThreadPoolExecutor

@@ -262,6 +262,29 @@ int rtc_color_at(const rtc_scene* scene, const double* rays, uint64_t n, double*
     return RTC_OK;
 }
 
+int rtc_intersect(const rtc_scene* scene, const double* rays, uint64_t n, uint32_t cap, double* t_out, int32_t* leaf_out,
+                  uint32_t* counts) {
+    if (!scene || (n && (!rays || !counts || (cap && (!t_out || !leaf_out))))) return set_err(RTC_ERR_INVALID, "null argument");
+    std::string e;
+    if (probe_intersect(scene->dev, rays, n, cap, t_out, leaf_out, counts, &e) != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+int rtc_prepare_computations(const rtc_scene* scene, const double* rays, uint64_t n, rtc_computations* out) {
+    if (!scene || (n && (!rays || !out))) return set_err(RTC_ERR_INVALID, "null argument");
+    std::string e;
+    if (probe_prepare(scene->dev, rays, n, out, &e) != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+int rtc_normal_at(const rtc_scene* scene, int32_t leaf, const double* points, uint64_t n, double* normals_out) {
+    if (!scene || (n && (!points || !normals_out))) return set_err(RTC_ERR_INVALID, "null argument");
+    if (leaf < 0 || (uint64_t)leaf >= scene->info[0]) return set_err(RTC_ERR_INVALID, "no such leaf");
+    std::string e;
+    const int rc = probe_normal_at(scene->dev, scene->info[3], leaf, points, n, normals_out, &e);
+    if (rc == -1) return set_err(RTC_ERR_INVALID, e);
+    if (rc != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+
 int rtc_tally_count(void) { return tally_count(); }
 int rtc_render_tally(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows, uint64_t* counts) {
     if (!scene || !camera || !counts) return set_err(RTC_ERR_INVALID, "null argument");

@@ -1,0 +1,215 @@
+// probe.cu — single-ray probes of the per-ray program, so the reference's own unit tests (shape.rs:692-1652,
+// intersection.rs:203-379, world.rs:200-209) can be asked of the CUDA path through the C ABI (include/rtc.h:
+// rtc_intersect, rtc_prepare_computations, rtc_normal_at).  Same device functions as the render kernel (rt_core.cuh,
+// every feature compiled in), sm_100a, -fmad=false.  Never on a frame's path.
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "../../include/rtc.h"
+#include "device_scene_impl.cuh"
+#include "render.cuh"
+#include "rt_core.cuh"
+
+namespace rtc {
+
+using namespace core;
+
+namespace {
+
+// World::intersect (world.rs:43-54): all intersections of one ray, then the reference's order — its stable sorts leave
+// (t ascending; equal t: DFS leaf order; within a leaf: push order).
+struct Collect {
+    double* t;
+    int32_t* leaf;
+    uint32_t cap, n;
+    __device__ void offer(const double* ts, int cnt, int32_t lf, int32_t, int32_t, int32_t) {
+        for (int k = 0; k < cnt; k++) {
+            if (n < cap) {
+                t[n] = ts[k];
+                leaf[n] = lf;
+            }
+            n++;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(64) intersect_kernel(const __grid_constant__ DScene s, const double* __restrict__ rays,
+                                                       uint64_t n, uint32_t cap, double* __restrict__ t_out,
+                                                       int32_t* __restrict__ leaf_out, uint32_t* __restrict__ counts) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Ray r{v3(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]), v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};
+    Collect c{t_out + i * cap, leaf_out + i * cap, cap, 0};
+    Tally tl;
+    all_hits_walk<FEAT_ALL>(s, r, RTC_INF, c, tl);
+    counts[i] = c.n;
+    const uint32_t m = c.n < cap ? c.n : cap;
+    for (uint32_t a = 1; a < m; a++) {  // stable insertion sort on (t, leaf)
+        const double ta = c.t[a];
+        const int32_t la = c.leaf[a];
+        uint32_t b = a;
+        while (b > 0 && (c.t[b - 1] > ta || (c.t[b - 1] == ta && c.leaf[b - 1] > la))) {
+            c.t[b] = c.t[b - 1];
+            c.leaf[b] = c.leaf[b - 1];
+            b--;
+        }
+        c.t[b] = ta;
+        c.leaf[b] = la;
+    }
+}
+
+// Intersection::hit (intersection.rs:79-83) + prepare_computations (intersection.rs:17-77) + Computations::schlick
+// (intersection.rs:107-128) for the hit of each ray.
+__global__ void __launch_bounds__(64) prepare_kernel(const __grid_constant__ DScene s, const double* __restrict__ rays,
+                                                     uint64_t n, rtc_computations* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Ray r{v3(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]), v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};
+    Tally tl;
+    Walk w = walk_closest();
+    scene_walk<FEAT_ALL>(s, r, w, tl);
+    rtc_computations o{};
+    o.leaf = -1;
+    if (w.type >= 0) {
+        o.hit = 1;
+        o.leaf = w.leaf;
+        o.t = w.upper;
+        // the un-flipped normal first: `inside` is normal_at . eyev < 0 (intersection.rs:22-25)
+        const V3 point = position(r, w.upper);
+        const V3 eyev = -r.d;
+        V3 nv = normal_at<FEAT_ALL>(s, w.type, w.index, point, tl);
+        o.inside = dot(nv, eyev) < 0.0 ? 1 : 0;
+        if (o.inside) nv = -nv;
+        const V3 reflectv = reflect(r.d, nv);
+        const V3 over = point + nv * kEps, under = point - nv * kEps;
+        double n1, n2;
+        refraction_indices<FEAT_ALL>(s, r, w.upper, w.leaf, w.type, w.index, n1, n2, tl);
+        o.n1 = n1;
+        o.n2 = n2;
+        o.reflectance = schlick(eyev, nv, n1, n2);
+        const V3 v[6] = {point, eyev, nv, reflectv, over, under};
+        double* dst[6] = {o.point, o.eyev, o.normalv, o.reflectv, o.over_point, o.under_point};
+        for (int k = 0; k < 6; k++) {
+            dst[k][0] = v[k].x;
+            dst[k][1] = v[k].y;
+            dst[k][2] = v[k].z;
+        }
+    }
+    out[i] = o;
+}
+
+// Shape::normal_at (shape.rs:466-519) of DFS leaf `leaf` at world points
+__global__ void __launch_bounds__(64) normal_kernel(const __grid_constant__ DScene s, int32_t type, int32_t index,
+                                                    const double* __restrict__ points, uint64_t n, double* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Tally tl;
+    const V3 nv = normal_at<FEAT_ALL>(s, type, index, v3(points[3 * i], points[3 * i + 1], points[3 * i + 2]), tl);
+    out[3 * i + 0] = nv.x;
+    out[3 * i + 1] = nv.y;
+    out[3 * i + 2] = nv.z;
+}
+
+// which table entry holds DFS leaf `leaf` (one thread; probes only)
+__global__ void find_leaf_kernel(const __grid_constant__ DScene s, uint32_t n_tris, int32_t leaf, int32_t* out) {
+    out[0] = out[1] = -1;
+    for (uint32_t k = 0; k < s.n_prims; k++)
+        if (s.prims[k].leaf == leaf) {
+            out[0] = NODE_PRIM;
+            out[1] = (int32_t)k;
+            return;
+        }
+    for (uint32_t k = 0; k < n_tris; k++)
+        if (s.tris[k].leaf == leaf) {
+            out[0] = NODE_MESH;
+            out[1] = (int32_t)k;
+            return;
+        }
+}
+
+struct Scratch {  // device buffers of one probe call, freed on every path out
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Scratch() {
+        for (void* q : p)
+            if (q) cudaFree(q);
+    }
+};
+#define PROBE_CUDA(call)                                   \
+    do {                                                   \
+        cudaError_t e_ = (call);                           \
+        if (e_ != cudaSuccess) {                           \
+            if (err) *err = cuda_err_string(#call, e_);    \
+            return -3;                                     \
+        }                                                  \
+    } while (0)
+unsigned blocks_for(uint64_t n) { return (unsigned)((n + 63) / 64); }
+
+}  // namespace
+
+int probe_intersect(DeviceScene* s, const double* rays, uint64_t n, uint32_t cap, double* t_out, int32_t* leaf_out,
+                    uint32_t* counts, std::string* err) {
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(s->mu());
+    PROBE_CUDA(cudaSetDevice(s->device));
+    Scratch d;
+    const size_t slots = (size_t)n * (cap ? cap : 1);
+    PROBE_CUDA(cudaMalloc(&d.p[0], n * 48));
+    PROBE_CUDA(cudaMalloc(&d.p[1], slots * 8));
+    PROBE_CUDA(cudaMalloc(&d.p[2], slots * 4));
+    PROBE_CUDA(cudaMalloc(&d.p[3], n * 4));
+    PROBE_CUDA(cudaMemcpyAsync(d.p[0], rays, n * 48, cudaMemcpyHostToDevice, s->stream));
+    intersect_kernel<<<blocks_for(n), 64, 0, s->stream>>>(s->view, (const double*)d.p[0], n, cap, (double*)d.p[1],
+                                                          (int32_t*)d.p[2], (uint32_t*)d.p[3]);
+    PROBE_CUDA(cudaGetLastError());
+    if (cap) {
+        PROBE_CUDA(cudaMemcpyAsync(t_out, d.p[1], slots * 8, cudaMemcpyDeviceToHost, s->stream));
+        PROBE_CUDA(cudaMemcpyAsync(leaf_out, d.p[2], slots * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    PROBE_CUDA(cudaMemcpyAsync(counts, d.p[3], n * 4, cudaMemcpyDeviceToHost, s->stream));
+    PROBE_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int probe_prepare(DeviceScene* s, const double* rays, uint64_t n, rtc_computations* out, std::string* err) {
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(s->mu());
+    PROBE_CUDA(cudaSetDevice(s->device));
+    Scratch d;
+    PROBE_CUDA(cudaMalloc(&d.p[0], n * 48));
+    PROBE_CUDA(cudaMalloc(&d.p[1], n * sizeof(rtc_computations)));
+    PROBE_CUDA(cudaMemcpyAsync(d.p[0], rays, n * 48, cudaMemcpyHostToDevice, s->stream));
+    prepare_kernel<<<blocks_for(n), 64, 0, s->stream>>>(s->view, (const double*)d.p[0], n, (rtc_computations*)d.p[1]);
+    PROBE_CUDA(cudaGetLastError());
+    PROBE_CUDA(cudaMemcpyAsync(out, d.p[1], n * sizeof(rtc_computations), cudaMemcpyDeviceToHost, s->stream));
+    PROBE_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int probe_normal_at(DeviceScene* s, uint64_t n_tris, int32_t leaf, const double* points, uint64_t n, double* out,
+                    std::string* err) {
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(s->mu());
+    PROBE_CUDA(cudaSetDevice(s->device));
+    Scratch d;
+    PROBE_CUDA(cudaMalloc(&d.p[0], n * 24));
+    PROBE_CUDA(cudaMalloc(&d.p[1], n * 24));
+    PROBE_CUDA(cudaMalloc(&d.p[2], 8));
+    find_leaf_kernel<<<1, 1, 0, s->stream>>>(s->view, (uint32_t)n_tris, leaf, (int32_t*)d.p[2]);
+    PROBE_CUDA(cudaGetLastError());
+    int32_t where[2] = {-1, -1};
+    PROBE_CUDA(cudaMemcpyAsync(where, d.p[2], 8, cudaMemcpyDeviceToHost, s->stream));
+    PROBE_CUDA(cudaStreamSynchronize(s->stream));
+    if (where[0] < 0) {
+        if (err) *err = "no such leaf";
+        return -1;
+    }
+    PROBE_CUDA(cudaMemcpyAsync(d.p[0], points, n * 24, cudaMemcpyHostToDevice, s->stream));
+    normal_kernel<<<blocks_for(n), 64, 0, s->stream>>>(s->view, where[0], where[1], (const double*)d.p[0], n, (double*)d.p[1]);
+    PROBE_CUDA(cudaGetLastError());
+    PROBE_CUDA(cudaMemcpyAsync(out, d.p[1], n * 24, cudaMemcpyDeviceToHost, s->stream));
+    PROBE_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+}  // namespace rtc

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <string>
 
+#include "../../include/rtc.h"
 #include "device_scene.h"
 
 namespace rtc {
@@ -42,6 +43,13 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* 
                 LaunchStats* stats, std::string* err);
 // World::color_at for explicit rays (host in, host out).
 int color_at_host(DeviceScene* s, const double* rays, uint64_t n, double* rgb, std::string* err);
+
+// Single-ray probes (probe.cu): World::intersect's sorted list, prepare_computations of the hit, Shape::normal_at.
+int probe_intersect(DeviceScene* s, const double* rays, uint64_t n, uint32_t cap, double* t_out, int32_t* leaf_out,
+                    uint32_t* counts, std::string* err);
+int probe_prepare(DeviceScene* s, const double* rays, uint64_t n, rtc_computations* out, std::string* err);
+int probe_normal_at(DeviceScene* s, uint64_t n_tris, int32_t leaf, const double* points, uint64_t n, double* out,
+                    std::string* err);
 
 // Work tallies of one frame (render_tally.cu): counts[tally_count()] in TallyIndex order (rt_core.cuh).
 int tally_count();
