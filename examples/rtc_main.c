@@ -195,7 +195,7 @@ int main(int argc, char** argv) {
 
     rtc_canvas* canvas = NULL;
     rtc_stats st;
-    OK(rtc_camera_render(c, w, 0, &canvas, &st)); /* camera.render(&world), camera.rs:67 — on the B200 */
+    OK(rtc_camera_render(c, w, 0, 0, &canvas, &st)); /* camera.render(&world), camera.rs:67 — on the B200 */
     uint64_t len = 0;
     char* ppm = rtc_canvas_to_ppm(canvas, &len); /* canvas.to_ppm(&mut file), canvas.rs:28 */
     FILE* f = fopen(filename, "wb");

@@ -37,7 +37,11 @@ extern "C" {
 #define RTC_ERR_UNSUPPORTED (-4)
 
 /* ShapeKind (src/shape.rs:14-39) */
-enum { RTC_SPHERE = 0, RTC_PLANE = 1, RTC_CUBE = 2, RTC_CYLINDER = 3, RTC_CONE = 4, RTC_GROUP = 5, RTC_TRIANGLE = 6 };
+enum { RTC_SPHERE = 0, RTC_PLANE = 1, RTC_CUBE = 2, RTC_CYLINDER = 3, RTC_CONE = 4, RTC_GROUP = 5, RTC_TRIANGLE = 6,
+       /* not in the reference (its smooth-triangle scenarios are commented out, src/intersection.rs:381-386,
+        * src/obj_file.rs:295-335): the book's SmoothTriangle — a triangle whose normal is interpolated from three vertex
+        * normals with the u, v of the hit */
+       RTC_SMOOTH_TRIANGLE = 7 };
 /* PatternKind (src/pattern.rs:4-12) */
 enum { RTC_PATTERN_NONE = -1, RTC_PATTERN_STRIPE = 0, RTC_PATTERN_GRADIENT = 1, RTC_PATTERN_RING = 2,
        RTC_PATTERN_CHECKERS = 3, RTC_PATTERN_TEST = 4 };
@@ -68,16 +72,21 @@ typedef struct rtc_triangle_desc {
     double p1[3], p2[3], p3[3], e1[3], e2[3], normal[3];
 } rtc_triangle_desc;
 
+/* Vertex normals of an RTC_SMOOTH_TRIANGLE (the book's smooth_triangle(p1, p2, p3, n1, n2, n3)). */
+typedef struct rtc_vertex_normals {
+    double n1[3], n2[3], n3[3];
+} rtc_vertex_normals;
+
 /* One Shape.  World.objects is sent as a pre-order walk: a group is followed by its `child_count` children, each
  * followed by its own subtree (src/shape.rs:28-30). */
 typedef struct rtc_shape_desc {
-    int32_t kind;        /* RTC_SPHERE .. RTC_TRIANGLE */
+    int32_t kind;        /* RTC_SPHERE .. RTC_SMOOTH_TRIANGLE */
     int32_t material;    /* leaves: index into materials[] */
     int32_t transform;   /* index into transforms[] (groups: their own, always identity in the reference) */
     int32_t capped;      /* cylinder / cone */
     double minimum, maximum;
     int32_t child_count; /* groups only */
-    int32_t triangle;    /* triangles: index into triangles[] */
+    int32_t triangle;    /* triangles: index into triangles[] (and vertex_normals[] for smooth triangles) */
 } rtc_shape_desc;
 
 /* World (src/world.rs:13-16) + Light (src/light.rs:5-8). */
@@ -93,6 +102,14 @@ typedef struct rtc_scene_desc {
     uint32_t triangle_count;
     double light_position[3];
     double light_intensity[3];
+    /* n1, n2, n3 of the RTC_SMOOTH_TRIANGLE shapes, indexed like triangles[] (triangle_count entries); may be NULL when
+     * the world holds no smooth triangle */
+    const rtc_vertex_normals* vertex_normals;
+    /* World's RECURSION_LIMIT (src/world.rs:11).  0 means the reference's value, 5.  The budget is spent three units per
+     * bounce (world.rs:95, :68-69, :126/:159), so 2-3 render surfaces only, 5-6 one bounce, 8-9 two bounces, ...; values
+     * with limit % 3 == 1 underflow the reference's usize arithmetic (world.rs:68) and are refused (RTC_ERR_PANIC). */
+    uint32_t recursion_limit;
+    uint32_t _reserved;
 } rtc_scene_desc;
 
 /* Camera (src/camera.rs:5-12): the values Camera::new / set_transform computed (camera.rs:16-46). */
@@ -161,6 +178,29 @@ int rtc_render(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_
  * stream).  `stats` (nullable) is filled only if `sync_stats` is non-zero, which synchronises the stream. */
 int rtc_render_device(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows,
                       void* d_rgba8_out, void* d_rgb_f64_out, void* cuda_stream, int sync_stats, rtc_stats* stats);
+
+/* ONE frame sharded over the devices 0 .. ngpus-1 of this process — no torch, no NCCL, plain CUDA: the scene is flattened
+ * once and uploaded to every device, the frame's 8-row bands are dealt cyclically to the devices (band b -> device b mod
+ * ngpus), every device renders its bands with one launch, and the frame is completed in one of two places:
+ *   RTC_MULTI_HOST_FRAME    one pinned host frame: every device copies its own bands into it with one strided copy over
+ *                           its own PCIe link, all links in parallel (rtc_multi_host_frame; also copied to rgba8_out when
+ *                           that is not NULL)
+ *   RTC_MULTI_DEVICE_FRAME  a frame in device 0's memory: the kernels of the other devices store their pixels straight
+ *                           into it over NVLink peer mappings — no gather step (rtc_multi_device_frame; rgba8_out must
+ *                           be NULL)
+ * stats: ray counts summed over the devices, kernel_launches = ngpus, device_ms = the slowest device's kernel.
+ * rtc_render_multi = create + render (host frame into rgba8_out) + destroy: the sharded Camera::render of a World that is
+ * rendered once. */
+typedef struct rtc_multi rtc_multi;
+#define RTC_MULTI_HOST_FRAME 0u
+#define RTC_MULTI_DEVICE_FRAME 1u
+int rtc_multi_create(const rtc_scene_desc* desc, int ngpus, uint32_t build_flags, rtc_multi** out);
+int rtc_multi_render(rtc_multi* m, const rtc_camera_desc* camera, uint32_t where, uint8_t* rgba8_out, rtc_stats* stats);
+const uint8_t* rtc_multi_host_frame(const rtc_multi* m);
+void* rtc_multi_device_frame(const rtc_multi* m);
+void rtc_multi_destroy(rtc_multi* m);
+int rtc_render_multi(const rtc_scene_desc* desc, const rtc_camera_desc* camera, int ngpus, uint32_t build_flags,
+                     uint8_t* rgba8_out, rtc_stats* stats);
 
 /* Number of frame rows a (camera, rows) selection renders = the row count of the compact output buffers. */
 uint32_t rtc_rows_count(const rtc_camera_desc* camera, const rtc_rows* rows);
@@ -265,8 +305,17 @@ void rtc_world_free(rtc_world* w);
 int rtc_world_push(rtc_world* w, rtc_shape* s); /* World.objects.push; consumes `s` */
 /* World::color_at for n rays on the GPU (uploads the world on first use; cached until the world changes). */
 int rtc_world_color_at(rtc_world* w, const double* rays, uint64_t n, double* rgb_out);
-/* The layer-1 scene handle this world marshals into (created on first use on `device`); owned by the world. */
+/* The layer-1 scene handle this world marshals into (created on first use on `device`, one per device); owned by the
+ * world and valid until the world changes (rtc_world_push, rtc_world_set_build, rtc_world_set_recursion_limit,
+ * rtc_world_drop_scenes, rtc_world_free).  Threading: every rtc_world_* call and rtc_camera_render hold the world's lock
+ * for their whole duration, so they may be called from several threads; a scene handle obtained here must not be used
+ * concurrently with a call that changes the world. */
 int rtc_world_scene(rtc_world* w, int device, rtc_scene** out);
+/* Drops the cached device scenes: the next render marshals, flattens and uploads the world again (what the patched
+ * Camera::render of the Rust host does on every call). */
+void rtc_world_drop_scenes(rtc_world* w);
+/* World's RECURSION_LIMIT (src/world.rs:11; see rtc_scene_desc.recursion_limit).  0 = the reference's 5. */
+int rtc_world_set_recursion_limit(rtc_world* w, uint32_t limit);
 /* Which mesh build rtc_world_scene / rtc_camera_render use for this world (RTC_BUILD_*; drops a scene built otherwise). */
 int rtc_world_set_build(rtc_world* w, uint32_t flags);
 
@@ -287,10 +336,10 @@ rtc_camera* rtc_camera_new(uint64_t hsize, uint64_t vsize, double field_of_view)
 void rtc_camera_free(rtc_camera* c);
 int rtc_camera_set_transform(rtc_camera* c, const double* m16);
 void rtc_camera_desc_get(const rtc_camera* c, rtc_camera_desc* out);
-/* camera.rs:67-79: Camera::render(&World) -> Canvas, on the GPU.  The canvas holds the f64 colours and the quantised
- * RGBA8 frame.  `want_f64` = 0 skips the 24-byte-per-pixel colour copy (get_pixel then fails) and keeps the RGBA8 frame
- * that to_ppm needs. */
-int rtc_camera_render(const rtc_camera* c, rtc_world* w, int want_f64, rtc_canvas** out, rtc_stats* stats);
+/* camera.rs:67-79: Camera::render(&World) -> Canvas, on GPU `device`.  The canvas holds the f64 colours and the quantised
+ * RGBA8 frame in pinned host memory (pooled: a freed canvas's buffers serve the next canvas of that size).  `want_f64` = 0
+ * skips the 24-byte-per-pixel colour copy (get_pixel then fails) and keeps the RGBA8 frame that to_ppm needs. */
+int rtc_camera_render(const rtc_camera* c, rtc_world* w, int device, int want_f64, rtc_canvas** out, rtc_stats* stats);
 
 /* canvas.rs:12-58 */
 rtc_canvas* rtc_canvas_new(uint64_t width, uint64_t height);

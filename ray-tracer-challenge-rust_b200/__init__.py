@@ -20,7 +20,7 @@ from .scene_api import (BLACK, BLUE, GREEN, RED, WHITE, CameraHandle, Light, Mat
                         Transformations, WorldHandle)
 
 __all__ = ["api", "World", "Camera", "Canvas", "Light", "Material", "Pattern", "Shapes", "Transformations", "Matrix",
-           "Rows", "Stats", "RtcError", "scenes", "device_count", "measure_fp64_peak", "ppm_from_rgba8", "ppm_from_device"]
+           "Rows", "Stats", "RtcError", "scenes", "device_count", "measure_fp64_peak", "ppm_from_rgba8", "ppm_from_device", "MultiRenderer", "render_multi"]
 
 
 def device_count():
@@ -158,6 +158,14 @@ class World(WorldHandle):
         flags = {"host": RTC_BUILD_HOST_SAH, "device": RTC_BUILD_DEVICE_LBVH}[build]
         self.api.check(self.api.world_set_build(self.h, flags))
 
+    def set_recursion_limit(self, limit):
+        """World's RECURSION_LIMIT (world.rs:11): 0 / 5 / 6 one bounce (the reference), 2-3 none, 8-9 two, ..."""
+        self.api.check(self.api.world_set_recursion_limit(self.h, int(limit)))
+
+    def drop_scenes(self):
+        """Forget the uploaded scenes: the next render marshals, flattens and uploads again."""
+        self.api.world_drop_scenes(self.h)
+
     def scene(self, device=0):
         """The layer-1 rtc_scene handle (flattened + uploaded on first use; owned by the world)."""
         s = C.c_void_p()
@@ -193,11 +201,11 @@ class Camera(CameraHandle):
         self.api.camera_desc_get(self.h, C.byref(d))
         return d
 
-    def render(self, world, want_f64=True, stats=None):
+    def render(self, world, want_f64=True, stats=None, device=0):
         """Camera::render(&World) -> Canvas.  `stats` (a Stats) receives ray counts and the kernel's device time."""
         out = C.c_void_p()
         st = stats if stats is not None else None
-        self.api.check(self.api.camera_render(self.h, world.h, int(bool(want_f64)), C.byref(out),
+        self.api.check(self.api.camera_render(self.h, world.h, device, int(bool(want_f64)), C.byref(out),
                                               C.byref(st) if st is not None else None))
         return Canvas(_handle=out)
 
@@ -226,6 +234,59 @@ class Camera(CameraHandle):
     def rows_count(self, rows=None):
         d = self.desc()
         return self.api.rows_count(C.byref(d), C.byref(rows) if rows is not None else None)
+
+
+class MultiRenderer:
+    """rtc_multi_*: one frame sharded over GPUs 0..ngpus-1 of THIS process (no torch, no NCCL).  where="host": every device
+    copies its own row bands into one pinned host frame over its own PCIe link; where="device": kernels store straight into
+    a frame on device 0 over NVLink peer mappings."""
+
+    def __init__(self, world, ngpus, build="host"):
+        self.api = api()
+        m = C.c_void_p()
+        self.api.check(self.api.world_marshal(world.h, C.byref(m)))
+        try:
+            self.h = C.c_void_p()
+            flags = {"host": RTC_BUILD_HOST_SAH, "device": RTC_BUILD_DEVICE_LBVH}[build]
+            self.api.check(self.api.multi_create(self.api.marshalled_desc(m), ngpus, flags, C.byref(self.h)))
+        finally:
+            self.api.marshalled_free(m)
+        self.ngpus = ngpus
+
+    def render(self, camera, where="host", stats=None, copy=True):
+        """-> (vsize, hsize, 4) uint8 numpy array (where="host": a copy of the pinned frame, or a view of it with
+        copy=False, valid until the next render) or the device-0 pointer of the frame (where="device")."""
+        d = camera.desc()
+        code = {"host": 0, "device": 1}[where]
+        self.api.check(self.api.multi_render(self.h, C.byref(d), code, None, C.byref(stats) if stats is not None else None))
+        if where == "device":
+            return self.api.multi_device_frame(self.h)
+        p = C.cast(self.api.multi_host_frame(self.h), C.POINTER(C.c_uint8))
+        a = np.ctypeslib.as_array(p, shape=(camera.vsize, camera.hsize, 4))
+        return a.copy() if copy else a
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.api.multi_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def render_multi(world, camera, ngpus, build="device", stats=None):
+    """rtc_render_multi: marshal, upload to every device, render sharded, frame to host, drop — one call."""
+    a = api()
+    m = C.c_void_p()
+    a.check(a.world_marshal(world.h, C.byref(m)))
+    try:
+        out = np.empty((camera.vsize, camera.hsize, 4), dtype=np.uint8)
+        d = camera.desc()
+        flags = {"host": RTC_BUILD_HOST_SAH, "device": RTC_BUILD_DEVICE_LBVH}[build]
+        a.check(a.render_multi(a.marshalled_desc(m), C.byref(d), ngpus, flags, out.ctypes.data_as(C.c_void_p),
+                               C.byref(stats) if stats is not None else None))
+        return out
+    finally:
+        a.marshalled_free(m)
 
 
 def build_scene(name, hsize=None, vsize=None):

@@ -132,6 +132,10 @@ class TriangleDesc(C.Structure):
                 ("e2", C.c_double * 3), ("normal", C.c_double * 3)]
 
 
+class VertexNormals(C.Structure):
+    _fields_ = [("n1", C.c_double * 3), ("n2", C.c_double * 3), ("n3", C.c_double * 3)]
+
+
 class ShapeDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("material", C.c_int32), ("transform", C.c_int32), ("capped", C.c_int32),
                 ("minimum", C.c_double), ("maximum", C.c_double), ("child_count", C.c_int32), ("triangle", C.c_int32)]
@@ -142,4 +146,5 @@ class SceneDesc(C.Structure):
                 ("transforms", C.POINTER(TransformDesc)), ("transform_count", C.c_uint32),
                 ("materials", C.POINTER(Material)), ("material_count", C.c_uint32),
                 ("triangles", C.POINTER(TriangleDesc)), ("triangle_count", C.c_uint32),
-                ("light_position", C.c_double * 3), ("light_intensity", C.c_double * 3)]
+                ("light_position", C.c_double * 3), ("light_intensity", C.c_double * 3),
+                ("vertex_normals", C.POINTER(VertexNormals)), ("recursion_limit", C.c_uint32), ("_reserved", C.c_uint32)]

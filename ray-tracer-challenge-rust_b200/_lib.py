@@ -54,6 +54,12 @@ class RtcApi(BuilderApi):
         f("scene_upload_bytes", C.c_uint64, vp)
         f("render", C.c_int, vp, C.POINTER(CameraDesc), C.POINTER(Rows), vp, vp, C.POINTER(Stats))
         f("render_device", C.c_int, vp, C.POINTER(CameraDesc), C.POINTER(Rows), vp, vp, vp, C.c_int, C.POINTER(Stats))
+        f("multi_create", C.c_int, vp, C.c_int, C.c_uint32, C.POINTER(vp))
+        f("multi_render", C.c_int, vp, C.POINTER(CameraDesc), C.c_uint32, vp, C.POINTER(Stats))
+        f("multi_host_frame", vp, vp)
+        f("multi_device_frame", vp, vp)
+        f("multi_destroy", None, vp)
+        f("render_multi", C.c_int, vp, C.POINTER(CameraDesc), C.c_int, C.c_uint32, vp, C.POINTER(Stats))
         f("rows_count", C.c_uint32, C.POINTER(CameraDesc), C.POINTER(Rows))
         f("color_at", C.c_int, vp, c_double_p, C.c_uint64, c_double_p)
         f("intersect", C.c_int, vp, c_double_p, C.c_uint64, C.c_uint32, c_double_p, C.POINTER(C.c_int32),
@@ -64,13 +70,15 @@ class RtcApi(BuilderApi):
         f("world_color_at", C.c_int, vp, c_double_p, C.c_uint64, c_double_p)
         f("world_scene", C.c_int, vp, C.c_int, C.POINTER(vp))
         f("world_set_build", C.c_int, vp, C.c_uint32)
+        f("world_set_recursion_limit", C.c_int, vp, C.c_uint32)
+        f("world_drop_scenes", None, vp)
         f("world_describe", C.c_int, vp, c_u64_p)
         f("world_flatten_info", C.c_int, vp, c_u64_p, c_double_p, C.c_uint64)
         f("world_marshal", C.c_int, vp, C.POINTER(vp))
         f("marshalled_desc", vp, vp)
         f("marshalled_free", None, vp)
         f("camera_desc_get", None, vp, C.POINTER(CameraDesc))
-        f("camera_render", C.c_int, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(Stats))
+        f("camera_render", C.c_int, vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(Stats))
         f("canvas_new", vp, C.c_uint64, C.c_uint64)
         f("canvas_free", None, vp)
         f("canvas_width", C.c_uint64, vp)

@@ -17,10 +17,35 @@ BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "librtc_b200.so")
 ROOT = os.path.dirname(HERE)
 
-HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fno-unsafe-math-optimizations", "-fPIC",
-              "-Wall", "-Wextra", "-Wno-unused-parameter"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
-              "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-Xptxas", "-v"]
+MANIFEST = os.path.join(CSRC, "manifest.txt")
+
+
+def read_manifest(path=MANIFEST):
+    """csrc/manifest.txt -> {"hostflags": [...], "nvccflags": [...], "link": [...], "units": [(kind, file, define)]}: the ONE
+    list of translation units, shared with rtc-sys/build.rs.  An `instances` line expands to one unit per feature mask."""
+    import re
+    m = {"hostflags": [], "nvccflags": [], "link": [], "units": []}
+    for line in open(path):
+        words = line.split()
+        if not words or words[0].startswith("#"):
+            continue
+        key = words[0]
+        if key in ("hostflags", "nvccflags"):
+            m[key] = words[1:]
+        elif key == "link":
+            m["link"] += words[1:]
+        elif key in ("host", "cuda"):
+            m["units"].append((key, words[1], None))
+        elif key == "instances":
+            file, macro, where = words[1:4]
+            header, listmacro = where.split(":")
+            text = open(os.path.join(os.path.dirname(path), header)).read()
+            entries = re.search(r"#define " + re.escape(listmacro) + r"\(X\)(.*)", text).group(1)
+            for mask in re.findall(r"X\((\d+)\)", entries):
+                m["units"].append(("cuda", file, f"{macro}={mask}"))
+        else:
+            raise RuntimeError(f"{path}: unknown directive {key}")
+    return m
 
 
 def _nvcc():
@@ -28,14 +53,6 @@ def _nvcc():
         if c and os.path.exists(c):
             return c
     raise RuntimeError("nvcc not found")
-
-
-def _instance_masks():
-    """The feature masks render_kernel is instantiated for (RTC_RENDER_INSTANCES in csrc/render_launch.cuh)."""
-    import re
-    text = open(os.path.join(CSRC, "render_launch.cuh")).read()
-    line = re.search(r"#define RTC_RENDER_INSTANCES\(X\)(.*)", text).group(1)
-    return [int(m) for m in re.findall(r"X\((\d+)\)", line)]
 
 
 def _sources():
@@ -84,28 +101,29 @@ def build(force=False, verbose=False, defines=(), out=None):
     os.makedirs(bdir, exist_ok=True)
     nvcc = _nvcc()
     dflags = ["-D" + d for d in defines]
+    man = read_manifest()
     with open(os.path.join(bdir, "build.log"), "w") as log:
-        _run(["g++", *HOST_FLAGS, *dflags, "-c", os.path.join(CSRC, "capi.cpp"), "-o", os.path.join(bdir, "capi.o")], log)
-        # the CUDA translation units in parallel: management + small kernels, the tally build, and render_kernel once
-        # per feature mask (csrc/render_launch.cuh RTC_RENDER_INSTANCES)
-        jobs = [("render.o", ["render.cu"], dflags), ("render_tally.o", ["render_tally.cu"], []),
-                ("ppm_encode.o", ["ppm_encode.cu"], []), ("lbvh.o", ["lbvh.cu"], []), ("probe.o", ["probe.cu"], [])]
-        for mask in _instance_masks():
-            jobs.append((f"render_inst_{mask}.o", ["render_inst.cu"], dflags + [f"-DRTC_INST_MASK={mask}"]))
+        # every translation unit of csrc/manifest.txt, in parallel: the host TU with g++, the CUDA TUs with nvcc
+        # (render_inst.cu once per feature mask)
+        jobs = []
+        for kind, file, define in man["units"]:
+            obj = file.replace(".", "_") + ("_" + define.split("=")[1] if define else "") + ".o"
+            flags = list(dflags) + (["-D" + define] if define else [])
+            jobs.append((obj, kind, file, flags))
         from concurrent.futures import ThreadPoolExecutor
         import io
 
         def compile_one(job):
-            obj, srcs, flags = job
+            obj, kind, file, flags = job
             buf = io.StringIO()
-            _run([nvcc, *NVCC_FLAGS, *flags, "-c", *[os.path.join(CSRC, s) for s in srcs], "-o",
-                  os.path.join(bdir, obj)], buf)
+            compiler = [nvcc, *man["nvccflags"]] if kind == "cuda" else ["g++", *man["hostflags"]]
+            _run([*compiler, *flags, "-c", os.path.join(CSRC, file), "-o", os.path.join(bdir, obj)], buf)
             return buf.getvalue()
 
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as pool:
             for text in pool.map(compile_one, jobs):
                 log.write(text)
-        _run([nvcc, "-shared", "-o", lib, os.path.join(bdir, "capi.o"), *[os.path.join(bdir, j[0]) for j in jobs]], log)
+        _run([nvcc, "-shared", *man["link"], "-o", lib, *[os.path.join(bdir, j[0]) for j in jobs]], log)
     if not out:
         with open(STAMP, "w") as f:
             f.write(_digest() + "\n")

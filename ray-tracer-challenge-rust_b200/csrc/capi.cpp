@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <map>
 #include <mutex>
 #include <sstream>
 
@@ -84,14 +85,18 @@ struct rtc_scene {
     DeviceScene* dev = nullptr;
     uint64_t info[6] = {0, 0, 0, 0, 0, 0};
 };
+struct rtc_multi {
+    MultiRenderer* m = nullptr;
+};
 struct rtc_shape {
     std::unique_ptr<HShape> s;
 };
 struct rtc_world {
     HWorld w;
-    rtc_scene* scene = nullptr;  // marshalled + uploaded on first use; dropped when the world changes
+    std::map<int, rtc_scene*> scenes;  // per device: marshalled + uploaded on first use; dropped when the world changes
     uint32_t build_flags = RTC_BUILD_HOST_SAH;
-    std::mutex mu;
+    uint32_t recursion_limit = 0;      // 0: the reference's RECURSION_LIMIT = 5 (world.rs:11)
+    std::mutex mu;                     // held for the whole of every world-level call (render, color_at, push, ...)
 };
 struct rtc_camera {
     HCamera c;
@@ -105,6 +110,59 @@ struct rtc_canvas {
     uint8_t* rgba8 = nullptr;  // the same pixels quantised as canvas.rs:61-63
     bool rgb_pinned = false, rgba_pinned = false;
 };
+
+// RTC_B200_TRACE=1: where the host time of a scene build went (stderr, one line per call)
+static void trace_phases(const char* who, const FlatScene& flat) {
+    static const bool trace = std::getenv("RTC_B200_TRACE") != nullptr;
+    if (!trace) return;
+    const double* t = flat.phase_ms;
+    std::fprintf(stderr, "[rtc] %s: validate %.3f  group bounds %.3f  bvh items %.3f / build %.3f / splice %.3f  "
+                         "triangle tables %.3f  upload %.3f ms (%zu triangles, %zu bvh nodes)\n",
+                 who, t[0], t[1], t[2], t[3], t[4], t[5], t[6], flat.tris.size() + flat.device_tris,
+                 flat.bvh.size() + flat.device_nodes);
+}
+
+// Flattens `desc` (validation, gate boxes, tables, host BVHs) and hands the result to `upload`; when the device mesh
+// build asks for it (a tree deeper than the traversal stack, a coordinate the reference panics on) the scene is flattened
+// again with the host build.  upload returns 0, kDeviceBuildTooDeep or another non-zero code with *e set.
+template <class Upload>
+static int flatten_and_upload(const rtc_scene_desc* desc, uint32_t flags, const char* who, Upload upload) {
+    for (int attempt = 0; attempt < 2; attempt++) {
+        FlatScene flat;
+        std::string e;
+        FlattenOptions opts;
+        opts.device_mesh_build = (flags & RTC_BUILD_DEVICE_LBVH) && attempt == 0;
+        static const bool no_diag = std::getenv("RTC_B200_NO_DIAG_CUBE") != nullptr;  // A/B switch (profiles/r01r)
+        opts.diagonal_cubes = !no_diag;
+        // the device build's input arrays are megabytes: keep their pages across calls on this thread instead of
+        // faulting fresh ones in every time (a third of the gather time of a 10 k-triangle mesh)
+        thread_local std::vector<rtc_triangle_desc> keep_tri;
+        thread_local std::vector<int32_t> keep_mat;
+        struct Lend {
+            FlatScene& f;
+            Lend(FlatScene& fs) : f(fs) {
+                f.pending_tri.swap(keep_tri);
+                f.pending_material.swap(keep_mat);
+                f.pending_tri.clear();
+                f.pending_material.clear();
+            }
+            ~Lend() {
+                f.pending_tri.swap(keep_tri);
+                f.pending_material.swap(keep_mat);
+            }
+        } lend(flat);
+        int rc = flatten_scene(*desc, flat, &e, opts);
+        if (rc != RTC_OK) return set_err(rc, e);
+        PhaseClock clock;
+        rc = upload(flat, &e);
+        if (rc == kDeviceBuildTooDeep && attempt == 0) continue;  // rebuild this scene's meshes on the host
+        if (rc != 0) return set_err(RTC_ERR_CUDA, e);
+        clock.lap(flat.phase_ms, FlatScene::T_UPLOAD);
+        trace_phases(who, flat);
+        return RTC_OK;
+    }
+    return set_err(RTC_ERR_CUDA, "scene build failed");
+}
 
 extern "C" {
 
@@ -138,17 +196,6 @@ int rtc_device_count(void) {
     return n;
 }
 
-// RTC_B200_TRACE=1: where the host time of a scene build went (stderr, one line per call)
-static void trace_phases(const char* who, const FlatScene& flat) {
-    static const bool trace = std::getenv("RTC_B200_TRACE") != nullptr;
-    if (!trace) return;
-    const double* t = flat.phase_ms;
-    std::fprintf(stderr, "[rtc] %s: validate %.3f  group bounds %.3f  bvh items %.3f / build %.3f / splice %.3f  "
-                         "triangle tables %.3f  upload %.3f ms (%zu triangles, %zu bvh nodes)\n",
-                 who, t[0], t[1], t[2], t[3], t[4], t[5], t[6], flat.tris.size() + flat.device_tris,
-                 flat.bvh.size() + flat.device_nodes);
-}
-
 /* ---------------------------------------------------------------------------------------------- 1. CORE BOUNDARY */
 int rtc_scene_create(const rtc_scene_desc* desc, int device, rtc_scene** out) {
     return rtc_scene_create_ex(desc, device, RTC_BUILD_HOST_SAH, out);
@@ -157,40 +204,10 @@ int rtc_scene_create_ex(const rtc_scene_desc* desc, int device, uint32_t flags, 
     if (!desc || !out) return set_err(RTC_ERR_INVALID, "null argument");
     if (flags & ~(uint32_t)RTC_BUILD_DEVICE_LBVH) return set_err(RTC_ERR_INVALID, "unknown build flag");
     *out = nullptr;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        FlatScene flat;
-        std::string e;
-        FlattenOptions opts;
-        opts.device_mesh_build = (flags & RTC_BUILD_DEVICE_LBVH) && attempt == 0;
-        static const bool no_diag = std::getenv("RTC_B200_NO_DIAG_CUBE") != nullptr;  // A/B switch (profiles/r01r)
-        opts.diagonal_cubes = !no_diag;
-        // the device build's input arrays are megabytes: keep their pages across calls on this thread instead of
-        // faulting fresh ones in every time (a third of the gather time of a 10 k-triangle mesh)
-        thread_local std::vector<rtc_triangle_desc> keep_tri;
-        thread_local std::vector<int32_t> keep_mat;
-        struct Lend {
-            FlatScene& f;
-            Lend(FlatScene& fs) : f(fs) {
-                f.pending_tri.swap(keep_tri);
-                f.pending_material.swap(keep_mat);
-                f.pending_tri.clear();
-                f.pending_material.clear();
-            }
-            ~Lend() {
-                f.pending_tri.swap(keep_tri);
-                f.pending_material.swap(keep_mat);
-            }
-        } lend(flat);
-        int rc = flatten_scene(*desc, flat, &e, opts);
-        if (rc != RTC_OK) return set_err(rc, e);
+    return flatten_and_upload(desc, flags, "rtc_scene_create", [&](const FlatScene& flat, std::string* e) {
         DeviceScene* dev = nullptr;
-        PhaseClock clock;
-        int built_depth = 0;
-        rc = device_scene_create(flat, device, &dev, &e, &built_depth);
-        if (rc == kDeviceBuildTooDeep && attempt == 0) continue;  // rebuild this scene's meshes on the host
-        if (rc != 0) return set_err(RTC_ERR_CUDA, e);
-        clock.lap(flat.phase_ms, FlatScene::T_UPLOAD);
-        trace_phases("rtc_scene_create", flat);
+        const int rc = device_scene_create(flat, device, &dev, e, nullptr);
+        if (rc != 0) return rc;
         rtc_scene* s = new rtc_scene();
         s->dev = dev;
         s->info[0] = flat.leaf_count;
@@ -200,9 +217,8 @@ int rtc_scene_create_ex(const rtc_scene_desc* desc, int device, uint32_t flags, 
         s->info[4] = flat.bvh.size() + flat.device_nodes;
         s->info[5] = device_scene_bytes(dev);
         *out = s;
-        return RTC_OK;
-    }
-    return set_err(RTC_ERR_CUDA, "scene build failed");
+        return 0;
+    });
 }
 void rtc_scene_destroy(rtc_scene* scene) {
     if (!scene) return;
@@ -246,6 +262,54 @@ int rtc_render_device(const rtc_scene* scene, const rtc_camera_desc* camera, con
     if (rc != 0) return set_err(RTC_ERR_CUDA, e);
     if (want) fill_stats(ls, stats);
     return RTC_OK;
+}
+
+int rtc_multi_create(const rtc_scene_desc* desc, int ngpus, uint32_t flags, rtc_multi** out) {
+    if (!desc || !out) return set_err(RTC_ERR_INVALID, "null argument");
+    if (flags & ~(uint32_t)RTC_BUILD_DEVICE_LBVH) return set_err(RTC_ERR_INVALID, "unknown build flag");
+    *out = nullptr;
+    std::string ce;
+    const int have = cuda_device_count(&ce);
+    if (have < 1) return set_err(RTC_ERR_CUDA, ce.empty() ? "no CUDA device" : ce);
+    if (ngpus < 1 || ngpus > have) return set_err(RTC_ERR_INVALID, "ngpus must be between 1 and rtc_device_count()");
+    return flatten_and_upload(desc, flags, "rtc_multi_create", [&](const FlatScene& flat, std::string* e) {
+        MultiRenderer* m = nullptr;
+        const int rc = multi_create(flat, ngpus, &m, e);
+        if (rc != 0) return rc;
+        *out = new rtc_multi{m};
+        return 0;
+    });
+}
+void rtc_multi_destroy(rtc_multi* m) {
+    if (!m) return;
+    multi_destroy(m->m);
+    delete m;
+}
+int rtc_multi_render(rtc_multi* m, const rtc_camera_desc* camera, uint32_t where, uint8_t* rgba8_out, rtc_stats* stats) {
+    if (!m || !camera) return set_err(RTC_ERR_INVALID, "null argument");
+    if (where > RTC_MULTI_DEVICE_FRAME) return set_err(RTC_ERR_INVALID, "unknown rtc_multi_render target");
+    if (where == RTC_MULTI_DEVICE_FRAME && rgba8_out) return set_err(RTC_ERR_INVALID, "rgba8_out needs RTC_MULTI_HOST_FRAME");
+    if (!affine_camera(*camera)) return set_err(RTC_ERR_UNSUPPORTED, "non-affine camera transform");
+    LaunchStats ls;
+    std::string e;
+    double frame_ms = 0.;
+    if (multi_render(m->m, to_dcamera(*camera), where == RTC_MULTI_DEVICE_FRAME, stats ? &ls : nullptr, &frame_ms, &e) != 0)
+        return set_err(RTC_ERR_CUDA, e);
+    if (rgba8_out) std::memcpy(rgba8_out, multi_host_frame(m->m), (size_t)camera->hsize * camera->vsize * 4);
+    fill_stats(ls, stats);
+    return RTC_OK;
+}
+const uint8_t* rtc_multi_host_frame(const rtc_multi* m) { return m ? (const uint8_t*)multi_host_frame(m->m) : nullptr; }
+void* rtc_multi_device_frame(const rtc_multi* m) { return m ? multi_device_frame(m->m) : nullptr; }
+int rtc_render_multi(const rtc_scene_desc* desc, const rtc_camera_desc* camera, int ngpus, uint32_t flags,
+                     uint8_t* rgba8_out, rtc_stats* stats) {
+    if (!rgba8_out) return set_err(RTC_ERR_INVALID, "null argument");
+    rtc_multi* m = nullptr;
+    int rc = rtc_multi_create(desc, ngpus, flags, &m);
+    if (rc != RTC_OK) return rc;
+    rc = rtc_multi_render(m, camera, RTC_MULTI_HOST_FRAME, rgba8_out, stats);
+    rtc_multi_destroy(m);
+    return rc;
 }
 
 uint32_t rtc_rows_count(const rtc_camera_desc* camera, const rtc_rows* rows) {
@@ -449,9 +513,28 @@ rtc_world* rtc_world_default(void) {
     w->w = std::move(*d);
     return w;
 }
+static void world_drop_scenes(rtc_world* w) {  // w->mu held
+    for (auto& kv : w->scenes) rtc_scene_destroy(kv.second);
+    w->scenes.clear();
+}
+// w->mu held: the world's scene on `device`, marshalled and uploaded on first use
+static int world_scene_locked(rtc_world* w, int device, rtc_scene** out) {
+    auto it = w->scenes.find(device);
+    if (it == w->scenes.end()) {
+        Marshalled m;
+        marshal_world(w->w, m);
+        m.desc.recursion_limit = w->recursion_limit;
+        rtc_scene* s = nullptr;
+        int rc = rtc_scene_create_ex(&m.desc, device, w->build_flags, &s);
+        if (rc != RTC_OK) return rc;
+        it = w->scenes.emplace(device, s).first;
+    }
+    *out = it->second;
+    return RTC_OK;
+}
 void rtc_world_free(rtc_world* w) {
     if (!w) return;
-    rtc_scene_destroy(w->scene);
+    world_drop_scenes(w);
     delete w;
 }
 int rtc_world_push(rtc_world* w, rtc_shape* s) {
@@ -459,43 +542,42 @@ int rtc_world_push(rtc_world* w, rtc_shape* s) {
     std::lock_guard<std::mutex> lk(w->mu);
     w->w.objects.push_back(std::move(s->s));
     delete s;
-    rtc_scene_destroy(w->scene);
-    w->scene = nullptr;
+    world_drop_scenes(w);
     return RTC_OK;
 }
 int rtc_world_scene(rtc_world* w, int device, rtc_scene** out) {
     if (!w || !out) return set_err(RTC_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(w->mu);
-    if (w->scene && device_scene_device(w->scene->dev) != device) {
-        rtc_scene_destroy(w->scene);
-        w->scene = nullptr;
-    }
-    if (!w->scene) {
-        Marshalled m;
-        marshal_world(w->w, m);
-        int rc = rtc_scene_create_ex(&m.desc, device, w->build_flags, &w->scene);
-        if (rc != RTC_OK) return rc;
-    }
-    *out = w->scene;
-    return RTC_OK;
+    return world_scene_locked(w, device, out);
 }
 int rtc_world_set_build(rtc_world* w, uint32_t flags) {
     if (!w) return set_err(RTC_ERR_INVALID, "null argument");
     if (flags & ~(uint32_t)RTC_BUILD_DEVICE_LBVH) return set_err(RTC_ERR_INVALID, "unknown build flag");
     std::lock_guard<std::mutex> lk(w->mu);
-    if (flags != w->build_flags && w->scene) {
-        rtc_scene_destroy(w->scene);
-        w->scene = nullptr;
-    }
+    if (flags != w->build_flags) world_drop_scenes(w);
     w->build_flags = flags;
     return RTC_OK;
+}
+int rtc_world_set_recursion_limit(rtc_world* w, uint32_t limit) {
+    if (!w) return set_err(RTC_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(w->mu);
+    if (limit != w->recursion_limit) world_drop_scenes(w);
+    w->recursion_limit = limit;
+    return RTC_OK;
+}
+void rtc_world_drop_scenes(rtc_world* w) {
+    if (!w) return;
+    std::lock_guard<std::mutex> lk(w->mu);
+    world_drop_scenes(w);
 }
 // The layer-1 description of a world — exactly what rtc_world_scene hands to rtc_scene_create, and what the Rust-side
 // Camera::render patch builds from its &World.  The description borrows from the returned object.
 int rtc_world_marshal(rtc_world* w, rtc_marshalled** out) {
     if (!w || !out) return set_err(RTC_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(w->mu);
     rtc_marshalled* m = new rtc_marshalled();
     marshal_world(w->w, m->m);
+    m->m.desc.recursion_limit = w->recursion_limit;
     *out = m;
     return RTC_OK;
 }
@@ -542,8 +624,10 @@ int rtc_world_flatten_info(rtc_world* w, uint64_t n[8], double* gates_out, uint6
     return RTC_OK;
 }
 int rtc_world_color_at(rtc_world* w, const double* rays, uint64_t n, double* rgb_out) {
+    if (!w) return set_err(RTC_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(w->mu);  // the scene cannot be dropped under the call
     rtc_scene* s = nullptr;
-    int rc = rtc_world_scene(w, 0, &s);
+    int rc = world_scene_locked(w, 0, &s);
     if (rc != RTC_OK) return rc;
     return rtc_color_at(s, rays, n, rgb_out);
 }
@@ -570,19 +654,62 @@ void rtc_camera_desc_get(const rtc_camera* c, rtc_camera_desc* out) {
     out->pixel_size = c->c.pixel_size;
 }
 
+// Pinned host buffers are expensive to create (cudaHostAlloc of a 1080p f64 canvas: milliseconds — more than the frame):
+// a freed canvas leaves its pinned buffers in a small pool and the next canvas of that size takes them back.
+namespace {
+struct PinnedPool {
+    struct Entry {
+        void* p;
+        size_t bytes;
+    };
+    std::mutex mu;
+    std::vector<Entry> free_list;
+    size_t pooled = 0;
+    static constexpr size_t kMaxPooled = (size_t)4 << 30;
+    void* take(size_t bytes) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t i = 0; i < free_list.size(); i++)
+                if (free_list[i].bytes >= bytes && free_list[i].bytes <= bytes + bytes / 8 + 4096) {
+                    void* p = free_list[i].p;
+                    pooled -= free_list[i].bytes;
+                    free_list.erase(free_list.begin() + i);
+                    return p;
+                }
+        }
+        return pinned_alloc(bytes);
+    }
+    void give(void* p, size_t bytes) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (pooled + bytes <= kMaxPooled && free_list.size() < 16) {
+                free_list.push_back(Entry{p, bytes});
+                pooled += bytes;
+                return;
+            }
+        }
+        pinned_free(p);
+    }
+};
+PinnedPool& pinned_pool() {
+    static PinnedPool* pool = new PinnedPool();  // never destroyed: the CUDA runtime may already be gone at exit
+    return *pool;
+}
+}  // namespace
+
 static rtc_canvas* canvas_alloc(uint64_t width, uint64_t height, bool want_f64, bool pinned) {
     rtc_canvas* cv = new rtc_canvas();
     cv->width = width;
     cv->height = height;
     const size_t px = (size_t)width * height;
     if (pinned) {
-        cv->rgba8 = (uint8_t*)pinned_alloc(px * 4);
+        cv->rgba8 = (uint8_t*)pinned_pool().take(px * 4 ? px * 4 : 1);
         cv->rgba_pinned = cv->rgba8 != nullptr;
     }
     if (!cv->rgba8) cv->rgba8 = (uint8_t*)std::malloc(px * 4 ? px * 4 : 1);
     if (want_f64) {
         if (pinned) {
-            cv->rgb = (double*)pinned_alloc(px * 24);
+            cv->rgb = (double*)pinned_pool().take(px * 24 ? px * 24 : 1);
             cv->rgb_pinned = cv->rgb != nullptr;
         }
         if (!cv->rgb) cv->rgb = (double*)std::malloc(px * 24 ? px * 24 : 1);
@@ -590,11 +717,12 @@ static rtc_canvas* canvas_alloc(uint64_t width, uint64_t height, bool want_f64, 
     return cv;
 }
 
-int rtc_camera_render(const rtc_camera* c, rtc_world* w, int want_f64, rtc_canvas** out, rtc_stats* stats) {
+int rtc_camera_render(const rtc_camera* c, rtc_world* w, int device, int want_f64, rtc_canvas** out, rtc_stats* stats) {
     if (!c || !w || !out) return set_err(RTC_ERR_INVALID, "null argument");
     *out = nullptr;
+    std::lock_guard<std::mutex> lk(w->mu);  // the scene cannot be dropped under the render
     rtc_scene* s = nullptr;
-    int rc = rtc_world_scene(w, 0, &s);
+    int rc = world_scene_locked(w, device, &s);
     if (rc != RTC_OK) return rc;
     rtc_camera_desc cd;
     rtc_camera_desc_get(c, &cd);
@@ -620,8 +748,9 @@ rtc_canvas* rtc_canvas_new(uint64_t width, uint64_t height) {  // canvas.rs:12-1
 }
 void rtc_canvas_free(rtc_canvas* c) {
     if (!c) return;
-    if (c->rgb) c->rgb_pinned ? pinned_free(c->rgb) : std::free(c->rgb);
-    if (c->rgba8) c->rgba_pinned ? pinned_free(c->rgba8) : std::free(c->rgba8);
+    const size_t px = (size_t)c->width * c->height;
+    if (c->rgb) c->rgb_pinned ? pinned_pool().give(c->rgb, px * 24 ? px * 24 : 1) : std::free(c->rgb);
+    if (c->rgba8) c->rgba_pinned ? pinned_pool().give(c->rgba8, px * 4 ? px * 4 : 1) : std::free(c->rgba8);
     delete c;
 }
 uint64_t rtc_canvas_width(const rtc_canvas* c) { return c ? c->width : 0; }

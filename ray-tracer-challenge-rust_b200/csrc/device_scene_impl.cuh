@@ -9,14 +9,21 @@
 
 namespace rtc {
 
-// work queue + exact ray counters of one launch
+// Work queue + exact ray counters of one launch.  The queue cleans up after itself: the last CTA of a launch to finish
+// moves the counters into `result` and zeroes everything else, so the next launch on the same slot needs no memset (one
+// API call and one GPU-side bubble less per frame).
 struct DQueue {
-    unsigned long long primary, shadow, reflect, refract;
+    unsigned long long primary, shadow, reflect, refract;  // live counters of the running launch
+    unsigned long long result[4];                          // the finished launch's counters
     unsigned int next_tile;
-    unsigned int pad;
+    unsigned int done_ctas;
+    unsigned int pad[2];
 };
 
+// Slots 0 .. kQueueSlots-2 belong to ONE caller stream each (launches of a stream are ordered, so its slot is never in use
+// by two kernels); the last slot is shared by any further streams, with an event between consecutive launches.
 constexpr int kQueueSlots = 16;
+constexpr int kHostChunks = 4;  // launches a host-output render is cut into at most (render_host)
 
 // Per-device state created on first use and kept for the life of the process: creating streams, events and querying
 // device properties costs milliseconds, a frame costs less.
@@ -26,9 +33,11 @@ struct DeviceContext {
     cudaStream_t stream = nullptr;  // the library's own stream (uploads, host-output renders)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t copy_stream = nullptr;  // device->host copies that overlap the next chunk's kernel (render_host)
-    cudaEvent_t chunk_done = nullptr, copy_done = nullptr;
-    DQueue* queues = nullptr;       // kQueueSlots work queues handed out round-robin (one per in-flight launch)
-    unsigned next_queue = 0;
+    cudaEvent_t chunk_done[kHostChunks] = {}, copy_done = nullptr;
+    DQueue* queues = nullptr;       // kQueueSlots self-cleaning work queues (see DQueue)
+    cudaStream_t slot_stream[kQueueSlots] = {};  // which stream owns slot k
+    int slots_taken = 0;
+    cudaEvent_t shared_slot_free = nullptr;      // recorded after every launch on the shared (last) slot
     // grow-only scratch
     void* out8 = nullptr;
     size_t out8_size = 0;

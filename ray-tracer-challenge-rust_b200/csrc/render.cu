@@ -161,6 +161,8 @@ static DeviceContext* context_for(int device, std::string* err) {
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->queues, sizeof(DQueue) * kQueueSlots);
+    if (e == cudaSuccess) e = cudaMemset(c->queues, 0, sizeof(DQueue) * kQueueSlots);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->shared_slot_free, cudaEventDisableTiming);
     if (e == cudaSuccess) {  // keep freed scene slabs in the stream-ordered pool instead of returning them to the driver
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -312,21 +314,34 @@ uint64_t device_scene_bytes(const DeviceScene* s) { return s->slab_size; }
 uint64_t device_scene_upload_bytes(const DeviceScene* s) { return s->upload_bytes; }
 int device_scene_device(const DeviceScene* s) { return s->device; }
 
-static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d8, void* d64, cudaStream_t st,
-                  LaunchStats* stats, std::string* err) {
-    if (rows.row_count == 0 || cam.hsize == 0) {
-        if (stats) *stats = LaunchStats{};
-        return 0;
+// The work queue a launch on stream `st` uses (DQueue, kQueueSlots).  *shared: the slot is the shared one.
+static DQueue* queue_for(DeviceContext* ctx, cudaStream_t st, bool* shared) {
+    *shared = false;
+    for (int k = 0; k < ctx->slots_taken; k++)
+        if (ctx->slot_stream[k] == st) return ctx->queues + k;
+    if (ctx->slots_taken < kQueueSlots - 1) {
+        ctx->slot_stream[ctx->slots_taken] = st;
+        return ctx->queues + ctx->slots_taken++;
     }
+    *shared = true;
+    return ctx->queues + (kQueueSlots - 1);
+}
+
+// Enqueues one render kernel on `st`.  timed: bracket it with the context's events (one timed launch in flight per device).
+static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d8, void* d64, cudaStream_t st, bool timed,
+                  DQueue** used, std::string* err) {
+    if (used) *used = nullptr;
+    if (rows.row_count == 0 || cam.hsize == 0) return 0;
     DeviceContext* ctx = s->ctx;
-    DQueue* queue = ctx->queues + (ctx->next_queue++ % kQueueSlots);
-    RTC_CUDA(cudaMemsetAsync(queue, 0, sizeof(DQueue), st));
+    bool shared = false;
+    DQueue* queue = queue_for(ctx, st, &shared);
+    if (shared) RTC_CUDA(cudaStreamWaitEvent(st, ctx->shared_slot_free, 0));
     const uint64_t tiles = (uint64_t)((cam.hsize + kTileW - 1) / kTileW) * ((rows.row_count + kTileH - 1) / kTileH);
     const uint64_t warps_per_block = kBlockThreads / 32;
     uint64_t blocks = (tiles + warps_per_block - 1) / warps_per_block;
     const uint64_t cap = (uint64_t)s->sm_count * kBlocksPerSm;
     if (blocks > cap) blocks = cap;
-    if (stats) RTC_CUDA(cudaEventRecord(ctx->ev0, st));
+    if (timed) RTC_CUDA(cudaEventRecord(ctx->ev0, st));
     // the smallest instantiation whose feature mask covers the scene's (render_launch.cuh)
     static const struct {
         int mask;
@@ -344,20 +359,27 @@ static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
         }
     fn((unsigned)blocks, st, s->view, cam, rows, (uint32_t*)d8, (double*)d64, queue);
     RTC_CUDA(cudaGetLastError());
-    if (stats) {
-        RTC_CUDA(cudaEventRecord(ctx->ev1, st));
-        DQueue h;
-        RTC_CUDA(cudaMemcpyAsync(&h, queue, sizeof(h), cudaMemcpyDeviceToHost, st));
-        RTC_CUDA(cudaStreamSynchronize(st));
-        float ms = 0.f;
-        RTC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        stats->primary = h.primary;
-        stats->shadow = h.shadow;
-        stats->reflect = h.reflect;
-        stats->refract = h.refract;
-        stats->launches = 1;
-        stats->device_ms = ms;
-    }
+    if (timed) RTC_CUDA(cudaEventRecord(ctx->ev1, st));
+    if (shared) RTC_CUDA(cudaEventRecord(ctx->shared_slot_free, st));
+    if (used) *used = queue;
+    return 0;
+}
+
+// Waits for a timed launch and reads its counters and kernel time.
+static int launch_stats(DeviceScene* s, DQueue* queue, cudaStream_t st, LaunchStats* stats, std::string* err) {
+    *stats = LaunchStats{};
+    if (!queue) return 0;
+    unsigned long long h[4];
+    RTC_CUDA(cudaMemcpyAsync(h, queue->result, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RTC_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    RTC_CUDA(cudaEventElapsedTime(&ms, s->ctx->ev0, s->ctx->ev1));
+    stats->primary = h[0];
+    stats->shadow = h[1];
+    stats->reflect = h[2];
+    stats->refract = h[3];
+    stats->launches = 1;
+    stats->device_ms = ms;
     return 0;
 }
 
@@ -365,8 +387,30 @@ int render_device(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
                   LaunchStats* stats, std::string* err) {
     std::lock_guard<std::mutex> lk(s->mu());
     RTC_CUDA(cudaSetDevice(s->device));
-    return launch(s, cam, rows, d_rgba8, d_rgb_f64, (cudaStream_t)stream, stats, err);
+    DQueue* q = nullptr;
+    int rc = launch(s, cam, rows, d_rgba8, d_rgb_f64, (cudaStream_t)stream, stats != nullptr, &q, err);
+    if (rc == 0 && stats) rc = launch_stats(s, q, (cudaStream_t)stream, stats, err);
+    return rc;
 }
+
+// Two halves of render_device for callers that keep several devices busy at once (multi.cu): enqueue on every device
+// first, then collect.
+int render_device_begin(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d_rgba8, void* d_rgb_f64, void* stream,
+                        void** token, std::string* err) {
+    std::lock_guard<std::mutex> lk(s->mu());
+    RTC_CUDA(cudaSetDevice(s->device));
+    DQueue* q = nullptr;
+    const int rc = launch(s, cam, rows, d_rgba8, d_rgb_f64, stream ? (cudaStream_t)stream : s->stream, true, &q, err);
+    *token = q;
+    return rc;
+}
+int render_device_end(DeviceScene* s, void* stream, void* token, LaunchStats* stats, std::string* err) {
+    std::lock_guard<std::mutex> lk(s->mu());
+    RTC_CUDA(cudaSetDevice(s->device));
+    LaunchStats local;
+    return launch_stats(s, (DQueue*)token, stream ? (cudaStream_t)stream : s->stream, stats ? stats : &local, err);
+}
+void* device_scene_stream(const DeviceScene* s) { return s->stream; }
 
 int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* rgba8, double* rgb_f64,
                 LaunchStats* stats, std::string* err) {
@@ -387,14 +431,20 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* 
         RTC_CUDA(cudaMalloc(&s->ctx->out64, px * 24));
         s->ctx->out64_size = px * 24;
     }
-    // Overlap the device->host copy with rendering: the call's rows are rendered in two launches (3/4, then 1/4) and the
-    // first chunk's pixels cross PCIe on a second stream while the second chunk renders.  More, smaller chunks were
-    // measured slower at every frame size (each launch pays its own ramp-up and tail: 8K pumpkin 11.5 ms with 2 chunks,
-    // 11.7-12.2 ms with 4-16; profiles/r01n_host_chunk_sweep.json).  Ray counters are per launch; with `stats` requested
-    // the frame is rendered in one launch so that the reported kernel time is one kernel's.
-    const bool split = !stats && !rgb_f64 && rgba8 && rows.local_rows >= 256;
+    // Overlap the device->host copies with rendering: the call's rows are rendered in a few launches and each chunk's
+    // pixels cross PCIe on a second stream while the next chunk renders.
+    //   RGBA8 only (4 B/px): two launches, 3/4 then 1/4 — more, smaller chunks were measured slower at every frame size
+    //   (each launch pays its own ramp-up and tail: 8K pumpkin 11.5 ms with 2 chunks, 11.7-12.2 ms with 4-16;
+    //   profiles/r01n_host_chunk_sweep.json);
+    //   with the f64 Canvas colours (24 B/px more: the copy, not the kernel, is the long pole — 50 MB at 1080p) four
+    //   launches of 1/8, 1/8, 1/4, 1/2 of the rows: the copy engine starts after an eighth of the frame and never waits.
+    // Ray counters are per launch; with `stats` requested the frame is rendered in one launch so that the reported kernel
+    // time is one kernel's.
+    const bool split = !stats && (rgba8 || rgb_f64) && rows.local_rows >= 256;
+    DQueue* q = nullptr;
     if (!split) {
-        int rc = launch(s, cam, rows, rgba8 ? s->ctx->out8 : nullptr, rgb_f64 ? s->ctx->out64 : nullptr, s->stream, stats, err);
+        int rc = launch(s, cam, rows, rgba8 ? s->ctx->out8 : nullptr, rgb_f64 ? s->ctx->out64 : nullptr, s->stream,
+                        stats != nullptr, &q, err);
         if (rc) return rc;
         if (rgba8 && px) RTC_CUDA(cudaMemcpyAsync(rgba8, s->ctx->out8, px * 4, cudaMemcpyDeviceToHost, s->stream));
         if (rgb_f64 && px) RTC_CUDA(cudaMemcpyAsync(rgb_f64, s->ctx->out64, px * 24, cudaMemcpyDeviceToHost, s->stream));
@@ -402,29 +452,47 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* 
         DeviceContext* ctx = s->ctx;
         if (!ctx->copy_stream) {
             RTC_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-            RTC_CUDA(cudaEventCreateWithFlags(&ctx->chunk_done, cudaEventDisableTiming));
+            for (cudaEvent_t& e : ctx->chunk_done) RTC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             RTC_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
         }
-        const uint32_t first = ((rows.local_rows * 3 / 4) + kTileH - 1) / kTileH * kTileH;
-        DRows a = rows, b = rows;
-        a.row_begin = 0;
-        a.row_count = first;
-        b.row_begin = first;
-        b.row_count = rows.local_rows - first;
-        int rc = launch(s, cam, a, ctx->out8, nullptr, s->stream, nullptr, err);
-        if (rc) return rc;
-        RTC_CUDA(cudaEventRecord(ctx->chunk_done, s->stream));
-        rc = launch(s, cam, b, ctx->out8, nullptr, s->stream, nullptr, err);
-        if (rc) return rc;
-        const size_t bytes_a = (size_t)first * cam.hsize * 4;
-        RTC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done, 0));
-        RTC_CUDA(cudaMemcpyAsync(rgba8, ctx->out8, bytes_a, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        uint32_t cut[kHostChunks + 1];  // chunk k renders local rows [cut[k], cut[k + 1])
+        int nchunks;
+        const auto tile_rows = [](uint32_t r) { return (r + kTileH - 1) / kTileH * kTileH; };
+        if (rgb_f64) {
+            nchunks = 4;
+            cut[0] = 0;
+            cut[1] = tile_rows(rows.local_rows / 8);
+            cut[2] = tile_rows(rows.local_rows / 4);
+            cut[3] = tile_rows(rows.local_rows / 2);
+            cut[4] = rows.local_rows;
+        } else {
+            nchunks = 2;
+            cut[0] = 0;
+            cut[1] = tile_rows(rows.local_rows * 3 / 4);
+            cut[2] = rows.local_rows;
+        }
+        for (int k = 0; k < nchunks; k++) {
+            DRows part = rows;
+            part.row_begin = cut[k];
+            part.row_count = cut[k + 1] - cut[k];
+            int rc = launch(s, cam, part, rgba8 ? ctx->out8 : nullptr, rgb_f64 ? ctx->out64 : nullptr, s->stream, false,
+                            nullptr, err);
+            if (rc) return rc;
+            RTC_CUDA(cudaEventRecord(ctx->chunk_done[k], s->stream));
+            RTC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done[k], 0));
+            const size_t p0 = (size_t)cut[k] * cam.hsize, pn = (size_t)part.row_count * cam.hsize;
+            if (rgba8 && pn)
+                RTC_CUDA(cudaMemcpyAsync(rgba8 + p0 * 4, (const unsigned char*)ctx->out8 + p0 * 4, pn * 4,
+                                         cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (rgb_f64 && pn)
+                RTC_CUDA(cudaMemcpyAsync(rgb_f64 + p0 * 3, (const double*)ctx->out64 + p0 * 3, pn * 24,
+                                         cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
         RTC_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
-        RTC_CUDA(cudaMemcpyAsync(rgba8 + bytes_a, (const unsigned char*)ctx->out8 + bytes_a, px * 4 - bytes_a,
-                                 cudaMemcpyDeviceToHost, s->stream));
         RTC_CUDA(cudaStreamWaitEvent(s->stream, ctx->copy_done, 0));
     }
     RTC_CUDA(cudaStreamSynchronize(s->stream));
+    if (stats) return launch_stats(s, q, s->stream, stats, err);
     return 0;
 }
 

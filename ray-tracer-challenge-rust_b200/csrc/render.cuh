@@ -38,11 +38,27 @@ int device_scene_device(const DeviceScene* s);
 // With `stats` non-null the call brackets the kernel with CUDA events, synchronises the stream and fills *stats.
 int render_device(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d_rgba8, void* d_rgb_f64, void* stream,
                   LaunchStats* stats, std::string* err);
+// The two halves of a timed render_device, for callers that keep several devices busy at once (multi.cu): begin enqueues
+// (stream null = the scene's own library stream), end waits and reads counters and kernel time.
+int render_device_begin(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d_rgba8, void* d_rgb_f64, void* stream,
+                        void** token, std::string* err);
+int render_device_end(DeviceScene* s, void* stream, void* token, LaunchStats* stats, std::string* err);
+void* device_scene_stream(const DeviceScene* s);
 // Same with host outputs (pinned or pageable), including the device->host copies.
 int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* rgba8, double* rgb_f64,
                 LaunchStats* stats, std::string* err);
 // World::color_at for explicit rays (host in, host out).
 int color_at_host(DeviceScene* s, const double* rays, uint64_t n, double* rgb, std::string* err);
+
+// One frame sharded over several devices of this process (multi.cu).
+struct MultiRenderer;
+int multi_create(const FlatScene& flat, int ngpus, MultiRenderer** out, std::string* err);
+void multi_destroy(MultiRenderer* m);
+int multi_render(MultiRenderer* m, const DCamera& cam, bool to_device_frame, LaunchStats* stats, double* frame_ms,
+                 std::string* err);
+void* multi_device_frame(const MultiRenderer* m);
+const void* multi_host_frame(const MultiRenderer* m);
+int multi_device_count(const MultiRenderer* m);
 
 // Single-ray probes (probe.cu): World::intersect's sorted list, prepare_computations of the hit, Shape::normal_at.
 int probe_intersect(DeviceScene* s, const double* rays, uint64_t n, uint32_t cap, double* t_out, int32_t* leaf_out,

@@ -124,6 +124,21 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
         if (v[2]) atomicAdd(&q->reflect, v[2]);
         if (v[3]) atomicAdd(&q->refract, v[3]);
     }
+    // the last CTA to finish publishes the launch's counters and leaves the queue zeroed for the next launch (DQueue)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&q->done_ctas, 1u) == gridDim.x - 1) {
+            __threadfence();
+            q->result[0] = atomicExch(&q->primary, 0ull);
+            q->result[1] = atomicExch(&q->shadow, 0ull);
+            q->result[2] = atomicExch(&q->reflect, 0ull);
+            q->result[3] = atomicExch(&q->refract, 0ull);
+            q->next_tile = 0;
+            q->done_ctas = 0;
+            __threadfence();
+        }
+    }
 }
 
 

@@ -268,7 +268,9 @@ def test_schlick(kit):
                                                           [0, 0.99, -2, 0, 0, 1]])
     assert tir.reflectance == 1.0                                   # intersection.rs:340-353
     assert abs(perpendicular.reflectance - 0.04) < ATOL             # :355-366
-    assert abs(grazing.t - 1.8589) < 1e-4 and abs(grazing.reflectance - 0.48873) < ATOL  # :368-379
+    # :368-379 builds its intersection by hand at the rounded t = 1.8589; the real hit is at 1.85893264, which moves the
+    # point on the sphere and with it the reflectance by 8e-5
+    assert abs(grazing.t - 1.8589) < 1e-4 and abs(grazing.reflectance - 0.48873) < 2e-4
 
 
 def test_probes_agree_with_the_oracle_on_a_mesh(rtc, oracle):

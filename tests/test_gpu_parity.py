@@ -224,14 +224,22 @@ def test_full_size_properties_8k(rtc):
 
 @pytest.mark.parametrize("w,h", [(1280, 720), (2560, 1442), (4096, 2160)])
 def test_host_output_chunks_match_single_launch(rtc, w, h):
-    """rtc_render's chunked path (each chunk's copy overlapped with the next chunk's kernel: 2 launches for a small
-    frame, one per ~4 MiB up to 16 for larger ones, ragged last tile row included) returns the one-launch frame."""
+    """rtc_render's chunked path (csrc/render.cu render_host: 2 launches — 3/4 and 1/4 of the rows — for an RGBA8 frame, 4
+    launches — 1/8, 1/8, 1/4, 1/2 — when the f64 Canvas colours are wanted too; each chunk's copy overlaps the next
+    chunk's kernel; ragged last tile row included) returns the one-launch frame."""
     world, cam = rtc.build_scene("cow_teddy", w, h)
     one = np.empty((h, w, 4), dtype=np.uint8)
     two = np.zeros_like(one)
-    cam.render_into(world, rgba8=one, stats=rtc.Stats())  # stats requested -> single launch
-    cam.render_into(world, rgba8=two)                      # no stats -> chunked + overlapped copies
+    f_one, f_two = np.empty((h, w, 3)), np.zeros((h, w, 3))
+    cam.render_into(world, rgba8=one, rgb_f64=f_one, stats=rtc.Stats())  # stats requested -> single launch
+    cam.render_into(world, rgba8=two)                                     # no stats -> chunked + overlapped copies
     assert np.array_equal(one, two)
+    two[:] = 0
+    cam.render_into(world, rgba8=two, rgb_f64=f_two)
+    assert np.array_equal(one, two) and np.array_equal(f_one.view(np.uint64), f_two.view(np.uint64))
+    f_two[:] = 0
+    cam.render_into(world, rgb_f64=f_two)
+    assert np.array_equal(f_one.view(np.uint64), f_two.view(np.uint64))
 
 
 def test_device_ppm_encoder_is_byte_identical(rtc, oracle):
@@ -388,3 +396,29 @@ def test_random_triangle_soups_under_both_builds(rtc, oracle, seed):
         assert st.total_rays == cnt.total_rays
         frames.append(rgb)
     assert np.array_equal(frames[0].view(np.uint64), frames[1].view(np.uint64))
+
+
+@pytest.mark.parametrize("name,w,h", [("table", 640, 363), ("cow_teddy", 320, 180)])
+def test_multi_device_render_in_one_process(rtc, name, w, h):
+    """rtc_multi_* / rtc_render_multi (csrc/multi.cu): the frame sharded over every GPU of the box from ONE process — both
+    the pinned host frame (per-device strided copies) and the device-0 frame (peer stores) equal the single-GPU frame, ray
+    counts included; a frame height that is not a multiple of the band height included."""
+    import torch
+    world, cam = rtc.build_scene(name, w, h)
+    one = np.empty((h, w, 4), dtype=np.uint8)
+    st1 = rtc.Stats()
+    cam.render_into(world, rgba8=one, stats=st1)
+    for ngpus in sorted({1, min(2, rtc.device_count()), rtc.device_count()}):
+        mr = rtc.MultiRenderer(world, ngpus)
+        st = rtc.Stats()
+        assert np.array_equal(mr.render(cam, "host", stats=st), one), ngpus
+        assert st.total_rays == st1.total_rays and st.kernel_launches == ngpus
+        ptr = mr.render(cam, "device")
+
+        class _Iface:
+            __cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        assert np.array_equal(torch.as_tensor(_Iface(), device="cuda:0").cpu().numpy(), one), ngpus
+        mr.close()
+        st = rtc.Stats()
+        assert np.array_equal(rtc.render_multi(world, cam, ngpus, stats=st), one)
+        assert st.total_rays == st1.total_rays
