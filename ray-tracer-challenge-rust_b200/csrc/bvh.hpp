@@ -95,6 +95,7 @@ struct BvhBuilder {
     std::vector<Item>& items;
     std::vector<DBvhNode>& nodes;
     double pad;
+    int leaf_max = kLeafMax;  // items per leaf (triangles: kLeafMax; clustered primitives: 1, their exact tests are dear)
     int max_depth = 0;
 
     static int bin_of(double c, double lo, double scale, int nb) {
@@ -269,7 +270,7 @@ struct BvhBuilder {
         Aabb box, cbox;
         range_boxes(begin, end, box, cbox);
         const uint32_t n = end - begin;
-        if (n <= (uint32_t)kLeafMax) return Sub{true, (int32_t)begin, (int32_t)n, box};
+        if (n <= (uint32_t)leaf_max) return Sub{true, (int32_t)begin, (int32_t)n, box};
         const uint32_t mid = split(begin, end, depth, cbox);
         const int32_t me = (int32_t)nodes.size();
         nodes.emplace_back();
@@ -299,8 +300,9 @@ struct Built {
     int depth = 0;
 };
 
-inline void build_range(std::vector<Item>& items, double pad, uint32_t begin, uint32_t end, int depth, Built& out) {
-    BvhBuilder b{items, out.nodes, pad};
+inline void build_range(std::vector<Item>& items, double pad, int leaf_max, uint32_t begin, uint32_t end, int depth,
+                        Built& out) {
+    BvhBuilder b{items, out.nodes, pad, leaf_max};
     if (depth >= kParallelDepth || end - begin < kParallelMin) {
         out.sub = b.build(begin, end, depth);
         out.depth = b.max_depth;
@@ -310,8 +312,8 @@ inline void build_range(std::vector<Item>& items, double pad, uint32_t begin, ui
     b.range_boxes(begin, end, box, cbox);
     const uint32_t mid = b.split(begin, end, depth, cbox);
     Built left, right;
-    std::thread other([&] { build_range(items, pad, mid, end, depth + 1, right); });
-    build_range(items, pad, begin, mid, depth + 1, left);
+    std::thread other([&] { build_range(items, pad, leaf_max, mid, end, depth + 1, right); });
+    build_range(items, pad, leaf_max, begin, mid, depth + 1, left);
     other.join();
     out.nodes.reserve(1 + left.nodes.size() + right.nodes.size());
     out.nodes.emplace_back();
@@ -335,6 +337,28 @@ inline void build_range(std::vector<Item>& items, double pad, uint32_t begin, ui
 }
 
 }  // namespace detail
+
+// The tree over ready-made items (boxes + centroids + ids): appends its nodes to `nodes`, leaf slots count from
+// `leaf_base`, order[slot] = id of the item stored there.  Returns the root node index (-1: everything fits one leaf).
+inline int32_t build_bvh_items(std::vector<detail::Item>& items, double pad, int leaf_max, std::vector<DBvhNode>& nodes,
+                               int32_t leaf_base, std::vector<uint32_t>& order, int* max_depth) {
+    using namespace detail;
+    const uint32_t n = (uint32_t)items.size();
+    order.resize(n);
+    Built root;
+    build_range(items, pad, leaf_max, 0, n, 0, root);
+    // global indices: nodes after the ones already in `nodes`, leaf slots after leaf_base
+    const int32_t base = (int32_t)nodes.size();
+    nodes.reserve(nodes.size() + root.nodes.size());
+    for (DBvhNode nd : root.nodes) {
+        nd.child0 += nd.count0 > 0 ? leaf_base : base;
+        nd.child1 += nd.count1 > 0 ? leaf_base : base;
+        nodes.push_back(nd);
+    }
+    for (uint32_t i = 0; i < n; i++) order[i] = items[i].id;
+    if (max_depth) *max_depth = root.depth + 1;
+    return root.sub.leaf ? -1 : base + root.sub.index;
+}
 
 inline int32_t build_bvh(const std::vector<BvhTri>& tris, std::vector<DBvhNode>& nodes, int32_t tri_base,
                          std::vector<uint32_t>& order, int* max_depth, double* max_abs_out = nullptr,
@@ -368,21 +392,11 @@ inline int32_t build_bvh(const std::vector<BvhTri>& tris, std::vector<DBvhNode>&
     if (n <= (uint32_t)kLeafMax) return -1;
     const double pad = kPadRel * std::max(max_abs, std::numeric_limits<double>::min());
     lap(0);
-    Built root;
-    build_range(items, pad, 0, n, 0, root);
+    int depth = 0;
+    const int32_t root = build_bvh_items(items, pad, kLeafMax, nodes, tri_base, order, &depth);
+    if (max_depth) *max_depth = depth;
     lap(1);
-    // global indices: nodes after the ones already in `nodes`, leaf slots after tri_base
-    const int32_t base = (int32_t)nodes.size();
-    nodes.reserve(nodes.size() + root.nodes.size());
-    for (DBvhNode nd : root.nodes) {
-        nd.child0 += nd.count0 > 0 ? tri_base : base;
-        nd.child1 += nd.count1 > 0 ? tri_base : base;
-        nodes.push_back(nd);
-    }
-    for (uint32_t i = 0; i < n; i++) order[i] = items[i].id;
-    if (max_depth) *max_depth = root.depth + 1;
-    lap(2);
-    return root.sub.leaf ? -1 : base + root.sub.index;
+    return root;
 }
 
 }  // namespace rtc

@@ -18,7 +18,7 @@
 
 namespace rtc {
 
-enum : int32_t { NODE_GATE = 0, NODE_PRIM = 1, NODE_MESH = 2 };
+enum : int32_t { NODE_GATE = 0, NODE_PRIM = 1, NODE_MESH = 2, NODE_CLUSTER = 3 };
 
 struct DProgramNode {
     int32_t type;    // NODE_*
@@ -29,31 +29,34 @@ struct DProgramNode {
 struct DXform {
     double m[12];  // inverse, rows 0..2
 };
-// reject: 0 = always run the exact test; 1 = a ray that misses the padded world box [blo,bhi] cannot intersect the
-// leaf; 2 = same, but valid only when every object-space direction component is clearly >= EPSILON (the cube's
-// check_axis treats smaller ones as parallel, shape.rs:593-599), decided in f32 with m32 (rows of the inverse's 3x3) and
-// the per-row rounding slack k; 3 = a cube whose inverse's 3x3 is diagonal: the same decision from m32[0..2] (the diagonal)
-// with one product per axis.
+// A non-triangle leaf.  Bounded leaves with enough bounded siblings are gathered into a CLUSTER — a small BVH over their
+// padded world boxes (see DMesh) — and stored in its leaf order; the others are PRIM entries of the program.
 struct alignas(16) DPrim {
     int32_t kind, material, xform, capped;
     double minimum, maximum;
     int32_t leaf;  // DFS leaf index
-    int32_t reject;
-    float k[3];
-    float m32[9];
-    float blo[3], bhi[3];  // padded world box, f32 rounded outward (tested like a BVH box)
-    int32_t cls;           // >= 0: member of a class of value-equal leaves (shape.rs:638-646), see DClassMember
-    int32_t pad2[3];
+    int32_t cls;   // >= 0: member of a class of value-equal leaves (shape.rs:638-646), see DClassMember
+    int32_t pad[2];
 };
-static_assert(sizeof(DPrim) == 128, "DPrim layout: read with 16-byte loads");
+static_assert(sizeof(DPrim) == 48, "DPrim layout: read with 16-byte loads");
 struct DGate {
     double lo[3], hi[3];
 };
+// MESH: a run of sibling triangles sharing one transform, traversed in the mesh's object space through a BVH.
+// CLUSTER (xform = -1): sibling spheres / cubes / finite cylinders under one parent, traversed with the WORLD ray through a
+// BVH over their world boxes, each leaf run then tested exactly in its own object space.  A cube's check_axis treats an
+// object-space direction component below EPSILON as parallel (shape.rs:593-599) and then reports intersections that have
+// drifted up to EPSILON * t outside the true cube, so cluster boxes of cubes are padded by EPSILON * kClusterReach * (the
+// cube's largest column norm): valid for unit-length rays that start within `reach` of the cluster's centre (rfast2 =
+// reach^2), which every camera, shadow, reflection and refraction ray of a scene around the cluster does; any other ray
+// takes the exact linear scan of the cluster's leaves.
 struct DMesh {
-    int32_t xform, root, tri_base, tri_count;  // root < 0: no BVH (tiny mesh), scan [tri_base, tri_base + tri_count)
-    float extent;                              // max |coordinate| of the mesh in object space (f32 slab error bound)
+    int32_t xform, root, tri_base, tri_count;  // root < 0: no BVH (tiny), scan [tri_base, tri_base + tri_count)
+    float extent;                              // max |coordinate| of the boxes (f32 slab error bound)
+    float cx, cy, cz, rfast2;                  // CLUSTER: centre and squared reach of the fast path
     int32_t pad[3];
 };
+static_assert(sizeof(DMesh) == 48, "DMesh layout");
 // f32 boxes rounded OUTWARD from the padded f64 boxes: 64 bytes hold both children, one fetch decides two subtrees.
 struct alignas(64) DBvhNode {
     float lo0[3], hi0[3], lo1[3], hi1[3];
@@ -100,9 +103,7 @@ struct DScene {
     int32_t n_classes;
     int32_t pad1;
     int32_t program_count;
-    int32_t reject_prims;  // how many prims carry a reject box (0: the walker skips the per-ray set-up for them)
-    float reject_extent;   // max |coordinate| over those boxes (f32 slab error bound)
-    int32_t pad0;
+    int32_t pad0[3];
     uint32_t n_prims, n_xforms, n_gates, n_materials;  // table lengths (shared-memory staging)
     double light_pos[3];
     double light_int[3];
@@ -120,5 +121,8 @@ struct DRows {
 };
 // depth of the per-thread traversal stack; flatten.hpp refuses a mesh whose BVH is deeper (the builder bounds depth)
 constexpr int kBvhStackDepth = 48;
+// the same for a kernel whose scenes hold clusters but no meshes (a cluster tree deeper than this is not built: its leaves
+// stay PRIM entries)
+constexpr int kClusterStackDepth = 16;
 
 }  // namespace rtc

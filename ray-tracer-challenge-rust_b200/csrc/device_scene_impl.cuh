@@ -61,6 +61,23 @@ struct DeviceScene {
     std::mutex& mu() { return ctx->mu; }
 };
 
+// Every entry point that selects a device puts the caller's current device back on the way out: the host program (torch,
+// another library, the caller's own CUDA code) keeps the device it had.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            prev = -1;
+            cudaGetLastError();
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 inline std::string cuda_err_string(const char* what, cudaError_t e) {
     return std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
 }

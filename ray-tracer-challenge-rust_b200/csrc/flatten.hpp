@@ -40,7 +40,11 @@ constexpr int kFlattenNeedsHostBuild = -100;
 
 struct FlattenOptions {
     bool device_mesh_build = false;  // leave meshes of >= kDeviceBuildMin triangles to the device build (lbvh.cuh)
-    bool diagonal_cubes = true;      // reject mode 3 for cubes without rotation or shear (one product per axis)
+#if defined(RTC_NO_CLUSTERS)  // A/B switch (tools/tune_variants.py)
+    bool clusters = false;
+#else
+    bool clusters = true;            // gather bounded sibling leaves into BVH clusters (off: every leaf is a PRIM entry)
+#endif
 };
 constexpr uint32_t kDeviceBuildMin = 256;
 
@@ -283,16 +287,28 @@ class Flattener {
         return std::nextafterf(f, std::numeric_limits<float>::infinity());
     }
 
-    // A conservative world-space box for a bounded leaf, so the walker can skip its exact test for rays that pass far
-    // away (own structure, not reference arithmetic: it may only skip tests whose exact result is "no intersection").
-    //   sphere / cube : the unit cube [-1,1]^3 (shape.rs:258-319)
+    // ---- clusters: a BVH over the world boxes of sibling spheres / cubes / finite cylinders (device_scene.h DMesh) ------
+    // Own structure, not reference arithmetic: it may only skip exact leaf tests whose result is "no intersection".
+    //   sphere / cube : the unit cube [-1,1]^3 through the leaf's transform (shape.rs:258-319)
     //   cylinder      : radius 1 walls for min < y < max; caps accept x^2 + z^2 <= |y| (shape.rs:584), i.e. radius
     //                   sqrt(|y|) — the box takes the larger of the two; needs finite min and max
-    //   cone, plane   : no box (the cone's a ~ 0 branch reports an intersection without a y-range check, shape.rs:363-368)
-    // The cube's check_axis treats |direction| < EPSILON as parallel (shape.rs:593-599), which reports intersections
-    // that drift outside the true cube by up to t * EPSILON; for cubes the box is therefore only used when all three
-    // object-space direction components are clearly >= EPSILON, which the walker decides in f32 from m32 and k.
-    void reject_box(const rtc_shape_desc& s, DPrim& p) {
+    //   cone, plane   : never clustered (the cone's a ~ 0 branch reports an intersection without a y-range check,
+    //                   shape.rs:363-368)
+    // The cube's check_axis treats |direction| < EPSILON as parallel (shape.rs:593-599) and then reports intersections that
+    // have drifted up to EPSILON * t outside the true cube along that axis: a cube's box is padded by EPSILON * (the longest
+    // ray the fast path admits) * (its largest column norm).
+    static constexpr uint32_t kClusterMin = 5;     // fewer bounded siblings are cheaper to test outright (hexagon: 2 per group)
+    static constexpr double kClusterReachR = 8.0;  // fast path: rays that start within 8 R + 10 of the cluster's centre
+    static constexpr double kClusterReachAdd = 10.0;
+    static constexpr double kClusterMaxScale = 5000.0;
+    struct ClusterItem {
+        DPrim prim;
+        uint32_t shape;
+        double lo[3], hi[3];
+        double scale;  // cubes: largest column norm of the transform's 3x3; others: 0 (no EPSILON drift)
+    };
+    // world box of a bounded leaf; false: not bounded (or not finite) — stays a PRIM entry
+    bool leaf_world_box(const rtc_shape_desc& s, ClusterItem& it) const {
         double r = 1.0, ylo = -1.0, yhi = 1.0;
         if (s.kind == RTC_SPHERE || s.kind == RTC_CUBE) {
         } else if (s.kind == RTC_CYLINDER && std::isfinite(s.minimum) && std::isfinite(s.maximum)) {
@@ -300,54 +316,115 @@ class Flattener {
             yhi = std::fmax(s.minimum, s.maximum);
             if (s.capped) r = std::fmax(1.0, std::sqrt(std::fmax(std::fabs(s.minimum), std::fabs(s.maximum))));
         } else {
-            return;
+            return false;
         }
         const rtc_transform_desc& td = d_.transforms[s.transform];
         const Mat4 t = Mat4::from(td.transform);
-        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, mag = 0.;
+        for (int a = 0; a < 3; a++) {
+            it.lo[a] = 1e300;
+            it.hi[a] = -1e300;
+        }
         for (int c = 0; c < 8; c++) {
             Vec4 w = mul(t, point((c & 1) ? r : -r, (c & 2) ? yhi : ylo, (c & 4) ? r : -r));
             const double v[3] = {w.x, w.y, w.z};
             for (int a = 0; a < 3; a++) {
-                if (!std::isfinite(v[a])) return;
-                lo[a] = std::fmin(lo[a], v[a]);
-                hi[a] = std::fmax(hi[a], v[a]);
-                mag = std::fmax(mag, std::fabs(v[a]));
+                if (!std::isfinite(v[a]) || std::fabs(v[a]) > 1e30) return false;
+                it.lo[a] = std::fmin(it.lo[a], v[a]);
+                it.hi[a] = std::fmax(it.hi[a], v[a]);
             }
         }
-        const double pad = 1e-7 * std::fmax(mag, 1e-30);
-        for (int a = 0; a < 3; a++) {
-            p.blo[a] = detail::f32_below(lo[a] - pad);
-            p.bhi[a] = detail::f32_above(hi[a] + pad);
-            out_.reject_extent = std::fmax(out_.reject_extent, std::fmax(std::fabs(p.blo[a]), std::fabs(p.bhi[a])));
-        }
-        p.reject = (s.kind == RTC_CUBE) ? 2 : 1;
-        bool diagonal = true;
-        for (int a = 0; a < 3; a++) {
-            double l1 = 0.;
+        it.scale = 0.;
+        if (s.kind == RTC_CUBE) {
             for (int c = 0; c < 3; c++) {
-                p.m32[a * 3 + c] = (float)td.inverse[a * 4 + c];
-                l1 += std::fabs(td.inverse[a * 4 + c]);
-                if (a != c && td.inverse[a * 4 + c] != 0.0) diagonal = false;
+                const double x = td.transform[c], y = td.transform[4 + c], z = td.transform[8 + c];
+                it.scale = std::fmax(it.scale, std::sqrt(x * x + y * y + z * z));
             }
-            // |f32 dot - exact dot| <= ~4 * 2^-24 * l1 * max|d|; k carries an 8x margin on top (2^-19)
-            p.k[a] = f32_above_(l1 * 1.9073486328125e-06);
+            if (!(it.scale <= kClusterMaxScale)) return false;
         }
-        if (opts_.diagonal_cubes && s.kind == RTC_CUBE && diagonal) {
-            // object-space direction component a is inverse[a][a] * d[a] exactly: the same bound with a single product
-            p.reject = 3;
-            const float d0 = p.m32[0], d1 = p.m32[4], d2 = p.m32[8];
-            for (int c = 0; c < 9; c++) p.m32[c] = 0.f;
-            p.m32[0] = d0; p.m32[1] = d1; p.m32[2] = d2;
-        }
+        return true;
     }
-
-    static constexpr uint32_t kRejectMinSiblings = 4;
-    uint32_t sibling_leaves(uint32_t begin, uint32_t end) const {
+    uint32_t cluster_candidates(uint32_t begin, uint32_t end) const {
         uint32_t n = 0;
+        ClusterItem tmp;
         for (uint32_t c = begin; c < end; c = end_[c])
-            if (d_.shapes[c].kind != RTC_GROUP && d_.shapes[c].kind != RTC_TRIANGLE) n++;
+            if (d_.shapes[c].kind != RTC_GROUP && d_.shapes[c].kind != RTC_TRIANGLE && leaf_world_box(d_.shapes[c], tmp)) n++;
         return n;
+    }
+    void set_site(uint32_t leaf, const LeafSite& st) {
+        if (!want_classes_) return;
+        if (sites_.size() <= leaf) sites_.resize(leaf + 1);
+        sites_[leaf] = st;
+    }
+    void emit_cluster(std::vector<ClusterItem>& run) {
+        const uint32_t n = (uint32_t)run.size();
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, smax = 0.;
+        for (const ClusterItem& it : run) {
+            for (int a = 0; a < 3; a++) {
+                lo[a] = std::fmin(lo[a], it.lo[a]);
+                hi[a] = std::fmax(hi[a], it.hi[a]);
+            }
+            smax = std::fmax(smax, it.scale);
+        }
+        double centre[3], r2 = 0.;
+        for (int a = 0; a < 3; a++) {
+            centre[a] = 0.5 * (lo[a] + hi[a]);
+            r2 += 0.25 * (hi[a] - lo[a]) * (hi[a] - lo[a]);
+        }
+        const double radius = std::sqrt(r2);
+        const double reach = kClusterReachR * radius + kClusterReachAdd;
+        // the longest fast-path ray to any point of a (padded) box: origin within `reach`, direction length within 1 %, and
+        // the pad itself (at most sqrt(3) * EPSILON * scale <= 0.09 of the length, kClusterMaxScale)
+        const double longest = 1.25 * (reach + radius);
+        std::vector<detail::Item> items(n);
+        double max_abs = 0.;
+        for (uint32_t k = 0; k < n; k++) {
+            const ClusterItem& ci = run[k];
+            const double drift = 1.0001e-5 * longest * ci.scale;
+            detail::Item& it = items[k];
+            for (int a = 0; a < 3; a++) {
+                it.lo[a] = ci.lo[a] - drift;
+                it.hi[a] = ci.hi[a] + drift;
+                it.c[a] = 0.5 * (it.lo[a] + it.hi[a]);
+                max_abs = std::fmax(max_abs, std::fmax(std::fabs(it.lo[a]), std::fabs(it.hi[a])));
+            }
+            it.id = k;
+            it.pad = 0;
+        }
+        DMesh m;
+        std::memset(&m, 0, sizeof(m));
+        m.xform = -1;
+        m.tri_base = (int32_t)out_.prims.size();
+        m.tri_count = (int32_t)n;
+        std::vector<uint32_t> order;
+        int depth = 0;
+        const double pad = kPadRel * std::fmax(max_abs, std::numeric_limits<double>::min());
+        const size_t nodes_before = out_.bvh.size();
+        m.root = build_bvh_items(items, pad, 1, out_.bvh, m.tri_base, order, &depth);
+        if (depth + 2 > kClusterStackDepth) {  // a degenerate layout (the builder bounds depth by ~log2 n otherwise)
+            out_.bvh.resize(nodes_before);
+            for (const ClusterItem& ci : run) {
+                set_site((uint32_t)ci.prim.leaf, LeafSite{ci.shape, (int32_t)out_.program.size(), (int32_t)out_.prims.size()});
+                out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, gate_node_});
+                out_.prims.push_back(ci.prim);
+            }
+            return;
+        }
+        if (depth > out_.bvh_max_depth) out_.bvh_max_depth = depth;
+        m.extent = f32_above_(max_abs * (1.0 + 2.0 * kPadRel));
+        m.cx = (float)centre[0];
+        m.cy = (float)centre[1];
+        m.cz = (float)centre[2];
+        // the device measures the origin's distance in f32 from the f32 centre: both roundings are far inside the 1.25
+        m.rfast2 = detail::f32_below(reach * reach);
+        const int32_t node = (int32_t)out_.program.size();
+        for (uint32_t slot = 0; slot < n; slot++) {
+            const ClusterItem& ci = run[order[slot]];
+            set_site((uint32_t)ci.prim.leaf, LeafSite{ci.shape, node, (int32_t)out_.prims.size()});
+            out_.prims.push_back(ci.prim);
+        }
+        out_.program.push_back(DProgramNode{NODE_CLUSTER, (int32_t)out_.meshes.size(), 0, gate_node_});
+        out_.meshes.push_back(m);
+        out_.feature_mask |= 256;
     }
 
     // ---- classes of value-equal leaves (shape.rs:638-646) -------------------------------------------------------------
@@ -460,7 +537,7 @@ class Flattener {
             if (cls[l] < 0) continue;
             const LeafSite& st = sites_[l];
             out_.class_members[fill[cls[l]]++] = DClassMember{st.node, st.slot};
-            if (out_.program[st.node].type == NODE_PRIM) out_.prims[st.slot].cls = cls[l];
+            if (out_.program[st.node].type != NODE_MESH) out_.prims[st.slot].cls = cls[l];
             else out_.tris[st.slot].cls = cls[l];
         }
     }
@@ -472,7 +549,8 @@ class Flattener {
     }
 
     void emit_children(uint32_t begin, uint32_t end) {
-        const bool boxes_pay = sibling_leaves(begin, end) > kRejectMinSiblings;
+        const bool cluster = opts_.clusters && cluster_candidates(begin, end) >= kClusterMin;
+        std::vector<ClusterItem> run;  // this parent's bounded leaves, when there are enough of them for a cluster
         uint32_t i = begin;
         while (i < end) {
             const rtc_shape_desc& s = d_.shapes[i];
@@ -485,7 +563,8 @@ class Flattener {
                 emit_mesh(i, j);
                 i = j;
             } else {
-                DPrim p;
+                ClusterItem ci;
+                DPrim& p = ci.prim;
                 std::memset(&p, 0, sizeof(p));
                 p.kind = s.kind;
                 p.material = s.material;
@@ -493,20 +572,21 @@ class Flattener {
                 p.capped = s.capped ? 1 : 0;
                 p.minimum = s.minimum;
                 p.maximum = s.maximum;
-                p.leaf = (int32_t)next_leaf_++;
-                out_.feature_mask |= 1 << s.kind;
-                // a reject box pays for itself where many siblings share one parent (a list the ray would otherwise walk
-                // in full); a couple of leaves behind a tight group gate are cheaper to test outright (measured on the
-                // hexagon scene: 12 leaves in 6 two-leaf groups — boxes cost 12 %)
-                if (boxes_pay) reject_box(s, p);
-                if (p.reject) out_.reject_prims++;
+                p.leaf = (int32_t)next_leaf_++;  // DFS order whatever the leaf's place in the tables
                 p.cls = -1;
-                if (want_classes_) sites_.push_back(LeafSite{i, (int32_t)out_.program.size(), (int32_t)out_.prims.size()});
-                out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, gate_node_});
-                out_.prims.push_back(p);
+                out_.feature_mask |= 1 << s.kind;
+                ci.shape = i;
+                if (cluster && leaf_world_box(s, ci)) {
+                    run.push_back(ci);  // hit selection is min over (t, DFS leaf): the order of the tests is free
+                } else {
+                    set_site((uint32_t)p.leaf, LeafSite{i, (int32_t)out_.program.size(), (int32_t)out_.prims.size()});
+                    out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, gate_node_});
+                    out_.prims.push_back(p);
+                }
                 i++;
             }
         }
+        if (!run.empty()) emit_cluster(run);
     }
 
     void require_identity(uint32_t i) const {
@@ -638,10 +718,10 @@ class Flattener {
             m.tri_base = -1;
             m.tri_count = (int32_t)n;
             m.extent = 0.f;
+            m.cx = m.cy = m.cz = m.rfast2 = 0.f;
             m.pad[0] = m.pad[1] = m.pad[2] = 0;
             out_.pending.push_back(p);
-            if (want_classes_)
-                for (uint32_t k = 0; k < n; k++) sites_.push_back(LeafSite{begin + k, (int32_t)out_.program.size(), -1});
+            for (uint32_t k = 0; k < n; k++) set_site(p.leaf0 + k, LeafSite{begin + k, (int32_t)out_.program.size(), -1});
             out_.program.push_back(DProgramNode{NODE_MESH, (int32_t)out_.meshes.size(), 0, gate_node_});
             out_.meshes.push_back(m);
             clock.lap(out_.phase_ms, FlatScene::T_TRIANGLES);
@@ -690,6 +770,7 @@ class Flattener {
         clock = PhaseClock();  // build_bvh booked its own phases
         if (attr_thread.joinable()) attr_thread.join();
         m.extent = f32_above_(max_abs * (1.0 + 2.0 * kPadRel));
+        m.cx = m.cy = m.cz = m.rfast2 = 0.f;
         m.pad[0] = m.pad[1] = m.pad[2] = 0;
         if (depth > out_.bvh_max_depth) out_.bvh_max_depth = depth;
         if (depth + 2 > kBvhStackDepth)
@@ -713,12 +794,8 @@ class Flattener {
             dt.cls = -1;
             out_.tri_attr[at + slot] = attr_in[k];
         }
-        if (want_classes_) {
-            const size_t s0 = sites_.size();
-            sites_.resize(s0 + n);
-            for (uint32_t slot = 0; slot < n; slot++)
-                sites_[s0 + order[slot]] = LeafSite{begin + order[slot], (int32_t)out_.program.size(), (int32_t)(at + slot)};
-        }
+        for (uint32_t slot = 0; slot < n; slot++)
+            set_site(leaf0 + order[slot], LeafSite{begin + order[slot], (int32_t)out_.program.size(), (int32_t)(at + slot)});
         clock.lap(out_.phase_ms, FlatScene::T_TRIANGLES);
         out_.program.push_back(DProgramNode{NODE_MESH, (int32_t)out_.meshes.size(), 0, gate_node_});
         out_.meshes.push_back(m);

@@ -48,6 +48,7 @@ struct MultiRenderer {
 
 void multi_destroy(MultiRenderer* m) {
     if (!m) return;
+    DeviceGuard guard_;
     for (int g = 0; g < (int)m->scene.size(); g++) {
         if (!m->scene[g]) continue;
         cudaSetDevice(device_scene_device(m->scene[g]));
@@ -63,6 +64,7 @@ void multi_destroy(MultiRenderer* m) {
 
 // Uploads the flattened scene to devices 0 .. ngpus-1.  Returns 0, -3 (CUDA, *err set) or kDeviceBuildTooDeep.
 int multi_create(const FlatScene& flat, int ngpus, MultiRenderer** out, std::string* err) {
+    DeviceGuard guard_;
     MultiRenderer* m = new MultiRenderer();
     m->n = ngpus;
     m->scene.assign(ngpus, nullptr);
@@ -101,6 +103,7 @@ static int ensure_peers(MultiRenderer* m, std::string* err) {
 // m->d_frame (device 0) or m->h_frame (pinned host); frame_ms = host wall clock from the first launch to the last byte.
 int multi_render(MultiRenderer* m, const DCamera& cam, bool to_device_frame, LaunchStats* stats, double* frame_ms,
                  std::string* err) {
+    DeviceGuard guard_;
     const size_t row_bytes = (size_t)cam.hsize * 4, frame_bytes = row_bytes * cam.vsize;
     const uint32_t nbands = (cam.vsize + kBandRows - 1) / kBandRows;
     if (to_device_frame) {

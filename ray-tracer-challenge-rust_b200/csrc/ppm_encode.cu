@@ -134,6 +134,7 @@ int ppm_encode_device(int device, const void* d_rgba8, uint64_t width, uint64_t 
         if (err) *err = cuda_err_string(what, e);
         return -3;
     };
+    DeviceGuard guard_;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail("cudaSetDevice", e);
     char header[64];

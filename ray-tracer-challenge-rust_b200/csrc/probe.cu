@@ -151,6 +151,7 @@ int probe_intersect(DeviceScene* s, const double* rays, uint64_t n, uint32_t cap
                     uint32_t* counts, std::string* err) {
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(s->mu());
+    DeviceGuard guard_;
     PROBE_CUDA(cudaSetDevice(s->device));
     Scratch d;
     const size_t slots = (size_t)n * (cap ? cap : 1);
@@ -174,6 +175,7 @@ int probe_intersect(DeviceScene* s, const double* rays, uint64_t n, uint32_t cap
 int probe_prepare(DeviceScene* s, const double* rays, uint64_t n, rtc_computations* out, std::string* err) {
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(s->mu());
+    DeviceGuard guard_;
     PROBE_CUDA(cudaSetDevice(s->device));
     Scratch d;
     PROBE_CUDA(cudaMalloc(&d.p[0], n * 48));
@@ -190,6 +192,7 @@ int probe_normal_at(DeviceScene* s, uint64_t n_tris, int32_t leaf, const double*
                     std::string* err) {
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(s->mu());
+    DeviceGuard guard_;
     PROBE_CUDA(cudaSetDevice(s->device));
     Scratch d;
     PROBE_CUDA(cudaMalloc(&d.p[0], n * 24));

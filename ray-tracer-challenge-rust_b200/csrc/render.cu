@@ -79,6 +79,7 @@ size_t slab_bytes(const std::vector<T>& v) {
 
 int enable_peer_access(int device, int peer, std::string* err) {
     if (device == peer) return 0;
+    DeviceGuard guard_;
     RTC_CUDA(cudaSetDevice(device));
     int can = 0;
     RTC_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
@@ -97,6 +98,7 @@ int enable_peer_access(int device, int peer, std::string* err) {
 
 static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
 int frame_share_create(int device, uint64_t bytes, void** d_ptr, unsigned char* handle64, std::string* err) {
+    DeviceGuard guard_;
     RTC_CUDA(cudaSetDevice(device));
     void* p = nullptr;
     RTC_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
@@ -112,6 +114,7 @@ int frame_share_create(int device, uint64_t bytes, void** d_ptr, unsigned char* 
     return 0;
 }
 int frame_share_open(int device, const unsigned char* handle64, void** d_ptr, std::string* err) {
+    DeviceGuard guard_;
     RTC_CUDA(cudaSetDevice(device));
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle64, 64);
@@ -121,6 +124,7 @@ int frame_share_open(int device, const unsigned char* handle64, void** d_ptr, st
     return 0;
 }
 int frame_share_close(int device, void* d_ptr, int owner, std::string* err) {
+    DeviceGuard guard_;
     RTC_CUDA(cudaSetDevice(device));
     if (owner) RTC_CUDA(cudaFree(d_ptr));
     else RTC_CUDA(cudaIpcCloseMemHandle(d_ptr));
@@ -181,6 +185,7 @@ static DeviceContext* context_for(int device, std::string* err) {
 }
 
 int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::string* err, int* built_depth) {
+    DeviceGuard guard_;
     DeviceContext* ctx = context_for(device, err);
     if (!ctx) return -3;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -284,8 +289,6 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->view.n_classes = f.class_offsets.empty() ? 0 : (int32_t)f.class_offsets.size() - 1;
     s->view.pad1 = 0;
     s->view.program_count = (int32_t)f.program.size();
-    s->view.reject_prims = f.reject_prims;
-    s->view.reject_extent = f.reject_extent;
     s->view.n_prims = (uint32_t)f.prims.size();
     s->view.n_xforms = (uint32_t)f.xforms.size();
     s->view.n_gates = (uint32_t)f.gates.size();
@@ -303,6 +306,7 @@ void device_scene_destroy(DeviceScene* s) {
     if (!s) return;
     {
         std::lock_guard<std::mutex> lk(s->ctx->mu);
+        DeviceGuard guard_;
         cudaSetDevice(s->device);
         // stream-ordered free: frames already queued on the library stream finish first.  Frames the caller queued on
         // its OWN stream must be synchronised by the caller before destroying the scene (see rtc_render_device).
@@ -386,6 +390,7 @@ static int launch_stats(DeviceScene* s, DQueue* queue, cudaStream_t st, LaunchSt
 int render_device(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d_rgba8, void* d_rgb_f64, void* stream,
                   LaunchStats* stats, std::string* err) {
     std::lock_guard<std::mutex> lk(s->mu());
+    DeviceGuard guard_;
     RTC_CUDA(cudaSetDevice(s->device));
     DQueue* q = nullptr;
     int rc = launch(s, cam, rows, d_rgba8, d_rgb_f64, (cudaStream_t)stream, stats != nullptr, &q, err);
@@ -398,6 +403,7 @@ int render_device(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
 int render_device_begin(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d_rgba8, void* d_rgb_f64, void* stream,
                         void** token, std::string* err) {
     std::lock_guard<std::mutex> lk(s->mu());
+    DeviceGuard guard_;
     RTC_CUDA(cudaSetDevice(s->device));
     DQueue* q = nullptr;
     const int rc = launch(s, cam, rows, d_rgba8, d_rgb_f64, stream ? (cudaStream_t)stream : s->stream, true, &q, err);
@@ -406,6 +412,7 @@ int render_device_begin(DeviceScene* s, const DCamera& cam, const DRows& rows, v
 }
 int render_device_end(DeviceScene* s, void* stream, void* token, LaunchStats* stats, std::string* err) {
     std::lock_guard<std::mutex> lk(s->mu());
+    DeviceGuard guard_;
     RTC_CUDA(cudaSetDevice(s->device));
     LaunchStats local;
     return launch_stats(s, (DQueue*)token, stream ? (cudaStream_t)stream : s->stream, stats ? stats : &local, err);
@@ -415,6 +422,7 @@ void* device_scene_stream(const DeviceScene* s) { return s->stream; }
 int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* rgba8, double* rgb_f64,
                 LaunchStats* stats, std::string* err) {
     std::lock_guard<std::mutex> lk(s->mu());
+    DeviceGuard guard_;
     RTC_CUDA(cudaSetDevice(s->device));
     const size_t px = (size_t)rows.local_rows * cam.hsize;
     if (rgba8 && s->ctx->out8_size < px * 4) {
@@ -499,6 +507,7 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* 
 int color_at_host(DeviceScene* s, const double* rays, uint64_t n, double* rgb, std::string* err) {
     std::lock_guard<std::mutex> lk(s->mu());
     if (n == 0) return 0;
+    DeviceGuard guard_;
     RTC_CUDA(cudaSetDevice(s->device));
     double *d_rays = nullptr, *d_rgb = nullptr;
     RTC_CUDA(cudaMalloc((void**)&d_rays, n * 48));
@@ -521,6 +530,7 @@ int color_at_host(DeviceScene* s, const double* rays, uint64_t n, double* rgb, s
 }
 
 int measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops, std::string* err) {
+    DeviceGuard guard_;
     RTC_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     RTC_CUDA(cudaGetDeviceProperties(&prop, device));

@@ -9,11 +9,6 @@
 #endif
 #include <cuda_runtime.h>
 
-// Instantiations without meshes are a short list of leaves: their tables (prims, transforms, gates, program, materials —
-// a few KB) are staged in SHARED memory once per persistent CTA and read from there.
-#if defined(RTC_TRY_STAGE_SMEM) && ((RTC_INST_MASK & 32) == 0)
-#define RTC_STAGE_SMEM 1
-#endif
 #include "render_launch.cuh"
 #include "rt_core.cuh"
 
@@ -31,39 +26,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
                                                                const __grid_constant__ DRows rows,
                                                                uint32_t* __restrict__ out8, double* __restrict__ out64,
                                                                DQueue* __restrict__ q) {
-#if defined(RTC_STAGE_SMEM)
-    // stage the small tables (16-byte granules) and retarget the scene's pointers; scenes too large for the buffer keep
-    // reading from global memory
-    constexpr uint32_t kStageBytes = 16 * 1024;
-    __shared__ __align__(16) unsigned char stage[kStageBytes];
-    DScene ls = s_in;
-    {
-        const uint32_t np = (uint32_t)ls.program_count * (uint32_t)sizeof(DProgramNode);
-        const uint32_t npr = ls.n_prims * (uint32_t)sizeof(DPrim), nx = ls.n_xforms * (uint32_t)sizeof(DXform);
-        const uint32_t ng = ls.n_gates * (uint32_t)sizeof(DGate), nm = ls.n_materials * (uint32_t)sizeof(DMaterial);
-        if (np + npr + nx + ng + nm <= kStageBytes) {
-            const void* src[5] = {ls.program, ls.prims, ls.xforms, ls.gates, ls.materials};
-            const uint32_t len[5] = {np, npr, nx, ng, nm};
-            uint32_t off = 0;
-            for (int t = 0; t < 5; t++) {
-                const int4* g = (const int4*)src[t];
-                int4* d = (int4*)(stage + off);
-                for (uint32_t i = threadIdx.x; i < len[t] / 16; i += blockDim.x) d[i] = g[i];
-                off += len[t];
-            }
-            __syncthreads();
-            off = 0;
-            ls.program = (const DProgramNode*)(stage + off); off += np;
-            ls.prims = (const DPrim*)(stage + off); off += npr;
-            ls.xforms = (const DXform*)(stage + off); off += nx;
-            ls.gates = (const DGate*)(stage + off); off += ng;
-            ls.materials = (const DMaterial*)(stage + off);
-        }
-    }
-    const DScene& s = ls;
-#else
     const DScene& s = s_in;
-#endif
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t tiles_x = (cam.hsize + kTileW - 1) / kTileW;
     const uint32_t tiles_y = (rows.row_count + kTileH - 1) / kTileH;
@@ -71,28 +34,20 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
     RayCounters rc;
     Tally tl;
     uint32_t primary = 0;
-    // Tile queue with optional guided batches (a warp takes up to kMaxTileBatch consecutive tiles per atomic, shrinking
-    // to one as the queue runs out).  MEASURED (profiles/r01g_tile_batch_sweep.json): batches of 4/8/16 are 1.1x-3x
-    // SLOWER on every config — neighbouring heavy tiles land on one warp and a warp's time is the sum of its tiles — and
-    // the single-address atomic is not a bottleneck (64 800 grabs per 1080p frame, < 13 % of one L2 slice), so the
-    // default is one tile per grab.
-    const uint32_t nwarps = gridDim.x * (kBlockThreads / 32);
-    uint32_t batch = ntiles / (4u * nwarps);
-    batch = batch < 1u ? 1u : (batch > kMaxTileBatch ? kMaxTileBatch : batch);
-    uint32_t tile = 0, tile_end = 0;
+    // Tile queue: one atomic per tile.  (Guided batches of 4/8/16 tiles per atomic were measured 1.1x-3x SLOWER on every
+    // config — neighbouring heavy tiles land on one warp — and the single-address atomic is < 13 % of one L2 slice:
+    // profiles/r01g_tile_batch_sweep.json.)  The NEXT tile is requested before the current one is rendered, so the
+    // atomic's round trip to L2 hides under a tile's worth of work instead of idling the warp (13 % of the teapot
+    // kernel's samples sat on the broadcast of that atomic: profiles/r01m_teapot_summary.md).
+    unsigned next = 0;
+    if (lane == 0) next = atomicAdd(&q->next_tile, 1u);
     for (;;) {
-        if (tile >= tile_end) {
-            unsigned first = 0;
-            if (lane == 0) first = atomicAdd(&q->next_tile, batch);
-            first = __shfl_sync(0xffffffffu, first, 0);
-            if (first >= ntiles) break;
-            tile = first;
-            tile_end = first + batch < ntiles ? first + batch : ntiles;
-            const uint32_t guided = (ntiles - tile_end) / (2u * nwarps);
-            batch = guided < 1u ? 1u : (guided > kMaxTileBatch ? kMaxTileBatch : guided);
-        }
+        const uint32_t tile = __shfl_sync(0xffffffffu, next, 0);
+        if (tile >= ntiles) break;
+#if !defined(RTC_NO_TILE_PREFETCH)
+        if (lane == 0) next = atomicAdd(&q->next_tile, 1u);
+#endif
         const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
-        tile++;
         const uint32_t px = tx * kTileW + (lane & (kTileW - 1));
         const uint32_t lrow = rows.row_begin + ty * kTileH + (lane / kTileW);  // row inside this call's compact output
         if (px < cam.hsize && lrow < rows.row_begin + rows.row_count) {
@@ -109,6 +64,9 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
                 out64[3 * o + 2] = c.z;
             }
         }
+#if defined(RTC_NO_TILE_PREFETCH)  // A/B switch (tools/tune_variants.py): ask for the next tile only when this one is done
+        if (lane == 0) next = atomicAdd(&q->next_tile, 1u);
+#endif
     }
     // ray counters: warp reduce, one atomic per warp and counter
     unsigned long long v[4] = {primary, rc.shadow, rc.reflect, rc.refract};

@@ -25,14 +25,11 @@ namespace rtc {
 constexpr int kBlockThreads = RTC_BLOCK_THREADS;
 constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;  // 6 -> 80 registers, 24 warps/SM: the measured optimum (profiles/r01d)
 constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
-#ifndef RTC_MAX_TILE_BATCH
-#define RTC_MAX_TILE_BATCH 1
-#endif
-constexpr uint32_t kMaxTileBatch = RTC_MAX_TILE_BATCH;
 
-// mask, in dispatch order (smallest first):  cubes + refraction (table) | spheres + cylinders + groups (hexagon) |
-// mesh + groups (teapot) | + plane (cow & teddy) | + refraction (pumpkin) | every primitive kind, no meshes | everything
-#define RTC_RENDER_INSTANCES(X) X(132) X(73) X(96) X(98) X(226) X(223) X(255)
+// mask, in dispatch order (smallest first):  clustered cubes + refraction (table) | spheres + cylinders + groups (hexagon)
+// | mesh + groups (teapot) | + plane (cow & teddy) | + refraction (pumpkin) | every primitive kind, clusters, no meshes |
+// everything
+#define RTC_RENDER_INSTANCES(X) X(388) X(73) X(96) X(98) X(226) X(479) X(511)
 
 using RenderLaunchFn = void (*)(unsigned grid, cudaStream_t stream, const DScene& s, const DCamera& cam, const DRows& rows,
                                 uint32_t* out8, double* out64, DQueue* q);

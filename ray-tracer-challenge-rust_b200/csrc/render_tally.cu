@@ -39,6 +39,7 @@ int tally_count() { return T_COUNT; }
 
 int render_tally(DeviceScene* s, const DCamera& cam, const DRows& rows, unsigned long long* counts, std::string* err) {
     std::lock_guard<std::mutex> lk(s->mu());
+    DeviceGuard guard_;
     cudaError_t e = cudaSetDevice(s->device);
     unsigned long long* d = nullptr;
     if (e == cudaSuccess) e = cudaMalloc((void**)&d, sizeof(unsigned long long) * (T_COUNT + 1));

@@ -110,7 +110,7 @@ class HostSim:
                                         _capi.c_double_p, C.POINTER(C.c_uint8), _capi.c_u64_p]
         self.lib.sim_color_at.argtypes = [vp, _capi.c_double_p, C.c_uint64, _capi.c_double_p]
 
-    def scene(self, world, device_build=False, diagonal_cubes=True):
+    def scene(self, world, device_build=False, clusters=True):
         """Marshal a product World exactly as rtc_world_scene does and flatten it for the simulation.  device_build:
         meshes go through the simulated device build (csrc/lbvh.cuh run as loops) instead of the host SAH builder."""
         api = world.api
@@ -119,7 +119,7 @@ class HostSim:
         try:
             s = C.c_void_p()
             depth = C.c_int(0)
-            rc = self.lib.sim_scene_create_ex(api.marshalled_desc(m), int(device_build) | (0 if diagonal_cubes else 2),
+            rc = self.lib.sim_scene_create_ex(api.marshalled_desc(m), int(device_build) | (0 if clusters else 2),
                                               C.byref(s), C.byref(depth))
             if rc != 0:
                 raise RuntimeError(f"hostsim {rc}: " + self.lib.sim_last_error().decode())

@@ -35,7 +35,7 @@ int sim_scene_create_ex(const rtc_scene_desc* desc, int device_build, void** out
     std::string e;
     FlattenOptions opts;
     opts.device_mesh_build = (device_build & 1) != 0;
-    opts.diagonal_cubes = (device_build & 2) == 0;  // bit 1: turn reject mode 3 (axis-aligned cubes) OFF
+    opts.clusters = (device_build & 2) == 0;  // bit 1: no clusters (every bounded leaf stays a PRIM entry)
     int rc = flatten_scene(*desc, s->flat, &e, opts);
     if (rc != RTC_OK) {
         g_err = e;
@@ -58,8 +58,6 @@ int sim_scene_create_ex(const rtc_scene_desc* desc, int device_build, void** out
     v.class_members = s->flat.class_members.data();
     v.n_classes = s->flat.class_offsets.empty() ? 0 : (int32_t)s->flat.class_offsets.size() - 1;
     v.program_count = (int32_t)s->flat.program.size();
-    v.reject_prims = s->flat.reject_prims;
-    v.reject_extent = s->flat.reject_extent;
     for (int k = 0; k < 3; k++) {
         v.light_pos[k] = s->flat.light_pos[k];
         v.light_int[k] = s->flat.light_int[k];

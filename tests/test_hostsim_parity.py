@@ -193,17 +193,17 @@ def test_general_cube_precheck_bit_exact(rtc, oracle, hostsim, name, w, h):
     world, cam = rtc.build_scene(name, w, h)
     ow, oc = helpers.scenes.build(oracle, name, w, h)
     ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
-    rgb, _, scnt = hostsim.scene(world, diagonal_cubes=False).render(cam)
+    rgb, _, scnt = hostsim.scene(world, clusters=False).render(cam)
     assert _bits_equal(ref, rgb)
     assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
 
 
 @pytest.mark.parametrize("seed", range(12))
-def test_random_worlds_bit_exact_without_diagonal_cubes(rtc, oracle, hostsim, seed):
+def test_random_worlds_bit_exact_without_clusters(rtc, oracle, hostsim, seed):
     world, cam = _wrap(rtc, *worldgen.random_world(rtc.api(), seed))
     ow, oc = worldgen.random_world(oracle, seed)
     ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
-    rgb, _, scnt = hostsim.scene(world, diagonal_cubes=False).render(cam)
+    rgb, _, scnt = hostsim.scene(world, clusters=False).render(cam)
     assert _bits_equal(ref, rgb), f"seed {seed}: {np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
     assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
 
@@ -260,3 +260,52 @@ def test_non_transitive_equality_is_refused(rtc, hostsim):
     world, cam = _wrap(rtc, *worldgen.chained_equal_world(rtc.api()))
     with pytest.raises(RuntimeError, match="not each other"):
         hostsim.scene(world)
+
+
+def _drift_world(api):
+    """Six cubes (three axis-aligned, three rotated) far apart (one cluster, radius ~ 150) and, for each, rays whose object-space x direction is
+    below EPSILON: check_axis then calls the x slab 'parallel' and decides by the ORIGIN's x alone (shape.rs:593-599), so the
+    reference reports hits for rays that have drifted out of the cube by the time they reach it."""
+    T, S = worldgen.sa.Transformations(api), worldgen.sa.Shapes(api)
+    world = worldgen.sa.WorldHandle(api, worldgen.sa.Light((0.0, 300.0, -300.0), (1.0, 1.0, 1.0)))
+    mats = []
+    for k in range(6):
+        c = S.cube()
+        m = T.translation(-150.0 + 60.0 * k, 3.0 * k, 10.0 * (k % 3))
+        if k % 2:  # a rotated cube's world box has slack; an axis-aligned one's box IS the cube — the sharp case
+            m = m * T.rotation_y(0.3 + 0.37 * k) * T.rotation_x(0.1 * k)
+        else:
+            m = m * T.scaling(1.0 + 0.5 * k, 1.0, 2.0)
+        c.set_transform(m)
+        c.material.color = (0.2 + 0.1 * k, 0.9 - 0.1 * k, 0.5)
+        c.material.ambient = 0.4
+        world.push(c)
+        mats.append(m.array().reshape(4, 4))
+    rays, drifted = [], []
+    for m in mats:
+        for dist in (150.0, 600.0, 1100.0):
+            for ox in (0.9999, -0.9999, 0.995, -0.995):
+                for lx in (2e-6, 5e-6, 9.5e-6, -2e-6, -9.5e-6, 1.5e-5):
+                    o = m @ np.array([ox, 0.3, -dist, 1.0])
+                    d = m @ np.array([lx, 0.0, 1.0, 0.0])
+                    d = d / np.linalg.norm(d[:3])
+                    rays.append(np.concatenate([o[:3], d[:3]]))
+                    x_at_cube = ox + lx * (dist - 1.0)  # object-space x where the ray reaches the front face
+                    drifted.append(abs(lx) < 1e-5 and abs(x_at_cube) > 1.0005)
+    return world, np.array(rays), np.array(drifted)
+
+
+def test_cluster_boxes_cover_the_epsilon_drift(rtc, oracle, hostsim):
+    """The cluster BVH (flatten.hpp emit_cluster) pads a cube's box by EPSILON * (longest admitted ray) * scale because the
+    reference reports 'parallel-axis' hits up to EPSILON * t outside the true cube; rays that start beyond the cluster's
+    reach take the exact linear scan.  Both must give the reference's colours, drifted hits included."""
+    w, rays, drifted = _drift_world(rtc.api())
+    world = rtc.World(_handle=w.h)
+    w.h = None
+    ow, _, _ = _drift_world(oracle)
+    ref = oracle.color_at(ow, rays)
+    assert drifted.sum() > 40 and (ref[drifted] != 0).any(axis=1).sum() > 40  # the reference does report such hits
+    scene = hostsim.scene(world)
+    assert scene.tables()[0] >= 5  # the six cubes did become a cluster (BVH nodes exist)
+    assert _bits_equal(ref, scene.color_at(rays))
+    assert _bits_equal(ref, hostsim.scene(world, clusters=False).color_at(rays))
