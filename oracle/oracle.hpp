@@ -858,11 +858,16 @@ inline Computations prepare_computations(const Intersection& self, const Ray& ra
 }
 
 // ---------------------------------------------------------------------------------------------- world.rs:11-163
-constexpr size_t RECURSION_LIMIT = 5;
+constexpr size_t RECURSION_LIMIT = 5;  // world.rs:11
 
 struct World {
     std::vector<Shape> objects;
     Light light{Tuple::point(0, 0, 0), WHITE};
+    // The reference's RECURSION_LIMIT is a `const` (world.rs:11); it is a member here so that the general-depth
+    // integrator of the CUDA path can be checked against the reference's recursion with the constant
+    // edited.  The budget is spent three units per bounce (world.rs:95, :68-69, :126/:159); a limit with limit % 3 == 1
+    // reaches shade_hit with remaining = 0 and underflows `remaining - 1` (world.rs:68: a panic in a debug build).
+    size_t recursion_limit = RECURSION_LIMIT;
 
     static World default_world() {  // world.rs:26-41
         World w;
@@ -891,6 +896,7 @@ struct World {
     }
     // world.rs:56-78   (remaining is usize: `remaining - 1` on 0 panics in debug, wraps in release)
     Color shade_hit(const Computations& comps, size_t remaining) const {
+        if (remaining == 0) throw Panic("attempt to subtract with overflow (src/world.rs:68)");
         const Shape* object = comps.object;
         const Material& material = object->material;
         if (ctx().counters) ctx().counters->shadow++;
@@ -904,7 +910,7 @@ struct World {
         }
         return surface + reflected + refracted;
     }
-    Color color_at(const Ray& ray) const { return internal_color_at(ray, RECURSION_LIMIT); }  // world.rs:80-82
+    Color color_at(const Ray& ray) const { return internal_color_at(ray, recursion_limit); }  // world.rs:80-82
     // world.rs:84-98
     Color internal_color_at(const Ray& ray, size_t remaining) const {
         if (remaining < 1) return BLACK;

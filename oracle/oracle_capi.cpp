@@ -190,6 +190,11 @@ World* orc_world_new(const double* light_pos, const double* intensity) {
 }
 World* orc_world_default() { return new World(World::default_world()); }
 void orc_world_free(World* w) { delete w; }
+// world.rs:11 with the constant edited (0 = the reference's 5)
+int orc_world_set_recursion_limit(World* w, uint32_t limit) {
+    w->recursion_limit = limit ? limit : RECURSION_LIMIT;
+    return 0;
+}
 int orc_world_push(World* w, Shape* s) {
     w->objects.push_back(std::move(*s));
     delete s;

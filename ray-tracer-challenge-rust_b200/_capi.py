@@ -106,6 +106,7 @@ class BuilderApi:
         f("world_default", vp)
         f("world_free", None, vp)
         f("world_push", C.c_int, vp, vp)
+        f("world_set_recursion_limit", C.c_int, vp, C.c_uint32)
         f("camera_new", vp, C.c_uint64, C.c_uint64, C.c_double)
         f("camera_free", None, vp)
         f("camera_set_transform", C.c_int, vp, c_double_p)

@@ -70,7 +70,6 @@ class RtcApi(BuilderApi):
         f("world_color_at", C.c_int, vp, c_double_p, C.c_uint64, c_double_p)
         f("world_scene", C.c_int, vp, C.c_int, C.POINTER(vp))
         f("world_set_build", C.c_int, vp, C.c_uint32)
-        f("world_set_recursion_limit", C.c_int, vp, C.c_uint32)
         f("world_drop_scenes", None, vp)
         f("world_describe", C.c_int, vp, c_u64_p)
         f("world_flatten_info", C.c_int, vp, c_u64_p, c_double_p, C.c_uint64)

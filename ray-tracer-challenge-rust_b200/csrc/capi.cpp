@@ -603,6 +603,7 @@ int rtc_world_flatten_info(rtc_world* w, uint64_t n[8], double* gates_out, uint6
     if (!w || !n) return set_err(RTC_ERR_INVALID, "null argument");
     Marshalled m;
     marshal_world(w->w, m);
+    m.desc.recursion_limit = w->recursion_limit;
     FlatScene flat;
     std::string e;
     int rc = flatten_scene(m.desc, flat, &e);

@@ -103,7 +103,8 @@ struct DScene {
     int32_t n_classes;
     int32_t pad1;
     int32_t program_count;
-    int32_t pad0[3];
+    int32_t recursion_limit;  // World's RECURSION_LIMIT (world.rs:11): 5 in the reference
+    int32_t pad0[2];
     uint32_t n_prims, n_xforms, n_gates, n_materials;  // table lengths (shared-memory staging)
     double light_pos[3];
     double light_int[3];
@@ -124,5 +125,7 @@ constexpr int kBvhStackDepth = 48;
 // the same for a kernel whose scenes hold clusters but no meshes (a cluster tree deeper than this is not built: its leaves
 // stay PRIM entries)
 constexpr int kClusterStackDepth = 16;
+// largest RECURSION_LIMIT the general-depth integrator accepts (six shaded generations, up to 63 shaded hits per pixel)
+constexpr int kMaxRecursionLimit = 18;
 
 }  // namespace rtc

@@ -41,7 +41,8 @@ struct FlatScene {
     std::vector<DClassMember> class_members;
     double light_pos[3] = {0, 0, 0}, light_int[3] = {0, 0, 0};
     uint64_t leaf_count = 0;
-    int32_t feature_mask = 0;  // bit k: leaves of ShapeKind k; 32 meshes; 64 gates; 128 a transparent material; 256 clusters
+    int32_t recursion_limit = 5;  // world.rs:11
+    int32_t feature_mask = 0;  // bit k: leaves of ShapeKind k; 32 meshes; 64 gates; 128 a transparent material; 256 clusters; 512 a RECURSION_LIMIT other than 5
     int32_t merged_gates = 0;  // nested single-child groups whose identical box shares the parent's gate
     int bvh_max_depth = 0;
     // device-built meshes (flatten option device_mesh_build)

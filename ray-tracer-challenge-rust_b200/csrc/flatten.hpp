@@ -82,6 +82,13 @@ class Flattener {
         }
         for (const DMaterial& m : out_.materials)
             if (m.transparency != 0.0) want_classes_ = true;
+        // RECURSION_LIMIT (world.rs:11) as a parameter: the budget is spent three units per bounce, and a limit with
+        // limit % 3 == 1 arrives at shade_hit with remaining = 0, whose `remaining - 1` underflows (world.rs:68)
+        const uint32_t limit = d_.recursion_limit ? d_.recursion_limit : 5u;
+        if (limit % 3 == 1) fail(RTC_ERR_PANIC, "attempt to subtract with overflow (src/world.rs:68): RECURSION_LIMIT % 3 == 1");
+        if (limit > (uint32_t)kMaxRecursionLimit) fail(RTC_ERR_UNSUPPORTED, "RECURSION_LIMIT above 18");
+        out_.recursion_limit = (int32_t)limit;
+        if (limit != 5) out_.feature_mask |= 512;
         clock.lap(out_.phase_ms, FlatScene::T_VALIDATE);
         emit_children(0, d_.shape_count);  // World.objects in order (world.rs:46-50)
         out_.leaf_count = next_leaf_;

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(kBlockThreads) color_at_kernel(const __grid_co
     Ray r{v3(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]), v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};
     RayCounters rc;
     Tally tl;
-    V3 c = color_at<FEAT_ALL>(s, r, rc, tl);
+    V3 c = color_at_any(s, r, rc, tl);
     rgb[3 * i + 0] = c.x;
     rgb[3 * i + 1] = c.y;
     rgb[3 * i + 2] = c.z;
@@ -289,6 +289,7 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->view.n_classes = f.class_offsets.empty() ? 0 : (int32_t)f.class_offsets.size() - 1;
     s->view.pad1 = 0;
     s->view.program_count = (int32_t)f.program.size();
+    s->view.recursion_limit = f.recursion_limit;
     s->view.n_prims = (uint32_t)f.prims.size();
     s->view.n_xforms = (uint32_t)f.xforms.size();
     s->view.n_gates = (uint32_t)f.gates.size();

@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
             const uint32_t py = (rows.band_first + band * rows.band_stride) * rows.band_rows + (lrow % rows.band_rows);
             const Ray ray = ray_for_pixel(cam, px, py);
             primary++;
-            const V3 c = color_at<kFeatures>(s, ray, rc, tl);
+            V3 c;
+            if constexpr (kFeatures & FEAT_DEPTH) c = color_at_general<kFeatures & FEAT_ALL>(s, ray, rc, tl);
+            else c = color_at<kFeatures>(s, ray, rc, tl);
             const size_t o = (size_t)(rows.frame_layout ? py : lrow) * cam.hsize + px;
             if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
             if (out64) {

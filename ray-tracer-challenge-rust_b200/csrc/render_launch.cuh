@@ -28,8 +28,8 @@ constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
 
 // mask, in dispatch order (smallest first):  clustered cubes + refraction (table) | spheres + cylinders + groups (hexagon)
 // | mesh + groups (teapot) | + plane (cow & teddy) | + refraction (pumpkin) | every primitive kind, clusters, no meshes |
-// everything
-#define RTC_RENDER_INSTANCES(X) X(388) X(73) X(96) X(98) X(226) X(479) X(511)
+// everything | everything with the general-depth integrator (a RECURSION_LIMIT other than the reference's 5)
+#define RTC_RENDER_INSTANCES(X) X(388) X(73) X(96) X(98) X(226) X(479) X(511) X(1023)
 
 using RenderLaunchFn = void (*)(unsigned grid, cudaStream_t stream, const DScene& s, const DCamera& cam, const DRows& rows,
                                 uint32_t* out8, double* out64, DQueue* q);

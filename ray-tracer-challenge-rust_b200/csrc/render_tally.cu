@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128) tally_kernel(const __grid_constant__ DSce
         const uint32_t px = (uint32_t)(i % cam.hsize), lrow = (uint32_t)(i / cam.hsize);
         const uint32_t band = lrow / rows.band_rows;
         const uint32_t py = (rows.band_first + band * rows.band_stride) * rows.band_rows + (lrow % rows.band_rows);
-        V3 c = color_at<FEAT_ALL>(s, ray_for_pixel(cam, px, py), rc, tl);
+        V3 c = color_at_any(s, ray_for_pixel(cam, px, py), rc, tl);
         if (c.x == -12345.678) out[T_COUNT] = 1;  // keep the colour computation alive
     }
     for (int k = 0; k < T_COUNT; k++) {

@@ -272,6 +272,11 @@ class WorldHandle:
             raise ValueError(self.api.error())
         shape.h = None
 
+    def set_recursion_limit(self, limit):
+        """world.rs:11 RECURSION_LIMIT for this world (0 = the reference's 5)."""
+        if self.api.world_set_recursion_limit(self.h, int(limit)) != 0:
+            raise ValueError(self.api.error())
+
     def __del__(self):
         if getattr(self, "h", None) is not None:
             self.api.world_free(self.h)

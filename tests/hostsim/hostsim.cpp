@@ -58,6 +58,7 @@ int sim_scene_create_ex(const rtc_scene_desc* desc, int device_build, void** out
     v.class_members = s->flat.class_members.data();
     v.n_classes = s->flat.class_offsets.empty() ? 0 : (int32_t)s->flat.class_offsets.size() - 1;
     v.program_count = (int32_t)s->flat.program.size();
+    v.recursion_limit = s->flat.recursion_limit;
     for (int k = 0; k < 3; k++) {
         v.light_pos[k] = s->flat.light_pos[k];
         v.light_int[k] = s->flat.light_int[k];
@@ -124,7 +125,7 @@ int sim_render(void* scene, const rtc_camera_desc* cam, const uint32_t* pixel_xy
                 }
                 Ray r = ray_for_pixel(dc, x, y);
                 Tally tl;
-                V3 c = color_at<FEAT_ALL>(s->view, r, rcs[tid], tl);
+                V3 c = color_at_any(s->view, r, rcs[tid], tl);
                 if (out_rgb) {
                     out_rgb[3 * i] = c.x;
                     out_rgb[3 * i + 1] = c.y;
@@ -160,7 +161,7 @@ int sim_color_at(void* scene, const double* rays, uint64_t n, double* rgb) {
     for (uint64_t i = 0; i < n; i++) {
         Ray r{v3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};
         Tally tl;
-        V3 c = color_at<FEAT_ALL>(s->view, r, rc, tl);
+        V3 c = color_at_any(s->view, r, rc, tl);
         rgb[3 * i] = c.x;
         rgb[3 * i + 1] = c.y;
         rgb[3 * i + 2] = c.z;

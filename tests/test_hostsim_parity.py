@@ -309,3 +309,50 @@ def test_cluster_boxes_cover_the_epsilon_drift(rtc, oracle, hostsim):
     assert scene.tables()[0] >= 5  # the six cubes did become a cluster (BVH nodes exist)
     assert _bits_equal(ref, scene.color_at(rays))
     assert _bits_equal(ref, hostsim.scene(world, clusters=False).color_at(rays))
+
+
+@pytest.mark.parametrize("limit", [2, 3, 6, 8, 9, 12])
+@pytest.mark.parametrize("name,w,h", [("table", 96, 54), ("pumpkin", 48, 27)])
+def test_general_depth_bit_exact(rtc, oracle, hostsim, name, w, h, limit):
+    """RECURSION_LIMIT (world.rs:11) as a parameter.  The iterative integrator with its explicit frame stack
+    (rt_core.cuh color_at_general) against the reference's recursion with the constant edited: 2-3 = surfaces only, 6 =
+    the reference's picture with the last generation's secondary rays counted, 8-9 = two bounces (binary branching at
+    every glass hit), 12 = three.  Pixels and ray counts, bit for bit."""
+    world, cam = rtc.build_scene(name, w, h)
+    world.set_recursion_limit(limit)
+    ow, oc = helpers.scenes.build(oracle, name, w, h)
+    ow.set_recursion_limit(limit)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    rgb, _, scnt = hostsim.scene(world).render(cam)
+    assert _bits_equal(ref, rgb), f"{np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+    if limit >= 8:
+        base, _ = oracle.render(helpers.scenes.build(oracle, name, w, h)[0], oc, mode=oracle.CACHED)
+        assert not _bits_equal(base, ref)  # a second bounce is visible in these scenes
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_general_depth_random_worlds_bit_exact(rtc, oracle, hostsim, seed):
+    world, cam = _wrap(rtc, *worldgen.random_world(rtc.api(), seed))
+    ow, oc = worldgen.random_world(oracle, seed)
+    limit = (8, 9, 11, 6, 3, 12)[seed]
+    world.set_recursion_limit(limit)
+    ow.set_recursion_limit(limit)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    rgb, _, scnt = hostsim.scene(world).render(cam)
+    assert _bits_equal(ref, rgb), f"seed {seed}: {np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+
+
+def test_recursion_limits_the_reference_cannot_run(rtc, hostsim):
+    """limit % 3 == 1 reaches shade_hit with remaining = 0: `remaining - 1` underflows usize (world.rs:68)."""
+    for limit in (1, 4, 7, 10):
+        world, cam = rtc.build_scene("hexagon", 16, 8)
+        world.set_recursion_limit(limit)
+        with pytest.raises(rtc.RtcError) as e:
+            world.flatten_info()
+        assert e.value.code == rtc.RTC_ERR_PANIC and "world.rs:68" in e.value.message
+    world.set_recursion_limit(20)
+    with pytest.raises(rtc.RtcError) as e:
+        world.flatten_info()
+    assert e.value.code == rtc.RTC_ERR_UNSUPPORTED
