@@ -133,7 +133,7 @@ static int flatten_and_upload(const rtc_scene_desc* desc, uint32_t flags, const 
         FlattenOptions opts;
         opts.device_mesh_build = (flags & RTC_BUILD_DEVICE_LBVH) && attempt == 0;
         static const bool no_clusters = std::getenv("RTC_B200_NO_CLUSTERS") != nullptr;  // A/B switch (profiles/r02)
-        opts.clusters = !no_clusters;
+        opts.clusters = opts.clusters && !no_clusters;
         // the device build's input arrays are megabytes: keep their pages across calls on this thread instead of
         // faulting fresh ones in every time (a third of the gather time of a 10 k-triangle mesh)
         thread_local std::vector<rtc_triangle_desc> keep_tri;

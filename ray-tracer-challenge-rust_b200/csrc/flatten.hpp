@@ -357,6 +357,12 @@ class Flattener {
             if (d_.shapes[c].kind != RTC_GROUP && d_.shapes[c].kind != RTC_TRIANGLE && leaf_world_box(d_.shapes[c], tmp)) n++;
         return n;
     }
+    void push_prim(const DPrim& p, const DBox32* box = nullptr) {
+        DBox32 b;
+        std::memset(&b, 0, sizeof(b));
+        out_.prims.push_back(p);
+        out_.prim_boxes.push_back(box ? *box : b);
+    }
     void set_site(uint32_t leaf, const LeafSite& st) {
         if (!want_classes_) return;
         if (sites_.size() <= leaf) sites_.resize(leaf + 1);
@@ -402,21 +408,7 @@ class Flattener {
         m.xform = -1;
         m.tri_base = (int32_t)out_.prims.size();
         m.tri_count = (int32_t)n;
-        std::vector<uint32_t> order;
-        int depth = 0;
         const double pad = kPadRel * std::fmax(max_abs, std::numeric_limits<double>::min());
-        const size_t nodes_before = out_.bvh.size();
-        m.root = build_bvh_items(items, pad, 1, out_.bvh, m.tri_base, order, &depth);
-        if (depth + 2 > kClusterStackDepth) {  // a degenerate layout (the builder bounds depth by ~log2 n otherwise)
-            out_.bvh.resize(nodes_before);
-            for (const ClusterItem& ci : run) {
-                set_site((uint32_t)ci.prim.leaf, LeafSite{ci.shape, (int32_t)out_.program.size(), (int32_t)out_.prims.size()});
-                out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, gate_node_});
-                out_.prims.push_back(ci.prim);
-            }
-            return;
-        }
-        if (depth > out_.bvh_max_depth) out_.bvh_max_depth = depth;
         m.extent = f32_above_(max_abs * (1.0 + 2.0 * kPadRel));
         m.cx = (float)centre[0];
         m.cy = (float)centre[1];
@@ -424,10 +416,40 @@ class Flattener {
         // the device measures the origin's distance in f32 from the f32 centre: both roundings are far inside the 1.25
         m.rfast2 = detail::f32_below(reach * reach);
         const int32_t node = (int32_t)out_.program.size();
-        for (uint32_t slot = 0; slot < n; slot++) {
-            const ClusterItem& ci = run[order[slot]];
-            set_site((uint32_t)ci.prim.leaf, LeafSite{ci.shape, node, (int32_t)out_.prims.size()});
-            out_.prims.push_back(ci.prim);
+        if (n <= (uint32_t)kClusterListMax) {  // a LIST: leaves in DFS order, each with its padded box
+            m.root = -1;
+            for (uint32_t k = 0; k < n; k++) {
+                const ClusterItem& ci = run[k];
+                DBox32 b;
+                std::memset(&b, 0, sizeof(b));
+                for (int a = 0; a < 3; a++) {
+                    b.lo[a] = detail::f32_below(items[k].lo[a] - pad);
+                    b.hi[a] = detail::f32_above(items[k].hi[a] + pad);
+                }
+                set_site((uint32_t)ci.prim.leaf, LeafSite{ci.shape, node, (int32_t)out_.prims.size()});
+                push_prim(ci.prim, &b);
+            }
+        } else {
+            std::vector<uint32_t> order;
+            int depth = 0;
+            const size_t nodes_before = out_.bvh.size();
+            m.root = build_bvh_items(items, pad, 1, out_.bvh, m.tri_base, order, &depth);
+            if (depth + 2 > kClusterStackDepth) {  // a degenerate layout (the builder bounds depth by ~log2 n otherwise)
+                out_.bvh.resize(nodes_before);
+                for (const ClusterItem& ci : run) {
+                    set_site((uint32_t)ci.prim.leaf, LeafSite{ci.shape, (int32_t)out_.program.size(), (int32_t)out_.prims.size()});
+                    out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, gate_node_});
+                    push_prim(ci.prim);
+                }
+                return;
+            }
+            if (depth > out_.bvh_max_depth) out_.bvh_max_depth = depth;
+            out_.feature_mask |= 1024;
+            for (uint32_t slot = 0; slot < n; slot++) {
+                const ClusterItem& ci = run[order[slot]];
+                set_site((uint32_t)ci.prim.leaf, LeafSite{ci.shape, node, (int32_t)out_.prims.size()});
+                push_prim(ci.prim);
+            }
         }
         out_.program.push_back(DProgramNode{NODE_CLUSTER, (int32_t)out_.meshes.size(), 0, gate_node_});
         out_.meshes.push_back(m);
@@ -588,7 +610,7 @@ class Flattener {
                 } else {
                     set_site((uint32_t)p.leaf, LeafSite{i, (int32_t)out_.program.size(), (int32_t)out_.prims.size()});
                     out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, gate_node_});
-                    out_.prims.push_back(p);
+                    push_prim(p);
                 }
                 i++;
             }

@@ -34,19 +34,15 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
     RayCounters rc;
     Tally tl;
     uint32_t primary = 0;
-    // Tile queue: one atomic per tile.  (Guided batches of 4/8/16 tiles per atomic were measured 1.1x-3x SLOWER on every
-    // config — neighbouring heavy tiles land on one warp — and the single-address atomic is < 13 % of one L2 slice:
-    // profiles/r01g_tile_batch_sweep.json.)  The NEXT tile is requested before the current one is rendered, so the
-    // atomic's round trip to L2 hides under a tile's worth of work instead of idling the warp (13 % of the teapot
-    // kernel's samples sat on the broadcast of that atomic: profiles/r01m_teapot_summary.md).
-    unsigned next = 0;
-    if (lane == 0) next = atomicAdd(&q->next_tile, 1u);
+    // Tile queue: one atomic per tile.  Measured and rejected: guided batches of 4/8/16 tiles per atomic (1.1x-3x slower on
+    // every config — neighbouring heavy tiles land on one warp; profiles/r01g_tile_batch_sweep.json) and requesting the
+    // NEXT tile before rendering the current one to hide the atomic's round trip (4-8 % slower on every config: the
+    // pending result holds a register across the whole tile; profiles/r02c_variants.json).
     for (;;) {
-        const uint32_t tile = __shfl_sync(0xffffffffu, next, 0);
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(&q->next_tile, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) break;
-#if !defined(RTC_NO_TILE_PREFETCH)
-        if (lane == 0) next = atomicAdd(&q->next_tile, 1u);
-#endif
         const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
         const uint32_t px = tx * kTileW + (lane & (kTileW - 1));
         const uint32_t lrow = rows.row_begin + ty * kTileH + (lane / kTileW);  // row inside this call's compact output
@@ -66,9 +62,6 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
                 out64[3 * o + 2] = c.z;
             }
         }
-#if defined(RTC_NO_TILE_PREFETCH)  // A/B switch (tools/tune_variants.py): ask for the next tile only when this one is done
-        if (lane == 0) next = atomicAdd(&q->next_tile, 1u);
-#endif
     }
     // ray counters: warp reduce, one atomic per warp and counter
     unsigned long long v[4] = {primary, rc.shadow, rc.reflect, rc.refract};

@@ -27,9 +27,10 @@ constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;  // 6 -> 80 registers, 24 warps/
 constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
 
 // mask, in dispatch order (smallest first):  clustered cubes + refraction (table) | spheres + cylinders + groups (hexagon)
-// | mesh + groups (teapot) | + plane (cow & teddy) | + refraction (pumpkin) | every primitive kind, clusters, no meshes |
+// | mesh + groups (teapot) | + plane (cow & teddy) | + refraction (pumpkin) | every primitive kind, clusters (lists and
+// trees), no meshes |
 // everything | everything with the general-depth integrator (a RECURSION_LIMIT other than the reference's 5)
-#define RTC_RENDER_INSTANCES(X) X(388) X(73) X(96) X(98) X(226) X(479) X(511) X(1023)
+#define RTC_RENDER_INSTANCES(X) X(388) X(73) X(96) X(98) X(226) X(1503) X(1535) X(2047)
 
 using RenderLaunchFn = void (*)(unsigned grid, cudaStream_t stream, const DScene& s, const DCamera& cam, const DRows& rows,
                                 uint32_t* out8, double* out64, DQueue* q);

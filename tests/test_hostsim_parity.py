@@ -306,7 +306,7 @@ def test_cluster_boxes_cover_the_epsilon_drift(rtc, oracle, hostsim):
     ref = oracle.color_at(ow, rays)
     assert drifted.sum() > 40 and (ref[drifted] != 0).any(axis=1).sum() > 40  # the reference does report such hits
     scene = hostsim.scene(world)
-    assert scene.tables()[0] >= 5  # the six cubes did become a cluster (BVH nodes exist)
+    assert scene.tables()[2] == 1  # the six cubes did become one cluster
     assert _bits_equal(ref, scene.color_at(rays))
     assert _bits_equal(ref, hostsim.scene(world, clusters=False).color_at(rays))
 
@@ -356,3 +356,37 @@ def test_recursion_limits_the_reference_cannot_run(rtc, hostsim):
     with pytest.raises(rtc.RtcError) as e:
         world.flatten_info()
     assert e.value.code == rtc.RTC_ERR_UNSUPPORTED
+
+
+def _many_leaves_world(api, seed, n=48):
+    """n bounded leaves (cubes, spheres, capped cylinders; some glass, some mirrors) side by side at World level — more than
+    kClusterListMax, so the cluster is a BVH (device_scene.h) — plus a floor plane that stays a PRIM entry."""
+    rng = np.random.default_rng(500 + seed)
+    T, S = worldgen.sa.Transformations(api), worldgen.sa.Shapes(api)
+    cam = worldgen.sa.CameraHandle(api, 56, 40, 0.9)
+    cam.set_transform(T.view_transform((0.0, 6.0, -14.0), (0.0, 0.5, 0.0), (0.0, 1.0, 0.0)))
+    world = worldgen.sa.WorldHandle(api, worldgen.sa.Light((-6.0, 12.0, -10.0), (1.0, 1.0, 0.95)))
+    floor = S.plane()
+    floor.set_transform(T.translation(0, -1.0, 0))
+    floor.material = worldgen._rand_material(T, rng, allow_glass=False)
+    world.push(floor)
+    for _ in range(n):
+        k = rng.integers(0, 3)
+        leaf = S.cube() if k == 0 else (S.sphere() if k == 1 else S.cylinder(-1.0, 1.0, True))
+        leaf.set_transform(T.translation(rng.uniform(-8, 8), rng.uniform(-0.5, 3.0), rng.uniform(-6, 8)) *
+                           T.rotation_y(rng.uniform(0, 3)) * T.scaling(*(rng.uniform(0.2, 0.9, 3))))
+        leaf.material = worldgen._rand_material(T, rng)
+        world.push(leaf)
+    return world, cam
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_large_cluster_is_a_tree_bit_exact(rtc, oracle, hostsim, seed):
+    world, cam = _wrap(rtc, *_many_leaves_world(rtc.api(), seed))
+    ow, oc = _many_leaves_world(oracle, seed)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    scene = hostsim.scene(world)
+    assert scene.tables()[0] >= 40 and scene.tables()[2] == 1  # one cluster, with BVH nodes
+    rgb, _, scnt = scene.render(cam)
+    assert _bits_equal(ref, rgb), f"{np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
