@@ -330,6 +330,11 @@ void rtc_marshalled_free(rtc_marshalled* m);
  *                transforms}; gates_out (nullable) receives the gate boxes, 6 doubles each (lo xyz, hi xyz). */
 int rtc_world_describe(rtc_world* w, uint64_t n[5]);
 int rtc_world_flatten_info(rtc_world* w, uint64_t n[8], double* gates_out, uint64_t gates_cap);
+/* features = {what the flattened world contains, what the render kernel instantiation chosen for it is compiled for}, both
+ * as bit masks: 1 spheres, 2 planes, 4 cubes, 8 cylinders, 16 cones, 32 triangle meshes, 64 groups, 128 a transparent
+ * material, 256 clusters of bounded sibling leaves, 512 a RECURSION_LIMIT other than 5, 1024 a cluster large enough to be
+ * a tree.  The second covers the first; equal masks mean the world has a kernel of its own (reports and tests). */
+int rtc_world_kernel_features(rtc_world* w, uint32_t features[2]);
 
 /* camera.rs:16-46 */
 rtc_camera* rtc_camera_new(uint64_t hsize, uint64_t vsize, double field_of_view);

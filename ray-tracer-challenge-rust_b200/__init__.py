@@ -189,6 +189,12 @@ class World(WorldHandle):
             info["gate_boxes"] = g
         return info
 
+    def kernel_features(self):
+        """(feature mask of the flattened world, feature mask of the render kernel instantiation chosen for it)."""
+        f = (C.c_uint32 * 2)()
+        self.api.check(self.api.world_kernel_features(self.h, f))
+        return int(f[0]), int(f[1])
+
 
 class Camera(CameraHandle):
     """Camera (camera.rs:5-79); render() is the drop-in for camera.rs:67-79."""

@@ -73,6 +73,7 @@ class RtcApi(BuilderApi):
         f("world_drop_scenes", None, vp)
         f("world_describe", C.c_int, vp, c_u64_p)
         f("world_flatten_info", C.c_int, vp, c_u64_p, c_double_p, C.c_uint64)
+        f("world_kernel_features", C.c_int, vp, C.POINTER(C.c_uint32))
         f("world_marshal", C.c_int, vp, C.POINTER(vp))
         f("marshalled_desc", vp, vp)
         f("marshalled_free", None, vp)

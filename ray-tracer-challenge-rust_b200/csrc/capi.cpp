@@ -624,6 +624,19 @@ int rtc_world_flatten_info(rtc_world* w, uint64_t n[8], double* gates_out, uint6
         }
     return RTC_OK;
 }
+int rtc_world_kernel_features(rtc_world* w, uint32_t features[2]) {
+    if (!w || !features) return set_err(RTC_ERR_INVALID, "null argument");
+    Marshalled m;
+    marshal_world(w->w, m);
+    m.desc.recursion_limit = w->recursion_limit;
+    FlatScene flat;
+    std::string e;
+    int rc = flatten_scene(m.desc, flat, &e);
+    if (rc != RTC_OK) return set_err(rc, e);
+    features[0] = (uint32_t)flat.feature_mask;
+    features[1] = (uint32_t)render_instance_mask(flat.feature_mask);
+    return RTC_OK;
+}
 int rtc_world_color_at(rtc_world* w, const double* rays, uint64_t n, double* rgb_out) {
     if (!w) return set_err(RTC_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(w->mu);  // the scene cannot be dropped under the call

@@ -100,7 +100,8 @@ class Flattener {
             out_.device_tris += p.n;
             out_.device_nodes += p.n - 1;
         }
-        if (!out_.meshes.empty()) out_.feature_mask |= 32;
+        for (const DMesh& m : out_.meshes)
+            if (m.xform >= 0) out_.feature_mask |= 32;  // a cluster is a DMesh too (xform -1): not a triangle run
         if (!out_.gates.empty()) out_.feature_mask |= 64;
         for (const DMaterial& m : out_.materials)
             if (m.transparency != 0.0) out_.feature_mask |= 128;

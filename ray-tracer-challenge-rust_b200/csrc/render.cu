@@ -18,6 +18,26 @@
 #include "rt_core.cuh"
 
 namespace rtc {
+// The smallest instantiation whose feature mask covers the scene's (render_launch.cuh lists them smallest first; the
+// last one covers everything).
+namespace {
+struct RenderInstance {
+    int mask;
+    RenderLaunchFn fn;
+};
+RenderInstance pick_instance(int feature_mask) {
+    static const RenderInstance kInstances[] = {
+#define RTC_TABLE_ENTRY(mask) {mask, launch_render_##mask},
+        RTC_RENDER_INSTANCES(RTC_TABLE_ENTRY)
+#undef RTC_TABLE_ENTRY
+    };
+    for (const RenderInstance& inst : kInstances)
+        if ((inst.mask & feature_mask) == feature_mask) return inst;
+    return RenderInstance{-1, nullptr};
+}
+}  // namespace
+int render_instance_mask(int feature_mask) { return pick_instance(feature_mask).mask; }
+
 
 using namespace core;
 
@@ -349,21 +369,7 @@ static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
     const uint64_t cap = (uint64_t)s->sm_count * kBlocksPerSm;
     if (blocks > cap) blocks = cap;
     if (timed) RTC_CUDA(cudaEventRecord(ctx->ev0, st));
-    // the smallest instantiation whose feature mask covers the scene's (render_launch.cuh)
-    static const struct {
-        int mask;
-        RenderLaunchFn fn;
-    } kInstances[] = {
-#define RTC_TABLE_ENTRY(mask) {mask, launch_render_##mask},
-        RTC_RENDER_INSTANCES(RTC_TABLE_ENTRY)
-#undef RTC_TABLE_ENTRY
-    };
-    RenderLaunchFn fn = nullptr;
-    for (const auto& inst : kInstances)
-        if ((inst.mask & s->feature_mask) == s->feature_mask) {
-            fn = inst.fn;
-            break;
-        }
+    const RenderLaunchFn fn = pick_instance(s->feature_mask).fn;
     fn((unsigned)blocks, st, s->view, cam, rows, (uint32_t*)d8, (double*)d64, queue);
     RTC_CUDA(cudaGetLastError());
     if (timed) RTC_CUDA(cudaEventRecord(ctx->ev1, st));

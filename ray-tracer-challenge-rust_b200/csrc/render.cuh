@@ -60,6 +60,9 @@ void* multi_device_frame(const MultiRenderer* m);
 const void* multi_host_frame(const MultiRenderer* m);
 int multi_device_count(const MultiRenderer* m);
 
+// Feature mask of the render_kernel instantiation a scene with this FEAT_* mask is rendered by (render_launch.cuh); -1: none.
+int render_instance_mask(int feature_mask);
+
 // Single-ray probes (probe.cu): World::intersect's sorted list, prepare_computations of the hit, Shape::normal_at.
 int probe_intersect(DeviceScene* s, const double* rays, uint64_t n, uint32_t cap, double* t_out, int32_t* leaf_out,
                     uint32_t* counts, std::string* err);

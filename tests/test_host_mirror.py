@@ -284,3 +284,11 @@ def test_non_transitive_shape_equality_is_refused(rtc):
     with pytest.raises(rtc.RtcError) as e:
         world.flatten_info()
     assert e.value.code == rtc.RTC_ERR_UNSUPPORTED and "not each other" in e.value.message
+
+
+@pytest.mark.parametrize("name,mask", [("table", 388), ("hexagon", 73), ("teapot", 96), ("cow_teddy", 98), ("pumpkin", 226)])
+def test_each_benchmark_world_has_a_kernel_of_its_own(rtc, name, mask):
+    """The five BASELINE configs are rendered by instantiations compiled for exactly what they contain (render_launch.cuh):
+    a cluster of cubes must not count as a triangle mesh, a mesh scene must not carry the cluster code, ..."""
+    world, _ = rtc.build_scene(name, 64, 36)
+    assert world.kernel_features() == (mask, mask)
