@@ -269,7 +269,12 @@ def run_b200(args):
         kernel_ms.append(s2.device_ms)
     kernel_ms_avg = sum(kernel_ms) / len(kernel_ms)
 
-    # ---- end to end through the drop-in call: upload World, render, gather, frame -> pinned host, drop scene --------
+    # ---- end to end through the drop-in call ---------------------------------------------------------------------------
+    # e2e        = what the patched Camera::render does per call (integration/reference.patch): forget the uploaded scene,
+    #              rtc_camera_render(want_f64 = 1) -> marshal the World, flatten, build the meshes, upload, render, bring
+    #              the f64 Canvas (24 B/px) AND the RGBA8 frame (4 B/px) to pinned host memory; free the canvas.
+    # e2e_rgba8  = the same without the f64 Canvas (a host that only wants the PPM): marshalled description kept,
+    #              rtc_scene_create_ex -> rtc_render into a pinned RGBA8 frame -> rtc_scene_destroy.
     api = rtc.api()
     import ctypes as C
     marshalled = C.c_void_p()
@@ -281,14 +286,13 @@ def run_b200(args):
 
     e2e_flags = rtc.RTC_BUILD_DEVICE_LBVH if args.e2e_build == "device" else rtc.RTC_BUILD_HOST_SAH
     e2e_h2d = [0]
+    world.set_build(args.e2e_build)
 
-    def e2e_step():
+    def e2e_rgba8_step():
         scene = C.c_void_p()
         api.check(api.scene_create_ex(desc, local_rank, e2e_flags, C.byref(scene)))
         e2e_h2d[0] = int(api.scene_upload_bytes(scene))
         if world_size == 1:
-            # the drop-in call itself: rtc_render with a HOST (pinned) output buffer — it renders in two chunks and
-            # overlaps the first chunk's device->host copy with the second chunk's kernel
             api.check(api.render(scene, C.byref(cdesc), None, C.c_void_p(host_frame.data_ptr()), None, None))
         else:
             frame = renderer.render(scene=scene)
@@ -297,17 +301,72 @@ def run_b200(args):
             torch.cuda.synchronize()
         api.scene_destroy(scene)
 
-    for _ in range(max(args.warmup, 3)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    canvas_box = [None]
+
+    def e2e_step():
+        world.drop_scenes()
+        if world_size == 1:
+            canvas_box[0] = None  # rtc_canvas_free of the previous step's canvas (its pinned pages go back to the pool)
+            canvas_box[0] = cam.render(world, want_f64=True, device=local_rank)
+        else:
+            # one process per GPU: every rank marshals + uploads its replica, renders its bands into rank 0's frame
+            frame = renderer.render(scene=world.scene(local_rank))
+            if rank == 0:
+                host_frame.copy_(frame, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def timed(step):
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    e2e8_s = timed(e2e_rgba8_step)
+    e2e_s = timed(e2e_step)
+    if world_size == 1:  # the drop-in call's own frame is the one the parity check below reads
+        host_frame.copy_(torch.from_numpy(canvas_box[0].pixels_rgba8().reshape(h, w, 4)))
+        canvas_f64_bytes = 24 * w * h
+    else:
+        canvas_f64_bytes = 0
+    canvas_box[0] = None
+    world.set_build("host")
+    world.drop_scenes()
     api.marshalled_free(marshalled)
     e2e_value = total_rays * args.steps / e2e_s / 1e6
-    clocks = sampler.stop() if rank == 0 else None  # sampled across all three timed loops
+    e2e8_value = total_rays * args.steps / e2e8_s / 1e6
+    clocks = sampler.stop() if rank == 0 else None  # sampled across all timed loops
+
+    # ---- N > 1: the config north_star states its scaling target on (pumpkin 7680x4320), device-resident, same loop ------
+    pumpkin_line = None
+    if world_size > 1 and args.workload != "pumpkin" and not args.no_extras:
+        pw, ph = 7680, 4320
+        pworld, pcam = rtc.build_scene("pumpkin", pw, ph)
+        pr = multi.ShardedRenderer(pworld, pcam, rank, world_size, local_rank, args.band_rows, args.exchange)
+        pst = rtc.Stats()
+        pr.render(stats=pst)
+        prays = sum(sum_over_ranks([pst.primary_rays, pst.shadow_rays, pst.reflect_rays, pst.refract_rays]))
+        for _ in range(3):
+            pr.render()
+        barrier()
+        psteps = max(3, min(args.steps, 10))
+        pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(psteps)]
+        for a_, b_ in pev:
+            flush.zero_()
+            a_.record()
+            pr.render()
+            b_.record()
+        barrier()
+        pms = max_over_ranks(sum(a_.elapsed_time(b_) for a_, b_ in pev)) / psteps
+        pumpkin_line = {"workload": f"pumpkin {pw}x{ph}", "n_gpus": world_size, "steps": psteps, "frame_ms": pms,
+                        "value": prays / pms / 1e3, "unit": "Mrays/s", "exchange": pr.mode,
+                        "what": "same device-resident loop as `value` (CUDA events per step, L2 flushed, max over ranks)"}
+        barrier()
+        pr.close()
+        del pr, pworld, pcam
 
     if rank != 0:
         if world_size > 1:
@@ -344,6 +403,8 @@ def run_b200(args):
     except (OSError, ValueError, KeyError):
         pass
 
+    build_note = ("RTC_BUILD_DEVICE_LBVH: meshes built on the GPU per step (csrc/lbvh.cu)" if args.e2e_build == "device"
+                  else "RTC_BUILD_HOST_SAH: binned SAH on the host per step")
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -361,15 +422,19 @@ def run_b200(args):
         "sustained": {"frames": n_sustain, "frame_ms": sustained_ms, "mrays_s": total_rays / sustained_ms / 1e3,
                       "what": "back-to-back frames for about a second, no L2 flush, one device timing around all"},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "frame_ms": e2e_s / args.steps * 1e3,
-                "h2d_bytes_per_step": e2e_h2d[0], "d2h_bytes_per_step": int(4 * w * h),
-                "build": ("RTC_BUILD_DEVICE_LBVH: meshes built on the GPU per step (csrc/lbvh.cu)" if args.e2e_build == "device"
-                          else "RTC_BUILD_HOST_SAH: binned SAH on the host per step"),
-                "what": ("per step: rtc_scene_create_ex (flatten + mesh build + upload) -> rtc_render into a pinned host "
-                         "RGBA8 frame (two chunks, copy overlapped with the second kernel) -> rtc_scene_destroy; wall clock"
+                "h2d_bytes_per_step": e2e_h2d[0], "d2h_bytes_per_step": int(4 * w * h + canvas_f64_bytes),
+                "build": build_note,
+                "what": ("the drop-in call, per step: rtc_world_drop_scenes -> rtc_camera_render(want_f64 = 1) = marshal the "
+                         "World + flatten + mesh build + upload + render + f64 Canvas (24 B/px) and RGBA8 frame (4 B/px) "
+                         "to pinned host memory -> rtc_canvas_free; wall clock"
                          if world_size == 1 else
-                         "per step: rtc_scene_create_ex (flatten + mesh build + upload) -> rtc_render_device (stores into "
-                         "rank 0's frame) -> barrier -> RGBA8 frame to pinned host memory -> rtc_scene_destroy; wall "
-                         "clock, max over ranks")},
+                         "per step and rank: rtc_world_drop_scenes -> rtc_world_scene (marshal + flatten + mesh build + "
+                         "upload) -> rtc_render_device (stores into rank 0's frame over NVLink) -> completion -> RGBA8 "
+                         "frame to pinned host memory on rank 0; wall clock, max over ranks")},
+        "e2e_rgba8": {"value": e2e8_value, "unit": "Mrays/s", "frame_ms": e2e8_s / args.steps * 1e3,
+                      "h2d_bytes_per_step": e2e_h2d[0], "d2h_bytes_per_step": int(4 * w * h), "build": build_note,
+                      "what": "marshalled description kept; per step: rtc_scene_create_ex -> rtc_render into a pinned "
+                              "host RGBA8 frame (no f64 Canvas) -> rtc_scene_destroy; wall clock"},
         "gpu_launches": args.steps * 1,  # timed (device-resident) region: one render_kernel launch per frame
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -383,6 +448,9 @@ def run_b200(args):
                           "peak_fma_tflops": fma / 1e3, "algorithmic_flops": alg_flops,
                           "bvh_box_flops_not_counted": bvh_flops, "tally": tally},
     }
+
+    if pumpkin_line is not None:
+        line["pumpkin_at_n"] = pumpkin_line
 
     if not args.no_cpu_baseline and world_size == 1:
         step_px = {"table": 8, "hexagon": 2, "teapot": 64, "cow_teddy": 96, "pumpkin": 192}.get(args.workload, 32)

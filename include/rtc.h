@@ -216,7 +216,9 @@ int rtc_color_at(const rtc_scene* scene, const double* rays, uint64_t n, double*
  *                             number found, which may exceed cap.
  *   rtc_prepare_computations  Intersection::hit (src/intersection.rs:79-83) then prepare_computations
  *                             (src/intersection.rs:17-77) and Computations::schlick (:107-128) for the hit of each ray.
- *   rtc_normal_at             Shape::normal_at (src/shape.rs:466-519) of one leaf at n world points. */
+ *   rtc_normal_at             Shape::normal_at (src/shape.rs:466-519) of one leaf at n world points.  For an
+ *                             RTC_SMOOTH_TRIANGLE leaf a "point" is read as (u, v, unused): the book's normal_at(tri, point,
+ *                             intersection_with_uv(t, tri, u, v)), which ignores the point. */
 typedef struct rtc_computations {
     int32_t hit;    /* 0: no intersection with t >= 0 (everything else is zero) */
     int32_t leaf;   /* Computations.object */
@@ -285,6 +287,9 @@ int rtc_material_set_pattern_transform(rtc_material* m, const double* t16);
 /* shape.rs:52-245.  kind: RTC_SPHERE..RTC_GROUP (triangles via rtc_shape_triangle). */
 rtc_shape* rtc_shape_new(int kind, double minimum, double maximum, int capped);
 rtc_shape* rtc_shape_triangle(const double* p1, const double* p2, const double* p3);
+/* The book's smooth_triangle(p1, p2, p3, n1, n2, n3) (RTC_SMOOTH_TRIANGLE; not in the reference). */
+rtc_shape* rtc_shape_smooth_triangle(const double* p1, const double* p2, const double* p3, const double* n1, const double* n2,
+                                     const double* n3);
 void rtc_shape_free(rtc_shape* s);
 int rtc_shape_set_transform(rtc_shape* s, const double* m16);      /* shape.rs:196-218: push-down, once per node */
 int rtc_shape_set_material(rtc_shape* s, const rtc_material* m);   /* shape.rs:220-229: push-down */
@@ -297,6 +302,10 @@ rtc_shape* rtc_obj_parse_file(const char* path, uint64_t* ignored_lines);
 rtc_shape* rtc_obj_parse_str(const char* text, uint64_t len, uint64_t* ignored_lines);
 /* group{ default_group{ triangles } } for vertex/face arrays (faces 1-based, 3 per triangle) */
 rtc_shape* rtc_mesh_from_arrays(const double* verts, uint64_t nverts, const int32_t* faces, uint64_t nfaces);
+/* The same for an OBJ with `vn` records and `f v//n` faces: corner k of face f uses vertex faces[3f + k] and normal
+ * face_normals[3f + k] (both 1-based); every triangle is an RTC_SMOOTH_TRIANGLE. */
+rtc_shape* rtc_smooth_mesh_from_arrays(const double* verts, uint64_t nverts, const double* normals, uint64_t nnormals,
+                                       const int32_t* faces, const int32_t* face_normals, uint64_t nfaces);
 
 /* world.rs:18-24, 26-41 */
 rtc_world* rtc_world_new(const double* light_position3, const double* light_intensity3);

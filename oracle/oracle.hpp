@@ -346,7 +346,10 @@ struct Material {
 };
 
 // ---------------------------------------------------------------------------------------------- shape.rs / bounds.rs
-enum class Kind { Sphere, Plane, Cube, Cylinder, Cone, Group, Triangle };
+// SmoothTriangle is NOT in the reference: its scenarios are quoted, commented out, at intersection.rs:381-386 and
+// obj_file.rs:295-335.  What is restated for it is the book's definition those comments cite (The Ray Tracer Challenge,
+// ch. 15), threaded through the reference's own Shape paths: parity for this kind is UNPINNED (absent from the reference).
+enum class Kind { Sphere, Plane, Cube, Cylinder, Cone, Group, Triangle, SmoothTriangle };
 
 struct Bounds {
     Tuple min, max;
@@ -360,6 +363,7 @@ struct Bounds {
 struct Intersection {
     double t;
     const Shape* object;
+    double u = 0., v = 0.;  // intersection_with_uv (intersection.rs:381-386, commented scenario): smooth triangles only
 };
 using Intersections = std::vector<Intersection>;
 
@@ -382,6 +386,7 @@ struct Shape {
     bool capped = false;
     std::vector<Shape> shapes;          // Group
     Tuple p1{}, p2{}, p3{}, e1{}, e2{}, normal{};  // Triangle
+    Tuple n1{}, n2{}, n3{};                        // SmoothTriangle: vertex normals
     Matrix4 transform = Matrix4::identity();
     Matrix4 transform_inverse = Matrix4::identity();            // shape.rs:45
     Matrix4 transform_inverse_transpose = Matrix4::identity();  // shape.rs:46
@@ -426,6 +431,17 @@ struct Shape {
         s.e1 = p2 - p1;
         s.e2 = p3 - p1;
         s.normal = s.e2.cross(s.e1).normalize();
+        return s;
+    }
+
+    // the book's smooth_triangle(p1, p2, p3, n1, n2, n3): a triangle (shape.rs:171-193) that also keeps three vertex normals
+    static Shape smooth_triangle(const Tuple& p1, const Tuple& p2, const Tuple& p3, const Tuple& n1, const Tuple& n2,
+                                 const Tuple& n3) {
+        ORC_ASSERT(n1.is_vector() && n2.is_vector() && n3.is_vector(),
+                   "assertion failed: n1.is_vector() && n2.is_vector() && n3.is_vector()");
+        Shape s = triangle(p1, p2, p3);
+        s.kind = Kind::SmoothTriangle;
+        s.n1 = n1; s.n2 = n2; s.n3 = n3;
         return s;
     }
 
@@ -510,6 +526,7 @@ struct Shape {
                 b = out;
                 break;
             }
+            case Kind::SmoothTriangle:
             case Kind::Triangle: {
                 Bounds tmp{Tuple::point(0., 0., 0.), Tuple::point(0., 0., 0.)};
                 tmp.add(shape.p1); tmp.add(shape.p2); tmp.add(shape.p3);
@@ -663,6 +680,7 @@ struct Shape {
                 }
                 break;
             }
+            case Kind::SmoothTriangle:  // the same test; the intersection keeps u and v
             case Kind::Triangle: {  // shape.rs:438-459 (Moller-Trumbore)
                 Tuple dir_cross_e2 = local_ray.direction.cross(e2);
                 double det = e1.dot(dir_cross_e2);
@@ -675,7 +693,8 @@ struct Shape {
                         double v = f * local_ray.direction.dot(origin_cross_e1);
                         if (!(v < 0.0 || (u + v) > 1.0)) {
                             double t = f * e2.dot(origin_cross_e1);
-                            result.push_back({t, this});
+                            if (kind == Kind::SmoothTriangle) result.push_back({t, this, u, v});
+                            else result.push_back({t, this});
                         }
                     }
                 }
@@ -691,7 +710,7 @@ struct Shape {
     }
 
     // shape.rs:466-519 (+ world_to_object :608-621, normal_to_world :623-635)
-    Tuple normal_at(const Tuple& world_point) const {
+    Tuple normal_at(const Tuple& world_point, const Intersection* hit = nullptr) const {
         Tuple lp = transform_inverse * world_point;
         Tuple ln;
         switch (kind) {
@@ -720,6 +739,10 @@ struct Shape {
             }
             case Kind::Group: throw Panic("internal error: entered unreachable code");
             case Kind::Triangle: ln = normal; break;
+            case Kind::SmoothTriangle:  // the book: tri.n2 * hit.u + tri.n3 * hit.v + tri.n1 * (1 - hit.u - hit.v)
+                if (!hit) throw Panic("normal_at of a smooth triangle needs the hit");
+                ln = n2 * hit->u + n3 * hit->v + n1 * (1.0 - hit->u - hit->v);
+                break;
         }
         ORC_ASSERT(ln.is_vector(), "assertion failed: local_normal.is_vector()");
         Tuple wn = transform_inverse_transpose * ln;  // normal_to_world
@@ -742,6 +765,9 @@ struct Shape {
                 for (size_t i = 0; i < shapes.size(); i++)
                     if (!(shapes[i] == o.shapes[i])) return false;
                 break;
+            case Kind::SmoothTriangle:
+                if (!(n1 == o.n1 && n2 == o.n2 && n3 == o.n3)) return false;
+                // fall through
             case Kind::Triangle:
                 if (!(p1 == o.p1 && p2 == o.p2 && p3 == o.p3 && e1 == o.e1 && e2 == o.e2 && normal == o.normal))
                     return false;
@@ -827,7 +853,7 @@ inline const Intersection* hit(const Intersections& xs) {
 inline Computations prepare_computations(const Intersection& self, const Ray& ray, const Intersections& xs) {
     Tuple point = ray.position(self.t);
     Tuple eyev = -ray.direction;
-    Tuple normalv = self.object->normal_at(point);
+    Tuple normalv = self.object->normal_at(point, &self);
     bool inside = normalv.dot(eyev) < 0.0;
     if (inside) normalv = -normalv;
     Tuple reflectv = ray.direction.reflect(normalv);
@@ -1051,6 +1077,7 @@ struct Camera {
 // ---------------------------------------------------------------------------------------------- obj_file.rs:5-128
 struct Parser {
     std::vector<Tuple> vertices;
+    std::vector<Tuple> normals;  // `vn` records (obj_file.rs:295-310, commented scenario)
     size_t ignored_lines = 0;
     Shape default_group = Shape::group();
     // The reference keeps named groups in a std HashMap (iteration order is randomised per process); this oracle
@@ -1087,6 +1114,20 @@ struct Parser {
         if (one_based == 0 || one_based - 1 >= vertices.size()) throw Panic("index out of bounds");
         return vertices[one_based - 1];
     }
+    Tuple normal(size_t one_based) const {
+        if (one_based == 0 || one_based - 1 >= normals.size()) throw Panic("index out of bounds");
+        return normals[one_based - 1];
+    }
+    // One corner of a face: `v`, `v/t`, `v//n` or `v/t/n` (obj_file.rs:312-335, commented scenario).  The texture index is
+    // skipped unread, as the book does.  -> vertex index, normal index (0: none).
+    static std::pair<size_t, size_t> parse_corner(const std::string& tok, const char* what, const std::string& line) {
+        const size_t s1 = tok.find('/');
+        if (s1 == std::string::npos) return {parse_usize(tok, what, line), 0};
+        const size_t v = parse_usize(tok.substr(0, s1), what, line);
+        const size_t s2 = tok.find('/', s1 + 1);
+        if (s2 == std::string::npos) return {v, 0};
+        return {v, parse_usize(tok.substr(s2 + 1), what, line)};
+    }
     Shape* find_group(const std::string& name) {
         for (auto& g : named_groups)
             if (g.first == name) return &g.second;
@@ -1116,15 +1157,24 @@ struct Parser {
                 result.vertices.push_back(Tuple::point(x, y, z));
             } else if (token == "f") {
                 if (tokens.size() < 3) throw Panic("face should have a v1/v2 in \"" + s + "\"");
-                size_t v1 = parse_usize(tokens[1], "v1", s);
-                size_t v2 = parse_usize(tokens[2], "v2", s);
+                auto [v1, vn1] = parse_corner(tokens[1], "v1", s);
+                auto [v2, vn2] = parse_corner(tokens[2], "v2", s);
                 for (size_t k = 3; k < tokens.size(); k++) {
-                    size_t v3 = parse_usize(tokens[k], "v3", s);
-                    Shape tri = Shape::triangle(result.vertex(v1), result.vertex(v2), result.vertex(v3));
+                    auto [v3, vn3] = parse_corner(tokens[k], "v3", s);
+                    // a face whose corners all name a normal is a smooth triangle; any other face is the reference's
+                    Shape tri = (vn1 && vn2 && vn3)
+                                    ? Shape::smooth_triangle(result.vertex(v1), result.vertex(v2), result.vertex(v3),
+                                                             result.normal(vn1), result.normal(vn2), result.normal(vn3))
+                                    : Shape::triangle(result.vertex(v1), result.vertex(v2), result.vertex(v3));
                     if (current_group) result.find_group(*current_group)->push_shape(std::move(tri));
                     else result.default_group.push_shape(std::move(tri));
                     v2 = v3;
+                    vn2 = vn3;
                 }
+            } else if (token == "vn") {
+                if (tokens.size() < 4) throw Panic("normal token to have a x/y/z in \"" + s + "\"");
+                double x = parse_f64(tokens[1], "x", s), y = parse_f64(tokens[2], "y", s), z = parse_f64(tokens[3], "z", s);
+                result.normals.push_back(Tuple::vector(x, y, z));
             } else if (token == "g") {
                 if (tokens.size() < 2) throw Panic("group should have a name in \"" + s + "\"");
                 if (Shape* g = result.find_group(tokens[1])) *g = Shape::group();

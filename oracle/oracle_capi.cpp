@@ -124,6 +124,15 @@ Shape* orc_shape_triangle(const double* p1, const double* p2, const double* p3) 
                                          Tuple::point(p3[0], p3[1], p3[2])));
     } catch (const std::exception& e) { fail(e); return nullptr; }
 }
+// the book's smooth_triangle (absent from the reference: intersection.rs:381-386, obj_file.rs:295-335 quote its scenarios)
+Shape* orc_shape_smooth_triangle(const double* p1, const double* p2, const double* p3, const double* n1, const double* n2,
+                                 const double* n3) {
+    try {
+        return new Shape(Shape::smooth_triangle(Tuple::point(p1[0], p1[1], p1[2]), Tuple::point(p2[0], p2[1], p2[2]),
+                                                Tuple::point(p3[0], p3[1], p3[2]), Tuple::vector(n1[0], n1[1], n1[2]),
+                                                Tuple::vector(n2[0], n2[1], n2[2]), Tuple::vector(n3[0], n3[1], n3[2])));
+    } catch (const std::exception& e) { fail(e); return nullptr; }
+}
 void orc_shape_free(Shape* s) { delete s; }
 int orc_shape_set_transform(Shape* s, const double* m) {
     try { s->set_transform(m16(m)); return 0; } catch (const std::exception& e) { return fail(e); }
@@ -175,6 +184,28 @@ Shape* orc_mesh_from_arrays(const double* verts, uint64_t nverts, const int32_t*
                 p[k] = Tuple::point(verts[(i - 1) * 3], verts[(i - 1) * 3 + 1], verts[(i - 1) * 3 + 2]);
             }
             def.push_shape(Shape::triangle(p[0], p[1], p[2]));
+        }
+        Shape g = Shape::group();
+        g.push_shape(std::move(def));
+        return new Shape(std::move(g));
+    } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+
+// The same for an OBJ that also holds `vn` records and `f v//n` faces: face f's corner k uses vertex faces[3f + k] and
+// normal face_normals[3f + k] (both 1-based).
+Shape* orc_smooth_mesh_from_arrays(const double* verts, uint64_t nverts, const double* normals, uint64_t nnormals,
+                                   const int32_t* faces, const int32_t* face_normals, uint64_t nfaces) {
+    try {
+        Shape def = Shape::group();
+        for (uint64_t f = 0; f < nfaces; f++) {
+            Tuple p[3], n[3];
+            for (int k = 0; k < 3; k++) {
+                int64_t i = faces[f * 3 + k], j = face_normals[f * 3 + k];
+                if (i < 1 || (uint64_t)i > nverts || j < 1 || (uint64_t)j > nnormals) throw Panic("index out of bounds");
+                p[k] = Tuple::point(verts[(i - 1) * 3], verts[(i - 1) * 3 + 1], verts[(i - 1) * 3 + 2]);
+                n[k] = Tuple::vector(normals[(j - 1) * 3], normals[(j - 1) * 3 + 1], normals[(j - 1) * 3 + 2]);
+            }
+            def.push_shape(Shape::smooth_triangle(p[0], p[1], p[2], n[0], n[1], n[2]));
         }
         Shape g = Shape::group();
         g.push_shape(std::move(def));

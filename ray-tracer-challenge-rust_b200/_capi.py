@@ -71,7 +71,7 @@ def dptr(a):
 class BuilderApi:
     """The construction subset shared by librtc_b200.so (`rtc_`) and the oracle (`orc_`)."""
 
-    SPHERE, PLANE, CUBE, CYLINDER, CONE, GROUP, TRIANGLE = range(7)
+    SPHERE, PLANE, CUBE, CYLINDER, CONE, GROUP, TRIANGLE, SMOOTH_TRIANGLE = range(8)
     PATTERN_NONE, PATTERN_STRIPE, PATTERN_GRADIENT, PATTERN_RING, PATTERN_CHECKERS, PATTERN_TEST = -1, 0, 1, 2, 3, 4
 
     def __init__(self, lib, prefix):
@@ -94,6 +94,7 @@ class BuilderApi:
         f("material_set_pattern_transform", C.c_int, C.POINTER(Material), c_double_p)
         f("shape_new", vp, C.c_int, C.c_double, C.c_double, C.c_int)
         f("shape_triangle", vp, c_double_p, c_double_p, c_double_p)
+        f("shape_smooth_triangle", vp, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p)
         f("shape_free", None, vp)
         f("shape_set_transform", C.c_int, vp, c_double_p)
         f("shape_set_material", C.c_int, vp, C.POINTER(Material))
@@ -102,6 +103,8 @@ class BuilderApi:
         f("obj_parse_file", vp, C.c_char_p, c_u64_p)
         f("obj_parse_str", vp, C.c_char_p, C.c_uint64, c_u64_p)
         f("mesh_from_arrays", vp, c_double_p, C.c_uint64, C.POINTER(C.c_int32), C.c_uint64)
+        f("smooth_mesh_from_arrays", vp, c_double_p, C.c_uint64, c_double_p, C.c_uint64, C.POINTER(C.c_int32),
+          C.POINTER(C.c_int32), C.c_uint64)
         f("world_new", vp, c_double_p, c_double_p)
         f("world_default", vp)
         f("world_free", None, vp)

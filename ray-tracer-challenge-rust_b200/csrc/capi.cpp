@@ -424,6 +424,14 @@ rtc_shape* rtc_shape_triangle(const double* p1, const double* p2, const double* 
     }
     return new rtc_shape{shape_triangle(p1, p2, p3)};
 }
+rtc_shape* rtc_shape_smooth_triangle(const double* p1, const double* p2, const double* p3, const double* n1, const double* n2,
+                                     const double* n3) {
+    if (!p1 || !p2 || !p3 || !n1 || !n2 || !n3) {
+        g_err = "null argument";
+        return nullptr;
+    }
+    return new rtc_shape{shape_smooth_triangle(p1, p2, p3, n1, n2, n3)};
+}
 void rtc_shape_free(rtc_shape* s) { delete s; }
 int rtc_shape_set_transform(rtc_shape* s, const double* m) {
     if (!s || !s->s || !m) return set_err(RTC_ERR_INVALID, "null argument");
@@ -489,6 +497,31 @@ rtc_shape* rtc_mesh_from_arrays(const double* verts, uint64_t nverts, const int3
             p[k] = verts + (i - 1) * 3;
         }
         shape_push(def.get(), shape_triangle(p[0], p[1], p[2]));
+    }
+    auto g = shape_new(RTC_GROUP, 0., 0., false);
+    shape_push(g.get(), std::move(def));
+    return new rtc_shape{std::move(g)};
+}
+
+rtc_shape* rtc_smooth_mesh_from_arrays(const double* verts, uint64_t nverts, const double* normals, uint64_t nnormals,
+                                       const int32_t* faces, const int32_t* face_normals, uint64_t nfaces) {
+    if ((nverts && !verts) || (nnormals && !normals) || (nfaces && (!faces || !face_normals))) {
+        g_err = "null argument";
+        return nullptr;
+    }
+    auto def = shape_new(RTC_GROUP, 0., 0., false);
+    for (uint64_t f = 0; f < nfaces; f++) {
+        const double *p[3], *n[3];
+        for (int k = 0; k < 3; k++) {
+            int64_t i = faces[f * 3 + k], j = face_normals[f * 3 + k];
+            if (i < 1 || (uint64_t)i > nverts || j < 1 || (uint64_t)j > nnormals) {
+                set_err(RTC_ERR_PANIC, "index out of bounds (src/obj_file.rs:117)");
+                return nullptr;
+            }
+            p[k] = verts + (i - 1) * 3;
+            n[k] = normals + (j - 1) * 3;
+        }
+        shape_push(def.get(), shape_smooth_triangle(p[0], p[1], p[2], n[0], n[1], n[2]));
     }
     auto g = shape_new(RTC_GROUP, 0., 0., false);
     shape_push(g.get(), std::move(def));

@@ -12,6 +12,7 @@
 //   bvh[]      : 64-byte nodes holding BOTH children's boxes (f32, padded and rounded outward) so one fetch tests two boxes.
 //   tris[]     : p1,e1,e2 of each triangle in BVH-leaf order + its DFS leaf index (the reference's tie-break order).
 //   tri_attr[] : per triangle (same order): precomputed world normal (shape.rs:509-518 is point-independent) + material.
+//   tri_smooth[]: per triangle (same order), only in scenes with smooth triangles: the three vertex normals.
 //   materials[]: material.rs:4-14 + flattened pattern with rows 0..2 of the pattern inverse.
 #pragma once
 #include <stdint.h>
@@ -90,6 +91,14 @@ struct alignas(16) DTriAttr {
     int32_t material;
     int32_t xform;  // the mesh's transform (patterns evaluate in the leaf's object space, pattern.rs:99)
 };
+// Vertex normals of a smooth triangle (the book's SmoothTriangle; rtc.h RTC_SMOOTH_TRIANGLE), object space, indexed like
+// tris[]; the table exists only in scenes that hold one (smooth = 0: a flat triangle of such a scene).
+struct alignas(16) DTriSmooth {
+    double n1[3], n2[3], n3[3];
+    int32_t smooth;
+    int32_t pad;
+};
+static_assert(sizeof(DTriSmooth) == 80, "DTriSmooth layout: read with 16-byte loads");
 struct DMaterial {
     double color[3];
     double ambient, diffuse, specular, shininess, reflective, transparency, refractive_index;
@@ -109,6 +118,7 @@ struct DScene {
     const DTriAttr* tri_attr;
     const DMaterial* materials;
     const DBox32* prim_boxes;
+    const DTriSmooth* tri_smooth;  // null: no smooth triangle in the scene
     const int32_t* class_offsets;
     const DClassMember* class_members;
     int32_t n_classes;

@@ -31,6 +31,7 @@ struct FlatScene {
     std::vector<DProgramNode> program;
     std::vector<DXform> xforms;
     std::vector<DPrim> prims;
+    std::vector<DTriSmooth> tri_smooth;  // empty, or same length as tris
     std::vector<DBox32> prim_boxes;  // same length as prims (zero for leaves outside LIST clusters)
     std::vector<DGate> gates;
     std::vector<DMesh> meshes;
@@ -44,7 +45,7 @@ struct FlatScene {
     uint64_t leaf_count = 0;
     int32_t recursion_limit = 5;  // world.rs:11
     int32_t feature_mask = 0;  // bit k: leaves of ShapeKind k; 32 meshes; 64 gates; 128 a transparent material; 256 clusters; 512 a RECURSION_LIMIT other than 5;
-                               // 1024 a cluster that is a BVH (more than kClusterListMax leaves)
+                               // 1024 a cluster that is a BVH (more than kClusterListMax leaves); 2048 a smooth triangle
     int32_t merged_gates = 0;  // nested single-child groups whose identical box shares the parent's gate
     int bvh_max_depth = 0;
     // device-built meshes (flatten option device_mesh_build)

@@ -140,11 +140,14 @@ class Flattener {
         if (!c) fail(RTC_ERR_INVALID, m);
     }
 
+    static bool is_tri(int32_t kind) { return kind == RTC_TRIANGLE || kind == RTC_SMOOTH_TRIANGLE; }
+    bool has_smooth_ = false;
+
     uint32_t scan(uint32_t i, int depth) {
         check(i < d_.shape_count, "pre-order walk runs past shape_count");
         check(depth < 64, "group nesting deeper than 64");
         const rtc_shape_desc& s = d_.shapes[i];
-        check(s.kind >= RTC_SPHERE && s.kind <= RTC_TRIANGLE, "unknown shape kind");
+        check(s.kind >= RTC_SPHERE && s.kind <= RTC_SMOOTH_TRIANGLE, "unknown shape kind");
         check(s.transform >= 0 && (uint32_t)s.transform < d_.transform_count, "transform index out of range");
         uint32_t next = i + 1;
         if (s.kind == RTC_GROUP) {
@@ -152,8 +155,14 @@ class Flattener {
             for (int32_t c = 0; c < s.child_count; c++) next = scan(next, depth + 1);
         } else {
             check(s.material >= 0 && (uint32_t)s.material < d_.material_count, "material index out of range");
-            if (s.kind == RTC_TRIANGLE)
+            if (is_tri(s.kind))
                 check(s.triangle >= 0 && (uint32_t)s.triangle < d_.triangle_count, "triangle index out of range");
+            if (s.kind == RTC_SMOOTH_TRIANGLE) {
+                check(d_.vertex_normals != nullptr, "vertex_normals is NULL in a world with a smooth triangle");
+                // vertex normals are placed by the host build only (the device build emits flat triangles)
+                if (opts_.device_mesh_build) fail(kFlattenNeedsHostBuild, "smooth triangles need the host mesh build");
+                has_smooth_ = true;
+            }
         }
         end_[i] = next;
         return next;
@@ -239,6 +248,7 @@ class Flattener {
             case RTC_CONE:
                 if (s.capped) return {point(-1., s.minimum, -1.), point(1., s.maximum, 1.)};
                 return {point(-1., -inf, -1.), point(1., inf, 1.)};
+            case RTC_SMOOTH_TRIANGLE:  // the book bounds a smooth triangle like a triangle
             case RTC_TRIANGLE: {  // bounds.rs:126-137: seeded with the origin
                 const rtc_triangle_desc& t = d_.triangles[s.triangle];
                 Box4 b{point(0., 0., 0.), point(0., 0., 0.)};
@@ -355,7 +365,7 @@ class Flattener {
         uint32_t n = 0;
         ClusterItem tmp;
         for (uint32_t c = begin; c < end; c = end_[c])
-            if (d_.shapes[c].kind != RTC_GROUP && d_.shapes[c].kind != RTC_TRIANGLE && leaf_world_box(d_.shapes[c], tmp)) n++;
+            if (d_.shapes[c].kind != RTC_GROUP && !is_tri(d_.shapes[c].kind) && leaf_world_box(d_.shapes[c], tmp)) n++;
         return n;
     }
     void push_prim(const DPrim& p, const DBox32* box = nullptr) {
@@ -487,7 +497,12 @@ class Flattener {
         if (a.kind != b.kind) return false;
         if (a.kind == RTC_CYLINDER || a.kind == RTC_CONE) {
             if (!(a.minimum == b.minimum && a.maximum == b.maximum && (a.capped != 0) == (b.capped != 0))) return false;
-        } else if (a.kind == RTC_TRIANGLE) {
+        } else if (is_tri(a.kind)) {
+            if (a.kind == RTC_SMOOTH_TRIANGLE) {
+                const rtc_vertex_normals& p = d_.vertex_normals[a.triangle];
+                const rtc_vertex_normals& q = d_.vertex_normals[b.triangle];
+                if (!(almost_n<3>(p.n1, q.n1) && almost_n<3>(p.n2, q.n2) && almost_n<3>(p.n3, q.n3))) return false;
+            }
             const rtc_triangle_desc& x = d_.triangles[a.triangle];
             const rtc_triangle_desc& y = d_.triangles[b.triangle];
             if (!(almost_n<3>(x.p1, y.p1) && almost_n<3>(x.p2, y.p2) && almost_n<3>(x.p3, y.p3) && almost_n<3>(x.e1, y.e1) &&
@@ -508,7 +523,7 @@ class Flattener {
         std::vector<uint32_t> idx(n);
         for (uint32_t l = 0; l < n; l++) {
             const rtc_shape_desc& s = d_.shapes[sites_[l].shape];
-            const double c = s.kind == RTC_TRIANGLE ? d_.triangles[s.triangle].p1[0] : d_.transforms[s.transform].transform[3];
+            const double c = is_tri(s.kind) ? d_.triangles[s.triangle].p1[0] : d_.transforms[s.transform].transform[3];
             // kinds are 1e6 apart on the key axis only if coordinates are small; compare kinds explicitly in the window
             key[l] = c;
             idx[l] = l;
@@ -587,9 +602,9 @@ class Flattener {
             if (s.kind == RTC_GROUP) {
                 emit_group(i);
                 i = end_[i];
-            } else if (s.kind == RTC_TRIANGLE) {
+            } else if (is_tri(s.kind)) {
                 uint32_t j = i + 1;
-                while (j < end && d_.shapes[j].kind == RTC_TRIANGLE && same_inverse(i, j)) j++;
+                while (j < end && is_tri(d_.shapes[j].kind) && same_inverse(i, j)) j++;
                 emit_mesh(i, j);
                 i = j;
             } else {
@@ -634,7 +649,7 @@ class Flattener {
             return false;
         const int32_t tr = d_.shapes[g + 1].transform;
         for (uint32_t c = g + 1; c < end_[g]; c++)
-            if (d_.shapes[c].kind != RTC_TRIANGLE || d_.shapes[c].transform != tr) return false;
+            if (!is_tri(d_.shapes[c].kind) || d_.shapes[c].transform != tr) return false;
         return true;
     }
 
@@ -823,6 +838,21 @@ class Flattener {
             dt.leaf = (int32_t)(leaf0 + k);
             dt.cls = -1;
             out_.tri_attr[at + slot] = attr_in[k];
+            if (has_smooth_) {
+                out_.tri_smooth.resize(at + n);  // value-initialised: smooth = 0
+                const rtc_shape_desc& sd = d_.shapes[begin + k];
+                if (sd.kind == RTC_SMOOTH_TRIANGLE) {
+                    DTriSmooth& sm = out_.tri_smooth[at + slot];
+                    const rtc_vertex_normals& vn = d_.vertex_normals[sd.triangle];
+                    for (int a = 0; a < 3; a++) {
+                        sm.n1[a] = vn.n1[a];
+                        sm.n2[a] = vn.n2[a];
+                        sm.n3[a] = vn.n3[a];
+                    }
+                    sm.smooth = 1;
+                    out_.feature_mask |= 2048;
+                }
+            }
         }
         for (uint32_t slot = 0; slot < n; slot++)
             set_site(leaf0 + order[slot], LeafSite{begin + order[slot], (int32_t)out_.program.size(), (int32_t)(at + slot)});

@@ -33,6 +33,7 @@ struct HShape {
     bool capped = false;
     std::vector<std::unique_ptr<HShape>> children;  // ShapeKind::Group { shapes }
     rtc_triangle_desc tri{};                        // ShapeKind::Triangle payload
+    rtc_vertex_normals vn{};                        // RTC_SMOOTH_TRIANGLE: n1, n2, n3
     Mat4 transform = Mat4::identity();
     Mat4 inverse = Mat4::identity();
     bool transformed = false;
@@ -83,6 +84,18 @@ inline std::unique_ptr<HShape> shape_triangle(const double* p1, const double* p2
     return s;
 }
 
+// The book's smooth_triangle(p1, p2, p3, n1, n2, n3) — not in the reference (rtc.h RTC_SMOOTH_TRIANGLE): a triangle that
+// also keeps its three vertex normals.
+inline std::unique_ptr<HShape> shape_smooth_triangle(const double* p1, const double* p2, const double* p3, const double* n1,
+                                                     const double* n2, const double* n3) {
+    auto s = shape_triangle(p1, p2, p3);
+    s->kind = RTC_SMOOTH_TRIANGLE;
+    std::memcpy(s->vn.n1, n1, sizeof(s->vn.n1));
+    std::memcpy(s->vn.n2, n2, sizeof(s->vn.n2));
+    std::memcpy(s->vn.n3, n3, sizeof(s->vn.n3));
+    return s;
+}
+
 // set_transform_internal (shape.rs:203-218): groups push the matrix down; a leaf left-multiplies it into its own
 inline void push_down_transform(HShape* s, const Mat4& t) {
     if (s->kind == RTC_GROUP) {
@@ -120,6 +133,7 @@ struct ObjResult {
     std::unique_ptr<HShape> group;  // Parser::obj_to_group()
     uint64_t ignored_lines = 0;
     uint64_t vertex_count = 0;
+    uint64_t normal_count = 0;  // `vn` records (obj_file.rs:295-310, commented scenario)
 };
 
 namespace detail {
@@ -179,11 +193,25 @@ inline uint64_t parse_usize(const char* b, const char* e, const char* what, cons
     if (!ok) throw HostPanic(std::string("face ") + what + " should be a usize in \"" + std::string(lb, le) + "\" (src/obj_file.rs:57-74)");
     return v;
 }
+// One corner of a face: `v`, `v/t`, `v//n` or `v/t/n` (obj_file.rs:312-335, commented scenario; the texture index is
+// skipped unread).  A plain `v` parses exactly as the reference does.  *n = 0: the corner names no normal.
+inline uint64_t parse_corner(const char* b, const char* e, const char* what, const char* lb, const char* le, uint64_t* n) {
+    *n = 0;
+    const char* s1 = b;
+    while (s1 < e && *s1 != '/') s1++;
+    const uint64_t v = parse_usize(b, s1, what, lb, le);
+    if (s1 == e) return v;
+    const char* s2 = s1 + 1;
+    while (s2 < e && *s2 != '/') s2++;
+    if (s2 < e) *n = parse_usize(s2 + 1, e, what, lb, le);
+    return v;
+}
 }  // namespace detail
 
 inline ObjResult obj_parse(const char* text, size_t len) {
     ObjResult out;
     std::vector<double> verts;  // xyz
+    std::vector<double> norms;  // xyz of the `vn` records
     auto default_group = shape_new(RTC_GROUP, 0., 0., false);
     // named groups in first-insertion order (the reference iterates a HashMap: any order); re-declaring a name
     // replaces the group (HashMap::insert, obj_file.rs:101-103)
@@ -192,6 +220,10 @@ inline ObjResult obj_parse(const char* text, size_t len) {
     auto vertex = [&](uint64_t one_based, double* p) {
         if (one_based == 0 || one_based > verts.size() / 3) throw HostPanic("index out of bounds (src/obj_file.rs:117)");
         std::memcpy(p, &verts[(one_based - 1) * 3], sizeof(double) * 3);
+    };
+    auto normal = [&](uint64_t one_based, double* p) {
+        if (one_based == 0 || one_based > norms.size() / 3) throw HostPanic("index out of bounds (vn)");
+        std::memcpy(p, &norms[(one_based - 1) * 3], sizeof(double) * 3);
     };
     size_t pos = 0;
     std::vector<std::pair<const char*, const char*>> tok;
@@ -222,18 +254,37 @@ inline ObjResult obj_parse(const char* text, size_t len) {
             verts.insert(verts.end(), xyz, xyz + 3);
         } else if (tl == 1 && *tok[0].first == 'f') {
             if (tok.size() < 2) throw HostPanic("face should have a v1 in \"" + line() + "\"");
-            uint64_t v1 = detail::parse_usize(tok[1].first, tok[1].second, "v1", lb, le);
+            uint64_t n1i, n2i, n3i;
+            uint64_t v1 = detail::parse_corner(tok[1].first, tok[1].second, "v1", lb, le, &n1i);
             if (tok.size() < 3) throw HostPanic("face should have a v2 in \"" + line() + "\"");
-            uint64_t v2 = detail::parse_usize(tok[2].first, tok[2].second, "v2", lb, le);
+            uint64_t v2 = detail::parse_corner(tok[2].first, tok[2].second, "v2", lb, le, &n2i);
             for (size_t k = 3; k < tok.size(); k++) {  // fan triangulation, obj_file.rs:70-94
-                uint64_t v3 = detail::parse_usize(tok[k].first, tok[k].second, "v3", lb, le);
+                uint64_t v3 = detail::parse_corner(tok[k].first, tok[k].second, "v3", lb, le, &n3i);
                 double p1[3], p2[3], p3[3];
                 vertex(v1, p1);
                 vertex(v2, p2);
                 vertex(v3, p3);
-                shape_push(current ? current : default_group.get(), shape_triangle(p1, p2, p3));
+                if (n1i && n2i && n3i) {  // every corner names a normal: a smooth triangle
+                    double a[3], b[3], c[3];
+                    normal(n1i, a);
+                    normal(n2i, b);
+                    normal(n3i, c);
+                    shape_push(current ? current : default_group.get(), shape_smooth_triangle(p1, p2, p3, a, b, c));
+                } else {
+                    shape_push(current ? current : default_group.get(), shape_triangle(p1, p2, p3));
+                }
                 v2 = v3;
+                n2i = n3i;
             }
+        } else if (tl == 2 && tok[0].first[0] == 'v' && tok[0].first[1] == 'n') {
+            static const char* names[3] = {"x", "y", "z"};
+            double xyz[3];
+            for (int k = 0; k < 3; k++) {
+                if (tok.size() < (size_t)k + 2)
+                    throw HostPanic(std::string("normal token to have a ") + names[k] + " in \"" + line() + "\"");
+                xyz[k] = detail::parse_f64(tok[k + 1].first, tok[k + 1].second, names[k], lb, le);
+            }
+            norms.insert(norms.end(), xyz, xyz + 3);
         } else if (tl == 1 && *tok[0].first == 'g') {
             if (tok.size() < 2) throw HostPanic("group should have a name in \"" + line() + "\"");
             std::string name(tok[1].first, tok[1].second);
@@ -252,6 +303,7 @@ inline ObjResult obj_parse(const char* text, size_t len) {
         }
     }
     out.vertex_count = verts.size() / 3;
+    out.normal_count = norms.size() / 3;
     out.group = shape_new(RTC_GROUP, 0., 0., false);  // obj_to_group, obj_file.rs:120-128
     shape_push(out.group.get(), std::move(default_group));
     for (auto& g : named) shape_push(out.group.get(), std::move(g.second));
@@ -266,6 +318,7 @@ struct Marshalled {
     std::vector<rtc_transform_desc> transforms;
     std::vector<rtc_material> materials;
     std::vector<rtc_triangle_desc> triangles;
+    std::vector<rtc_vertex_normals> vertex_normals;  // empty unless the world holds a smooth triangle; else like triangles
     rtc_scene_desc desc{};
 };
 
@@ -320,9 +373,13 @@ struct Marshaller {
             return;
         }
         d.material = material_id(s->material);
-        if (s->kind == RTC_TRIANGLE) {
+        if (s->kind == RTC_TRIANGLE || s->kind == RTC_SMOOTH_TRIANGLE) {
             d.triangle = (int32_t)m.triangles.size();
             m.triangles.push_back(s->tri);
+            if (s->kind == RTC_SMOOTH_TRIANGLE) {
+                m.vertex_normals.resize(m.triangles.size(), rtc_vertex_normals{});
+                m.vertex_normals.back() = s->vn;
+            }
         }
         m.shapes.push_back(d);
     }
@@ -352,6 +409,8 @@ inline void marshal_world(const HWorld& w, Marshalled& out) {
     d.material_count = (uint32_t)out.materials.size();
     d.triangles = out.triangles.data();
     d.triangle_count = (uint32_t)out.triangles.size();
+    if (!out.vertex_normals.empty()) out.vertex_normals.resize(out.triangles.size(), rtc_vertex_normals{});
+    d.vertex_normals = out.vertex_normals.empty() ? nullptr : out.vertex_normals.data();
     for (int k = 0; k < 3; k++) {
         d.light_position[k] = w.light_position[k];
         d.light_intensity[k] = w.light_intensity[k];

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(64) prepare_kernel(const __grid_constant__ DSc
         // the un-flipped normal first: `inside` is normal_at . eyev < 0 (intersection.rs:22-25)
         const V3 point = position(r, w.upper);
         const V3 eyev = -r.d;
-        V3 nv = normal_at<FEAT_ALL>(s, w.type, w.index, point, tl);
+        V3 nv = normal_at<FEAT_ALL>(s, w.type, w.index, point, r, tl);
         o.inside = dot(nv, eyev) < 0.0 ? 1 : 0;
         if (o.inside) nv = -nv;
         const V3 reflectv = reflect(r.d, nv);
@@ -105,7 +105,12 @@ __global__ void __launch_bounds__(64) normal_kernel(const __grid_constant__ DSce
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Tally tl;
-    const V3 nv = normal_at<FEAT_ALL>(s, type, index, v3(points[3 * i], points[3 * i + 1], points[3 * i + 2]), tl);
+    // a smooth triangle's normal does not depend on the point but on the hit's (u, v): points[] holds (u, v, unused) then —
+    // the book's normal_at(tri, point, hit) with an intersection_with_uv
+    const bool smooth = type == NODE_MESH && s.tri_smooth != nullptr && s.tri_smooth[index].smooth != 0;
+    const Ray none{v3(0., 0., 0.), v3(0., 0., 0.)};
+    const V3 nv = smooth ? smooth_normal(s, index, points[3 * i], points[3 * i + 1])
+                         : normal_at<FEAT_ALL>(s, type, index, v3(points[3 * i], points[3 * i + 1], points[3 * i + 2]), none, tl);
     out[3 * i + 0] = nv.x;
     out[3 * i + 1] = nv.y;
     out[3 * i + 2] = nv.z;

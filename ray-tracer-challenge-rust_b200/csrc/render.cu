@@ -212,14 +212,14 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     RTC_CUDA(cudaSetDevice(device));
     // device-built meshes (lbvh.cu) own the table entries after the host-built ones: allocated here, never uploaded
     const auto with_extra = [](size_t raw_bytes, size_t extra_bytes) { return (raw_bytes + extra_bytes + 255) & ~(size_t)255; };
-    constexpr int kTables = 12;
+    constexpr int kTables = 13;
     const size_t sizes[kTables] = {slab_bytes(f.program), slab_bytes(f.xforms),   slab_bytes(f.prims),
                              slab_bytes(f.gates),   slab_bytes(f.meshes),
                              with_extra(f.bvh.size() * sizeof(DBvhNode), (size_t)f.device_nodes * sizeof(DBvhNode)),
                              with_extra(f.tris.size() * sizeof(DTri), (size_t)f.device_tris * sizeof(DTri)),
                              with_extra(f.tri_attr.size() * sizeof(DTriAttr), (size_t)f.device_tris * sizeof(DTriAttr)),
                              slab_bytes(f.materials), slab_bytes(f.class_offsets), slab_bytes(f.class_members),
-                             slab_bytes(f.prim_boxes)};
+                             slab_bytes(f.prim_boxes), slab_bytes(f.tri_smooth)};
     size_t total = 256;
     for (size_t b : sizes) total += b;
     // pinned staging mirrors the slab's layout (one copy when nothing is device-built), followed by the device build's inputs
@@ -235,13 +235,14 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     size_t off[kTables], at = 0;
     const void* src[kTables] = {f.program.data(), f.xforms.data(),   f.prims.data(),    f.gates.data(), f.meshes.data(),
                           f.bvh.data(),     f.tris.data(),     f.tri_attr.data(), f.materials.data(),
-                          f.class_offsets.data(), f.class_members.data(), f.prim_boxes.data()};
+                          f.class_offsets.data(), f.class_members.data(), f.prim_boxes.data(), f.tri_smooth.data()};
     const size_t raw[kTables] = {f.program.size() * sizeof(DProgramNode), f.xforms.size() * sizeof(DXform),
                            f.prims.size() * sizeof(DPrim),          f.gates.size() * sizeof(DGate),
                            f.meshes.size() * sizeof(DMesh),         f.bvh.size() * sizeof(DBvhNode),
                            f.tris.size() * sizeof(DTri),            f.tri_attr.size() * sizeof(DTriAttr),
                            f.materials.size() * sizeof(DMaterial),  f.class_offsets.size() * sizeof(int32_t),
-                           f.class_members.size() * sizeof(DClassMember), f.prim_boxes.size() * sizeof(DBox32)};
+                           f.class_members.size() * sizeof(DClassMember), f.prim_boxes.size() * sizeof(DBox32),
+                           f.tri_smooth.size() * sizeof(DTriSmooth)};
     for (int k = 0; k < kTables; k++) {
         off[k] = at;
         if (raw[k]) std::memcpy(host + at, src[k], raw[k]);
@@ -308,6 +309,7 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->view.class_offsets = (const int32_t*)(base + off[9]);
     s->view.class_members = (const DClassMember*)(base + off[10]);
     s->view.prim_boxes = (const DBox32*)(base + off[11]);
+    s->view.tri_smooth = f.tri_smooth.empty() ? nullptr : (const DTriSmooth*)(base + off[12]);
     s->view.n_classes = f.class_offsets.empty() ? 0 : (int32_t)f.class_offsets.size() - 1;
     s->view.pad1 = 0;
     s->view.program_count = (int32_t)f.program.size();

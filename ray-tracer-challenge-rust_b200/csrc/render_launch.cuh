@@ -28,9 +28,9 @@ constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
 
 // mask, in dispatch order (smallest first):  clustered cubes + refraction (table) | spheres + cylinders + groups (hexagon)
 // | mesh + groups (teapot) | + plane (cow & teddy) | + refraction (pumpkin) | every primitive kind, clusters (lists and
-// trees), no meshes |
+// trees), no meshes | smooth-triangle meshes + plane (cow & teddy with vertex normals) |
 // everything | everything with the general-depth integrator (a RECURSION_LIMIT other than the reference's 5)
-#define RTC_RENDER_INSTANCES(X) X(388) X(73) X(96) X(98) X(226) X(1503) X(1535) X(2047)
+#define RTC_RENDER_INSTANCES(X) X(388) X(73) X(96) X(98) X(226) X(1503) X(2146) X(3583) X(4095)
 
 using RenderLaunchFn = void (*)(unsigned grid, cudaStream_t stream, const DScene& s, const DCamera& cam, const DRows& rows,
                                 uint32_t* out8, double* out64, DQueue* q);

@@ -228,6 +228,11 @@ class Shapes:
         a, b, c = as_f64(p1, 3), as_f64(p2, 3), as_f64(p3, 3)
         return Shape(self.api, self.api.shape_triangle(dptr(a), dptr(b), dptr(c)), BuilderApi.TRIANGLE)
 
+    def smooth_triangle(self, p1, p2, p3, n1, n2, n3):
+        """The book's smooth_triangle (not in the reference; rtc.h RTC_SMOOTH_TRIANGLE)."""
+        a = [as_f64(x, 3) for x in (p1, p2, p3, n1, n2, n3)]
+        return Shape(self.api, self.api.shape_smooth_triangle(*[dptr(x) for x in a]), BuilderApi.SMOOTH_TRIANGLE)
+
     def obj_file(self, path):
         """Parser::from_obj_file(path).obj_to_group()"""
         ign = C.c_uint64(0)
@@ -247,6 +252,17 @@ class Shapes:
         v = as_f64(vertices)
         f = np.ascontiguousarray(faces, dtype=np.int32)
         h = self.api.mesh_from_arrays(dptr(v), v.size // 3, f.ctypes.data_as(C.POINTER(C.c_int32)), f.size // 3)
+        return Shape(self.api, h, BuilderApi.GROUP)
+
+
+    def smooth_mesh(self, vertices, normals, faces, face_normals=None):
+        """The same for `vn` records and `f v//n` faces (face_normals defaults to faces: one normal per vertex)."""
+        v, n = as_f64(vertices), as_f64(normals)
+        f = np.ascontiguousarray(faces, dtype=np.int32)
+        fn = f if face_normals is None else np.ascontiguousarray(face_normals, dtype=np.int32)
+        i32p = C.POINTER(C.c_int32)
+        h = self.api.smooth_mesh_from_arrays(dptr(v), v.size // 3, dptr(n), n.size // 3, f.ctypes.data_as(i32p),
+                                             fn.ctypes.data_as(i32p), f.size // 3)
         return Shape(self.api, h, BuilderApi.GROUP)
 
 

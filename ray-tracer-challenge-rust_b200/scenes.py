@@ -24,12 +24,28 @@ CONFIGS = {
     "teapot": (1920, 1080),
     "cow_teddy": (3840, 2160),
     "pumpkin": (7680, 4320),
+    "cow_teddy_smooth": (3840, 2160),  # C4 with smooth triangles: not a BASELINE config of its own
 }
 
 
 def load_mesh(name):
     d = np.load(os.path.join(ASSETS, name + ".npz"))
     return d["vertices"], d["faces"]
+
+
+def vertex_normals(vertices, faces):
+    """One normal per vertex for an asset that ships none (cow-nonormals.obj, teddy.obj): the sum of the adjacent faces'
+    cross products (area-weighted), accumulated in face order, normalised.  Plain numpy, so the oracle and the product
+    are handed the same bits."""
+    v = np.asarray(vertices, dtype=np.float64)
+    f = np.asarray(faces, dtype=np.int64) - 1
+    fn = np.cross(v[f[:, 2]] - v[f[:, 0]], v[f[:, 1]] - v[f[:, 0]])  # e2 x e1, the orientation of shape.rs:185
+    n = np.zeros_like(v)
+    for k in range(3):
+        np.add.at(n, f[:, k], fn)
+    length = np.linalg.norm(n, axis=1, keepdims=True)
+    length[length == 0.0] = 1.0
+    return n / length
 
 
 def _light():
@@ -133,8 +149,8 @@ def teapot(api, hsize=1920, vsize=1080):  # main.rs:368-397
     return world, cam
 
 
-def _cow(api, T, S):  # main.rs:340-351
-    cow = S.mesh(*load_mesh("cow"))
+def _cow(api, T, S, cow=None):  # main.rs:340-351
+    cow = cow if cow is not None else S.mesh(*load_mesh("cow"))
     cow.set_transform(T.translation(0., 3.5, 0.) * T.scaling(0.5, 0.5, 0.5))
     m = Material()
     m.color, m.ambient, m.diffuse, m.specular, m.shininess, m.reflective = WHITE, 0.1, 0.7, 0.9, 300.0, 0.2
@@ -150,12 +166,19 @@ def cow(api, hsize=400, vsize=200):  # main.rs:328-363 — what the shipped bina
     return world, cam
 
 
-def cow_teddy(api, hsize=3840, vsize=2160):
+def cow_teddy(api, hsize=3840, vsize=2160, smooth=False):
+    """smooth=True: the same scene with every mesh triangle a smooth triangle over generated vertex normals (BASELINE's
+    config 4 names smooth_triangle meshes; the assets carry no `vn` records and the reference has no smooth triangles)."""
     T, S = Transformations(api), Shapes(api)
     cam = _camera(api, T, hsize, vsize, (8.0, 6.0, -8.0), (0.0, 3.0, 0.0))
     world = WorldHandle(api, _light())
-    world.push(_cow(api, T, S))
-    teddy = S.mesh(*load_mesh("teddy"))
+
+    def mesh(name):
+        v, f = load_mesh(name)
+        return S.smooth_mesh(v, vertex_normals(v, f), f) if smooth else S.mesh(v, f)
+
+    world.push(_cow(api, T, S, mesh("cow")))
+    teddy = mesh("teddy")
     teddy.set_transform(T.translation(-4.5, 2.6, 1.5) * T.scaling(0.12, 0.12, 0.12))
     m = Material()
     m.color = (1.0, 0.6, 0.3)
@@ -187,8 +210,12 @@ def pumpkin(api, hsize=7680, vsize=4320):
     return world, cam
 
 
+def cow_teddy_smooth(api, hsize=3840, vsize=2160):
+    return cow_teddy(api, hsize, vsize, smooth=True)
+
+
 BUILDERS = {"hexagon": hexagon, "table": table, "teapot": teapot, "cow": cow, "cow_teddy": cow_teddy,
-            "pumpkin": pumpkin}
+            "pumpkin": pumpkin, "cow_teddy_smooth": cow_teddy_smooth}
 
 
 def build(api, name, hsize=None, vsize=None):

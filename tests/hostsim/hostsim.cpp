@@ -55,6 +55,7 @@ int sim_scene_create_ex(const rtc_scene_desc* desc, int device_build, void** out
     v.tri_attr = s->flat.tri_attr.data();
     v.materials = s->flat.materials.data();
     v.prim_boxes = s->flat.prim_boxes.data();
+    v.tri_smooth = s->flat.tri_smooth.empty() ? nullptr : s->flat.tri_smooth.data();
     v.class_offsets = s->flat.class_offsets.data();
     v.class_members = s->flat.class_members.data();
     v.n_classes = s->flat.class_offsets.empty() ? 0 : (int32_t)s->flat.class_offsets.size() - 1;

@@ -422,3 +422,48 @@ def test_multi_device_render_in_one_process(rtc, name, w, h):
         st = rtc.Stats()
         assert np.array_equal(rtc.render_multi(world, cam, ngpus, stats=st), one)
         assert st.total_rays == st1.total_rays
+
+
+# ---- smooth triangles.  Parity UNPINNED against the reference, which does not implement them
+# (intersection.rs:381-386, obj_file.rs:295-335 are commented-out scenarios): the oracle follows the book's definition.
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("build", ["host", "device"])
+def test_smooth_triangle_worlds_match_oracle(rtc, oracle, seed, build):
+    """Vertex-normal meshes (one of glass), a run that mixes flat and smooth triangles, a mirror floor.  "device": the
+    request for the GPU mesh build is honoured by falling back to the host build (vertex normals are placed by the host)."""
+    import worldgen
+    w, c = worldgen.smooth_world(rtc.api(), seed, hsize=96, vsize=64)
+    world = rtc.World(_handle=w.h)
+    w.h = None
+    cam = rtc.Camera.__new__(rtc.Camera)
+    cam.api, cam.hsize, cam.vsize, cam.field_of_view, cam.h = c.api, c.hsize, c.vsize, c.field_of_view, c.h
+    c.h = None
+    world.set_build(build)
+    st = rtc.Stats()
+    canvas = cam.render(world, stats=st)
+    ow, oc = worldgen.smooth_world(oracle, seed, hsize=96, vsize=64)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    _check(ref, canvas.pixels_f64().reshape(-1, 3), oracle.quantise_rgba8(ref), canvas.pixels_rgba8())
+    assert (st.primary_rays, st.shadow_rays, st.reflect_rays, st.refract_rays) == \
+        (cnt.primary, cnt.shadow, cnt.reflect, cnt.refract)
+
+
+def test_config_4_with_smooth_triangles(rtc, oracle):
+    """BASELINE config 4 (cow + teddy + reflective floor at 3840x2160) with every triangle a smooth triangle over generated
+    vertex normals: the 1/64 pixel subset of the full-resolution camera against the oracle, and the frame differs from the
+    flat-triangle render of the same scene."""
+    w, h = 3840, 2160
+    world, cam = rtc.build_scene("cow_teddy_smooth", w, h)
+    assert world.kernel_features() == (2146, 2146)
+    rgba = np.empty((h, w, 4), dtype=np.uint8)
+    st = rtc.Stats()
+    cam.render_into(world, rgba8=rgba, stats=st)
+    assert st.primary_rays == w * h
+    ow, oc = helpers.scenes.build(oracle, "cow_teddy_smooth", w, h)
+    px = helpers.subset_pixels(w, h, 64, 32)
+    ref, _ = oracle.render(ow, oc, mode=oracle.CACHED, pixels=px)
+    _check(ref, None, oracle.quantise_rgba8(ref), rgba[px[:, 1], px[:, 0]])
+    fworld, fcam = rtc.build_scene("cow_teddy", w, h)
+    flat = np.empty((h, w, 4), dtype=np.uint8)
+    fcam.render_into(fworld, rgba8=flat)
+    assert (flat != rgba).any(axis=2).mean() > 0.02

@@ -390,3 +390,76 @@ def test_large_cluster_is_a_tree_bit_exact(rtc, oracle, hostsim, seed):
     rgb, _, scnt = scene.render(cam)
     assert _bits_equal(ref, rgb), f"{np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
     assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+
+
+# ---- smooth triangles.  Parity UNPINNED against the reference: it does not implement them (its
+# scenarios are commented out at intersection.rs:381-386 and obj_file.rs:295-335); the oracle follows the book's definition
+# those comments quote, and what is checked here is that the product computes that definition bit for bit.
+@pytest.mark.parametrize("seed", range(4))
+def test_smooth_triangle_worlds_bit_exact(rtc, oracle, hostsim, seed):
+    world, cam = _wrap(rtc, *worldgen.smooth_world(rtc.api(), seed))
+    ow, oc = worldgen.smooth_world(oracle, seed)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    assert world.kernel_features()[0] & 2048
+    rgb, _, scnt = hostsim.scene(world).render(cam)
+    assert _bits_equal(ref, rgb), f"seed {seed}: {np.count_nonzero((ref != rgb).any(axis=1))} pixels differ"
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+
+
+def test_smooth_cow_and_teddy_bit_exact_and_different_from_flat(rtc, oracle, hostsim):
+    world, cam = rtc.build_scene("cow_teddy_smooth", 96, 54)
+    assert world.kernel_features() == (98 + 2048, 98 + 2048)  # its own instantiation
+    ow, oc = helpers.scenes.build(oracle, "cow_teddy_smooth", 96, 54)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    rgb, _, scnt = hostsim.scene(world).render(cam)
+    assert _bits_equal(ref, rgb)
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+    fw, fc = helpers.scenes.build(oracle, "cow_teddy", 96, 54)
+    flat, _ = oracle.render(fw, fc, mode=oracle.CACHED)
+    assert (flat != ref).any(axis=1).mean() > 0.05  # interpolated normals do change the shading
+
+
+OBJ_WITH_NORMALS = """
+v 0 1 0
+v -1 0 0
+v 1 0 0
+v 0 -1 0.5
+
+vn -1 0 -0.2
+vn 1 0 -0.2
+vn 0 1 -0.2
+vn 0 -1 -1
+
+f 1//3 2//1 3//2
+f 2/7/1 4/8/4 3/9/2
+f 1 2 4
+g side
+f 1//3 3//2 4//4 2//1
+"""
+
+
+def test_obj_with_vertex_normals_parses_like_the_oracle(rtc, oracle, hostsim):
+    """obj_file.rs:295-335 (commented scenarios): `vn` records, `f v//n` and `f v/t/n` corners, a flat face among them,
+    fan triangulation carrying the normals, a named group — parsed by the product's parser and by the oracle's, rendered
+    by both."""
+    def build(api):
+        T, S = worldgen.sa.Transformations(api), worldgen.sa.Shapes(api)
+        cam = worldgen.sa.CameraHandle(api, 40, 30, 0.8)
+        cam.set_transform(T.view_transform((0.3, 0.4, -4.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0)))
+        world = worldgen.sa.WorldHandle(api, worldgen.sa.Light((-3.0, 4.0, -5.0), (1.0, 1.0, 1.0)))
+        g = S.obj_str(OBJ_WITH_NORMALS)
+        assert g.ignored_lines == 0 and g.leaf_count() == 5
+        g.set_transform(T.rotation_y(0.3) * T.scaling(1.2, 1.0, 1.0))
+        world.push(g)
+        return world, cam
+    world, cam = _wrap(rtc, *build(rtc.api()))
+    ow, oc = build(oracle)
+    ref, cnt = oracle.render(ow, oc, mode=oracle.CACHED)
+    assert (ref != 0).any()
+    rgb, _, scnt = hostsim.scene(world).render(cam)
+    assert _bits_equal(ref, rgb)
+    assert scnt == [cnt.primary, cnt.shadow, cnt.reflect, cnt.refract]
+    with pytest.raises(ValueError):  # a normal index past the `vn` records panics like a vertex index does
+        worldgen.sa.Shapes(rtc.api()).obj_str("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//2 3//1\n")
+    with pytest.raises(ValueError):
+        worldgen.sa.Shapes(oracle).obj_str("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//2 3//1\n")

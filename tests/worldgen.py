@@ -276,3 +276,63 @@ def chained_equal_world(api):
         s.set_transform(T.translation(8e-6 * k, 0.0, 0.0))
         world.push(s)
     return world, cam
+
+
+def smooth_world(api, seed, hsize=48, vsize=32):
+    """-> (world, camera).  Smooth triangles (the book's SmoothTriangle, absent from the reference): a lumpy shell whose
+    every triangle carries vertex normals (one of glass: refraction bends along the interpolated normal, the n1/n2 walk
+    crosses smooth triangles), a hand-built group that MIXES flat and smooth triangles in one run (one mesh on the
+    device), a reflective floor that mirrors them, and a non-uniformly scaled transform (normal_to_world matters)."""
+    rng = np.random.default_rng(3000 + seed)
+    T, S = sa.Transformations(api), sa.Shapes(api)
+    cam = sa.CameraHandle(api, hsize, vsize, rng.uniform(0.7, 1.0))
+    cam.set_transform(T.view_transform((rng.uniform(-2, 2), rng.uniform(1, 3), -7.0), (0.0, 0.3, 0.0), (0.0, 1.0, 0.0)))
+    world = sa.WorldHandle(api, sa.Light((rng.uniform(-5, 5), 7.0, -6.0), (1.0, 1.0, 0.95)))
+    floor = S.plane()
+    floor.set_transform(T.translation(0, -1.6, 0))
+    fm = sa.Material()
+    fm.reflective = 0.35
+    fm.pattern = sa.Pattern.checkers((0.2, 0.2, 0.2), (0.9, 0.9, 0.9))
+    floor.material = fm
+    world.push(floor)
+
+    def shell(nu, nv, radius, lump):
+        us = np.linspace(0, 2 * math.pi, nu, endpoint=False)
+        vs = np.linspace(0.15, math.pi - 0.15, nv)
+        verts = []
+        for v in vs:
+            for u in us:
+                r = radius * (1 + lump * math.sin(3 * u) * math.sin(2 * v))
+                verts.append((r * math.sin(v) * math.cos(u), r * math.cos(v), r * math.sin(v) * math.sin(u)))
+        faces = []
+        for j in range(nv - 1):
+            for i in range(nu):
+                a, b = j * nu + i, j * nu + (i + 1) % nu
+                c, d = a + nu, b + nu
+                faces += [(a + 1, b + 1, c + 1), (b + 1, d + 1, c + 1)]
+        return np.array(verts, dtype=np.float64), np.array(faces, dtype=np.int32)
+
+    for k in range(2):
+        v, f = shell(int(rng.integers(10, 16)), int(rng.integers(8, 12)), rng.uniform(0.8, 1.3), rng.uniform(0.0, 0.3))
+        n = v / np.linalg.norm(v, axis=1, keepdims=True) + rng.normal(0, 0.05, v.shape)  # not unit length on purpose
+        if k == 0:
+            g = S.smooth_mesh(v, n, f)
+        else:  # flat and smooth triangles interleaved in one run of siblings
+            g = S.group()
+            for j, (a, b, c) in enumerate(f):
+                if j % 3 == 0:
+                    g.push_shape(S.triangle(v[a - 1], v[b - 1], v[c - 1]))
+                else:
+                    g.push_shape(S.smooth_triangle(v[a - 1], v[b - 1], v[c - 1], n[a - 1], n[b - 1], n[c - 1]))
+        m = sa.Material()
+        m.color = tuple(rng.uniform(0.2, 1.0, 3))
+        if k == 0 and seed % 2 == 0:
+            m.transparency, m.refractive_index, m.reflective = 0.8, 1.5, 0.3
+            m.diffuse, m.ambient = 0.2, 0.05
+        else:
+            m.reflective = rng.uniform(0.0, 0.5)
+        g.set_material(m)
+        g.set_transform(T.translation(-1.4 + 2.8 * k, rng.uniform(-0.2, 0.4), rng.uniform(-0.5, 0.5)) *
+                        T.rotation_y(rng.uniform(0, 3)) * T.scaling(1.0, rng.uniform(0.5, 1.4), 0.8))
+        world.push(g)
+    return world, cam
