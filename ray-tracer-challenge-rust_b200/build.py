@@ -57,8 +57,9 @@ def _nvcc():
 
 def _sources():
     out = []
-    for d, _, files in os.walk(CSRC):
-        out += [os.path.join(d, f) for f in files]
+    for d, dirs, files in os.walk(CSRC):
+        dirs[:] = [x for x in dirs if not x.startswith(".") and x != "__pycache__"]  # tool caches are not sources
+        out += [os.path.join(d, f) for f in files if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h", ".txt"))]
     out += [os.path.join(ROOT, "include", "rtc.h"), os.path.abspath(__file__)]
     return out
 

@@ -282,13 +282,13 @@ def test_probes_agree_with_the_oracle_on_a_mesh(rtc, oracle):
     ref, _ = oracle.render(ow, oc, mode=oracle.CACHED)
     d = cam.desc()
     rays = []
-    o = np.empty(3)
-    dr = np.empty(3)
+    o = np.empty(4)   # orc_camera_ray_for_pixel writes 4-tuples (x, y, z, w)
+    dr = np.empty(4)
     for y in range(12):
         for x in range(24):
             oracle.camera_ray_for_pixel(oc.h, x, y, o.ctypes.data_as(helpers._capi.c_double_p),
                                         dr.ctypes.data_as(helpers._capi.c_double_p))
-            rays.append(list(o) + list(dr))
+            rays.append(list(o[:3]) + list(dr[:3]))
     xs = world.intersect(rays)
     hits = np.array([any(t >= 0 for t, _ in x) for x in xs])
     lit = (ref.reshape(-1, 3) != 0).any(axis=1)
