@@ -245,6 +245,11 @@ int rtc_render_tally(const rtc_scene* scene, const rtc_camera_desc* camera, cons
  * counted as 2.  Used as the FP64 roofline denominator (the path must run without FMA contraction). */
 int rtc_measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops);
 
+/* Self-test of the kernels' shared-divisor division (several IEEE quotients over one divisor with the reciprocal refinement
+ * done once; csrc/rt_core.cuh SharedDivisor): `pairs` generated operand pairs — raw bit patterns, ordinary magnitudes,
+ * special values — each divided both ways on the device and compared bit for bit.  *mismatches must come back 0. */
+int rtc_selftest_shared_divisor(int device, uint64_t pairs, uint64_t seed, uint64_t* mismatches);
+
 const char* rtc_last_error(void);
 int rtc_device_count(void);
 /* cudaDeviceEnablePeerAccess(peer) from `device` (no-op if already enabled): lets kernels launched on `device` store into

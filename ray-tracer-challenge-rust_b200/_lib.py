@@ -67,6 +67,7 @@ class RtcApi(BuilderApi):
         f("prepare_computations", C.c_int, vp, c_double_p, C.c_uint64, C.POINTER(Computations))
         f("normal_at", C.c_int, vp, C.c_int32, c_double_p, C.c_uint64, c_double_p)
         f("measure_fp64_peak", C.c_int, C.c_int, c_double_p, c_double_p)
+        f("selftest_shared_divisor", C.c_int, C.c_int, C.c_uint64, C.c_uint64, c_u64_p)
         f("world_color_at", C.c_int, vp, c_double_p, C.c_uint64, c_double_p)
         f("world_scene", C.c_int, vp, C.c_int, C.POINTER(vp))
         f("world_set_build", C.c_int, vp, C.c_uint32)

@@ -349,6 +349,13 @@ int rtc_normal_at(const rtc_scene* scene, int32_t leaf, const double* points, ui
     return RTC_OK;
 }
 
+int rtc_selftest_shared_divisor(int device, uint64_t pairs, uint64_t seed, uint64_t* mismatches) {
+    if (!mismatches) return set_err(RTC_ERR_INVALID, "null argument");
+    std::string e;
+    if (divisor_selftest(device, pairs, seed, mismatches, &e) != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+
 int rtc_tally_count(void) { return tally_count(); }
 int rtc_render_tally(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows, uint64_t* counts) {
     if (!scene || !camera || !counts) return set_err(RTC_ERR_INVALID, "null argument");

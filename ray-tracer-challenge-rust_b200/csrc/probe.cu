@@ -133,6 +133,49 @@ __global__ void find_leaf_kernel(const __grid_constant__ DScene s, uint32_t n_tr
         }
 }
 
+// div_by(a, shared_divisor(d)) against the compiler's own a / d (rt_core.cuh): operand pairs from a counter-based
+// generator — raw 64-bit patterns (every exponent, NaNs, infinities, subnormals), values of ordinary magnitude, and
+// specials paired with everything — compared bit for bit.
+__device__ unsigned long long mix64(unsigned long long x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) divisor_selftest_kernel(unsigned long long pairs_per_thread, unsigned long long seed,
+                                                               unsigned long long* mismatches) {
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const double specials[12] = {0.0, -0.0, 1.0, -1.0, 2.0, 0.5, 1e-5, RTC_INF, -RTC_INF, __longlong_as_double(0x7ff8000000000000LL),
+                                 __longlong_as_double(0x0000000000000001LL), __longlong_as_double(0x7fefffffffffffffLL)};
+    unsigned long long bad = 0;
+    for (unsigned long long k = 0; k < pairs_per_thread; k++) {
+        const unsigned long long h0 = mix64(seed ^ (tid * pairs_per_thread + k) * 3ull);
+        const unsigned long long h1 = mix64(h0), h2 = mix64(h1);
+        double a, d;
+        switch (h2 & 3) {
+            case 0:  // raw bit patterns
+                a = __longlong_as_double((long long)h0);
+                d = __longlong_as_double((long long)h1);
+                break;
+            case 1:
+            case 2: {  // ordinary magnitudes: random mantissa, exponent within 2^-40 .. 2^40
+                const unsigned long long ea = 1023ull - 40ull + ((h2 >> 8) % 81ull), ed = 1023ull - 40ull + ((h2 >> 20) % 81ull);
+                a = __longlong_as_double((long long)((h0 & 0x800fffffffffffffull) | (ea << 52)));
+                d = __longlong_as_double((long long)((h1 & 0x800fffffffffffffull) | (ed << 52)));
+                break;
+            }
+            default:  // a special on one side or both
+                a = ((h2 >> 4) & 1) ? specials[(h2 >> 8) % 12] : __longlong_as_double((long long)h0);
+                d = ((h2 >> 5) & 1) ? specials[(h2 >> 16) % 12] : __longlong_as_double((long long)h1);
+                break;
+        }
+        const SharedDivisor sd = shared_divisor(d);
+        const double q = div_by(a, sd), ref = a / d;
+        if (__double_as_longlong(q) != __double_as_longlong(ref)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 struct Scratch {  // device buffers of one probe call, freed on every path out
     void* p[4] = {nullptr, nullptr, nullptr, nullptr};
     ~Scratch() {
@@ -190,6 +233,20 @@ int probe_prepare(DeviceScene* s, const double* rays, uint64_t n, rtc_computatio
     PROBE_CUDA(cudaGetLastError());
     PROBE_CUDA(cudaMemcpyAsync(out, d.p[1], n * sizeof(rtc_computations), cudaMemcpyDeviceToHost, s->stream));
     PROBE_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int divisor_selftest(int device, uint64_t pairs, uint64_t seed, uint64_t* mismatches, std::string* err) {
+    DeviceGuard guard_;
+    PROBE_CUDA(cudaSetDevice(device));
+    Scratch d;
+    PROBE_CUDA(cudaMalloc(&d.p[0], 8));
+    PROBE_CUDA(cudaMemset(d.p[0], 0, 8));
+    const unsigned blocks = 148 * 8, threads = 256;
+    const unsigned long long per_thread = (pairs + (uint64_t)blocks * threads - 1) / ((uint64_t)blocks * threads);
+    divisor_selftest_kernel<<<blocks, threads>>>(per_thread, seed, (unsigned long long*)d.p[0]);
+    PROBE_CUDA(cudaGetLastError());
+    PROBE_CUDA(cudaMemcpy(mismatches, d.p[0], 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -70,6 +70,9 @@ int probe_prepare(DeviceScene* s, const double* rays, uint64_t n, rtc_computatio
 int probe_normal_at(DeviceScene* s, uint64_t n_tris, int32_t leaf, const double* points, uint64_t n, double* out,
                     std::string* err);
 
+// Self-test of rt_core.cuh's SharedDivisor against the compiler's f64 division over `pairs` generated operand pairs.
+int divisor_selftest(int device, uint64_t pairs, uint64_t seed, uint64_t* mismatches, std::string* err);
+
 // Work tallies of one frame (render_tally.cu): counts[tally_count()] in TallyIndex order (rt_core.cuh).
 int tally_count();
 int render_tally(DeviceScene* s, const DCamera& cam, const DRows& rows, unsigned long long* counts, std::string* err);

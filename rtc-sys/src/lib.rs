@@ -272,6 +272,7 @@ extern "C" {
         counts: *mut u64,
     ) -> c_int;
     pub fn rtc_measure_fp64_peak(device: c_int, nofma_gflops: *mut f64, fma_gflops: *mut f64) -> c_int;
+    pub fn rtc_selftest_shared_divisor(device: c_int, pairs: u64, seed: u64, mismatches: *mut u64) -> c_int;
 
     pub fn rtc_enable_peer_access(device: c_int, peer: c_int) -> c_int;
     pub fn rtc_frame_share_create(device: c_int, bytes: u64, d_ptr: *mut *mut c_void, handle64: *mut u8) -> c_int;

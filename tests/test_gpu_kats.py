@@ -328,3 +328,15 @@ def test_obj_faces_with_normals(kit):
         np.testing.assert_allclose(w.normal_at(leaf, [[0.45, 0.25, 0.0]])[0], [-0.5547, 0.83205, 0.0], atol=ATOL)
         np.testing.assert_allclose(w.normal_at(leaf, [[0.0, 0.0, 0.0]])[0], [0.0, 1.0, 0.0], atol=ATOL)   # n1 at p1
         np.testing.assert_allclose(w.normal_at(leaf, [[1.0, 0.0, 0.0]])[0], [-1.0, 0.0, 0.0], atol=ATOL)  # n2 at p2
+
+
+def test_shared_divisor(rtc):
+    """rt_core.cuh SharedDivisor: x / m, y / m, z / m (and check_axis's two quotients, the quadratics' two roots) with the
+    reciprocal refinement of the compiler's own division sequence done once — every quotient must be bit for bit the
+    compiler's a / d.  10^9 operand pairs per seed: raw bit patterns, ordinary magnitudes, special values."""
+    import ctypes as C
+    api = rtc.api()
+    for seed in (1, 2, 3):
+        bad = C.c_uint64(123)
+        api.check(api.selftest_shared_divisor(0, 10 ** 9, seed, C.byref(bad)))
+        assert bad.value == 0
