@@ -40,14 +40,18 @@ struct alignas(16) DPrim {
     int32_t pad[2];
 };
 static_assert(sizeof(DPrim) == 48, "DPrim layout: read with 16-byte loads");
-// The padded world box of a clustered leaf (f32, rounded outward), indexed like prims[]: a cluster of up to
-// kClusterListMax leaves is a plain LIST of these, scanned front to back — measured faster than a tree over so few boxes
-// (table scene, 18 cubes: 0.99 ms with a BVH, profiles/r02c_variants.json) because the scan has no stack, no divergent
-// descent and half the loads; larger clusters get the BVH.
+// A cluster of up to kClusterListMax leaves is a SKIP LIST of padded f32 world boxes (rounded outward), walked front to
+// back with no stack: a LEAF entry (skip < 0) is one leaf's box — the exact test of prims[prim] runs if the ray passes it;
+// a HEADER entry (skip >= 0) is the box around the next `skip` entries — a ray that misses it jumps past them.  Headers are
+// the inner nodes of a SAH tree over the leaves, kept only where the expected number of box tests falls (flatten.hpp).
+// Measured against a stack-based BVH walk over the same few boxes (table scene, 18 cubes: 0.93 ms) and against the flat
+// list without headers (0.62 ms): profiles/r02c_variants.json, r02p_variants.json.  Larger clusters get the BVH.
 struct alignas(16) DBox32 {
     float lo[3], hi[3];
-    float pad[2];
+    int32_t skip;  // >= 0: header over the next `skip` entries; -1: leaf
+    int32_t prim;  // leaf: index into prims[]
 };
+static_assert(sizeof(DBox32) == 32, "DBox32 layout: read with two 16-byte loads");
 constexpr int kClusterListMax = 32;
 struct DGate {
     double lo[3], hi[3];
@@ -62,10 +66,10 @@ struct DGate {
 // takes the exact linear scan of the cluster's leaves.
 struct DMesh {
     int32_t xform, root, tri_base, tri_count;  // root < 0: no BVH — a tiny mesh (scan its triangles) or a LIST cluster
-                                               // (scan prim_boxes[tri_base .. tri_base + tri_count), DBox32)
     float extent;                              // max |coordinate| of the boxes (f32 slab error bound)
     float cx, cy, cz, rfast2;                  // CLUSTER: centre and squared reach of the fast path
-    int32_t pad[3];
+    int32_t entry_base, entry_count;           // LIST cluster: its skip list is cluster_entries[entry_base .. + entry_count)
+    int32_t pad;
 };
 static_assert(sizeof(DMesh) == 48, "DMesh layout");
 // f32 boxes rounded OUTWARD from the padded f64 boxes: 64 bytes hold both children, one fetch decides two subtrees.
@@ -117,7 +121,7 @@ struct DScene {
     const DTri* tris;
     const DTriAttr* tri_attr;
     const DMaterial* materials;
-    const DBox32* prim_boxes;
+    const DBox32* cluster_entries;
     const DTriSmooth* tri_smooth;  // null: no smooth triangle in the scene
     const int32_t* class_offsets;
     const DClassMember* class_members;

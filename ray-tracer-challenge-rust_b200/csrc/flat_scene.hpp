@@ -32,7 +32,7 @@ struct FlatScene {
     std::vector<DXform> xforms;
     std::vector<DPrim> prims;
     std::vector<DTriSmooth> tri_smooth;  // empty, or same length as tris
-    std::vector<DBox32> prim_boxes;  // same length as prims (zero for leaves outside LIST clusters)
+    std::vector<DBox32> cluster_entries;  // skip lists of the LIST clusters (device_scene.h DBox32)
     std::vector<DGate> gates;
     std::vector<DMesh> meshes;
     std::vector<DBvhNode> bvh;

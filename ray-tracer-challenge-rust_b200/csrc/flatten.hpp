@@ -45,6 +45,11 @@ struct FlattenOptions {
 #else
     bool clusters = true;            // gather bounded sibling leaves into BVH clusters (off: every leaf is a PRIM entry)
 #endif
+#if defined(RTC_NO_CLUSTER_HEADERS)  // A/B switch: LIST clusters without header entries (a flat list of leaf boxes)
+    bool cluster_headers = false;
+#else
+    bool cluster_headers = true;
+#endif
 };
 constexpr uint32_t kDeviceBuildMin = 256;
 
@@ -368,11 +373,115 @@ class Flattener {
             if (d_.shapes[c].kind != RTC_GROUP && !is_tri(d_.shapes[c].kind) && leaf_world_box(d_.shapes[c], tmp)) n++;
         return n;
     }
-    void push_prim(const DPrim& p, const DBox32* box = nullptr) {
+    void push_prim(const DPrim& p) { out_.prims.push_back(p); }
+
+    // ---- the skip list of a LIST cluster (device_scene.h DBox32) -------------------------------------------------------
+    // A small exact-sweep SAH tree over the leaves' padded boxes, written out in depth-first order; an inner node becomes a
+    // HEADER entry only where that lowers the expected number of box tests (surface-area heuristic: a ray that enters a box
+    // of area A enters a box of area a inside it with probability a / A).  The root is never a header: the scenes this serves
+    // have the camera inside the cluster.
+    struct SkipNode {
+        double lo[3], hi[3];
+        int left = -1, right = -1;  // inner
+        int item = -1;              // leaf: index into the cluster's run
+        int leaves = 1;
+    };
+    static double box_area(const double* lo, const double* hi) {
+        const double x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+        return 2.0 * (x * y + y * z + z * x);
+    }
+    static int skip_build(std::vector<SkipNode>& nodes, const std::vector<detail::Item>& items, std::vector<int> idx) {
+        SkipNode nd;
+        for (int a = 0; a < 3; a++) {
+            nd.lo[a] = 1e300;
+            nd.hi[a] = -1e300;
+        }
+        for (int i : idx)
+            for (int a = 0; a < 3; a++) {
+                nd.lo[a] = std::fmin(nd.lo[a], items[i].lo[a]);
+                nd.hi[a] = std::fmax(nd.hi[a], items[i].hi[a]);
+            }
+        nd.leaves = (int)idx.size();
+        if (idx.size() == 1) {
+            nd.item = idx[0];
+            nodes.push_back(nd);
+            return (int)nodes.size() - 1;
+        }
+        double best = 1e300;
+        std::vector<int> best_l, best_r;
+        for (int axis = 0; axis < 3; axis++) {
+            std::vector<int> o = idx;
+            std::stable_sort(o.begin(), o.end(), [&](int x, int y) { return items[x].c[axis] < items[y].c[axis]; });
+            for (size_t cut = 1; cut < o.size(); cut++) {
+                double lo[2][3], hi[2][3];
+                for (int h = 0; h < 2; h++)
+                    for (int a = 0; a < 3; a++) {
+                        lo[h][a] = 1e300;
+                        hi[h][a] = -1e300;
+                    }
+                for (size_t k = 0; k < o.size(); k++) {
+                    const int h = k < cut ? 0 : 1;
+                    for (int a = 0; a < 3; a++) {
+                        lo[h][a] = std::fmin(lo[h][a], items[o[k]].lo[a]);
+                        hi[h][a] = std::fmax(hi[h][a], items[o[k]].hi[a]);
+                    }
+                }
+                const double cost = box_area(lo[0], hi[0]) * (double)cut + box_area(lo[1], hi[1]) * (double)(o.size() - cut);
+                if (cost < best) {
+                    best = cost;
+                    best_l.assign(o.begin(), o.begin() + cut);
+                    best_r.assign(o.begin() + cut, o.end());
+                }
+            }
+        }
+        const int l = skip_build(nodes, items, best_l), r = skip_build(nodes, items, best_r);
+        nd.left = l;
+        nd.right = r;
+        nodes.push_back(nd);
+        return (int)nodes.size() - 1;
+    }
+    // Expected box tests of subtree n when the nearest tested box above it is node `anc` (-1: none — the walk starts here);
+    // memoised per (n, anc).  .second: make n a header in that context.
+    using SkipMemo = std::map<std::pair<int, int>, std::pair<double, bool>>;
+    static std::pair<double, bool> skip_cost(const std::vector<SkipNode>& nodes, int n, int anc, SkipMemo& memo) {
+        const SkipNode& nd = nodes[n];
+        if (nd.item >= 0) return {1.0, false};
+        const auto key = std::make_pair(n, anc);
+        const auto it = memo.find(key);
+        if (it != memo.end()) return it->second;
+        const double plain = skip_cost(nodes, nd.left, anc, memo).first + skip_cost(nodes, nd.right, anc, memo).first;
+        const double area = box_area(nd.lo, nd.hi);
+        const double within = anc >= 0 ? box_area(nodes[anc].lo, nodes[anc].hi) : 0.0;
+        const double p = within > 0.0 ? std::fmin(1.0, area / within) : 1.0;
+        const double head = 1.0 + p * (skip_cost(nodes, nd.left, n, memo).first + skip_cost(nodes, nd.right, n, memo).first);
+        const bool use = anc >= 0 && nd.leaves >= 3 && head < plain;  // anc < 0: the root is never a header
+        const std::pair<double, bool> r{use ? head : plain, use};
+        memo.emplace(key, r);
+        return r;
+    }
+    void skip_emit(const std::vector<SkipNode>& nodes, int n, int anc, SkipMemo& memo, bool headers, double pad,
+                   int32_t prim_base) {
+        const SkipNode& nd = nodes[n];
+        const bool head = nd.item < 0 && headers && skip_cost(nodes, n, anc, memo).second;
+        if (nd.item < 0 && !head) {
+            skip_emit(nodes, nd.left, anc, memo, headers, pad, prim_base);
+            skip_emit(nodes, nd.right, anc, memo, headers, pad, prim_base);
+            return;
+        }
         DBox32 b;
         std::memset(&b, 0, sizeof(b));
-        out_.prims.push_back(p);
-        out_.prim_boxes.push_back(box ? *box : b);
+        for (int a = 0; a < 3; a++) {
+            b.lo[a] = detail::f32_below(nd.lo[a] - pad);
+            b.hi[a] = detail::f32_above(nd.hi[a] + pad);
+        }
+        b.skip = -1;
+        b.prim = nd.item >= 0 ? prim_base + nd.item : -1;
+        const size_t at = out_.cluster_entries.size();
+        out_.cluster_entries.push_back(b);
+        if (nd.item >= 0) return;
+        skip_emit(nodes, nd.left, n, memo, headers, pad, prim_base);
+        skip_emit(nodes, nd.right, n, memo, headers, pad, prim_base);
+        out_.cluster_entries[at].skip = (int32_t)(out_.cluster_entries.size() - at - 1);
     }
     void set_site(uint32_t leaf, const LeafSite& st) {
         if (!want_classes_) return;
@@ -427,18 +536,22 @@ class Flattener {
         // the device measures the origin's distance in f32 from the f32 centre: both roundings are far inside the 1.25
         m.rfast2 = detail::f32_below(reach * reach);
         const int32_t node = (int32_t)out_.program.size();
-        if (n <= (uint32_t)kClusterListMax) {  // a LIST: leaves in DFS order, each with its padded box
+        if (n <= (uint32_t)kClusterListMax) {  // a LIST: leaves in DFS order in prims[], the skip list over their boxes
             m.root = -1;
+            m.entry_base = (int32_t)out_.cluster_entries.size();
+            std::vector<SkipNode> nodes;
+            std::vector<int> all(n);
+            for (uint32_t k = 0; k < n; k++) all[k] = (int)k;
+            const int root = skip_build(nodes, items, all);
+            SkipMemo memo;
+            // the root is never a header, but its box is what the headers beneath it are measured against
+            skip_emit(nodes, nodes[root].left, root, memo, opts_.cluster_headers, pad, m.tri_base);
+            skip_emit(nodes, nodes[root].right, root, memo, opts_.cluster_headers, pad, m.tri_base);
+            m.entry_count = (int32_t)out_.cluster_entries.size() - m.entry_base;
             for (uint32_t k = 0; k < n; k++) {
                 const ClusterItem& ci = run[k];
-                DBox32 b;
-                std::memset(&b, 0, sizeof(b));
-                for (int a = 0; a < 3; a++) {
-                    b.lo[a] = detail::f32_below(items[k].lo[a] - pad);
-                    b.hi[a] = detail::f32_above(items[k].hi[a] + pad);
-                }
                 set_site((uint32_t)ci.prim.leaf, LeafSite{ci.shape, node, (int32_t)out_.prims.size()});
-                push_prim(ci.prim, &b);
+                push_prim(ci.prim);
             }
         } else {
             std::vector<uint32_t> order;
@@ -764,7 +877,7 @@ class Flattener {
             m.tri_count = (int32_t)n;
             m.extent = 0.f;
             m.cx = m.cy = m.cz = m.rfast2 = 0.f;
-            m.pad[0] = m.pad[1] = m.pad[2] = 0;
+            m.entry_base = m.entry_count = m.pad = 0;
             out_.pending.push_back(p);
             for (uint32_t k = 0; k < n; k++) set_site(p.leaf0 + k, LeafSite{begin + k, (int32_t)out_.program.size(), -1});
             out_.program.push_back(DProgramNode{NODE_MESH, (int32_t)out_.meshes.size(), 0, gate_node_});
@@ -816,7 +929,7 @@ class Flattener {
         if (attr_thread.joinable()) attr_thread.join();
         m.extent = f32_above_(max_abs * (1.0 + 2.0 * kPadRel));
         m.cx = m.cy = m.cz = m.rfast2 = 0.f;
-        m.pad[0] = m.pad[1] = m.pad[2] = 0;
+        m.entry_base = m.entry_count = m.pad = 0;
         if (depth > out_.bvh_max_depth) out_.bvh_max_depth = depth;
         if (depth + 2 > kBvhStackDepth)
             fail(RTC_ERR_UNSUPPORTED, "mesh BVH deeper than the device traversal stack (more than ~16M triangles)");

@@ -219,7 +219,7 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
                              with_extra(f.tris.size() * sizeof(DTri), (size_t)f.device_tris * sizeof(DTri)),
                              with_extra(f.tri_attr.size() * sizeof(DTriAttr), (size_t)f.device_tris * sizeof(DTriAttr)),
                              slab_bytes(f.materials), slab_bytes(f.class_offsets), slab_bytes(f.class_members),
-                             slab_bytes(f.prim_boxes), slab_bytes(f.tri_smooth)};
+                             slab_bytes(f.cluster_entries), slab_bytes(f.tri_smooth)};
     size_t total = 256;
     for (size_t b : sizes) total += b;
     // pinned staging mirrors the slab's layout (one copy when nothing is device-built), followed by the device build's inputs
@@ -235,13 +235,13 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     size_t off[kTables], at = 0;
     const void* src[kTables] = {f.program.data(), f.xforms.data(),   f.prims.data(),    f.gates.data(), f.meshes.data(),
                           f.bvh.data(),     f.tris.data(),     f.tri_attr.data(), f.materials.data(),
-                          f.class_offsets.data(), f.class_members.data(), f.prim_boxes.data(), f.tri_smooth.data()};
+                          f.class_offsets.data(), f.class_members.data(), f.cluster_entries.data(), f.tri_smooth.data()};
     const size_t raw[kTables] = {f.program.size() * sizeof(DProgramNode), f.xforms.size() * sizeof(DXform),
                            f.prims.size() * sizeof(DPrim),          f.gates.size() * sizeof(DGate),
                            f.meshes.size() * sizeof(DMesh),         f.bvh.size() * sizeof(DBvhNode),
                            f.tris.size() * sizeof(DTri),            f.tri_attr.size() * sizeof(DTriAttr),
                            f.materials.size() * sizeof(DMaterial),  f.class_offsets.size() * sizeof(int32_t),
-                           f.class_members.size() * sizeof(DClassMember), f.prim_boxes.size() * sizeof(DBox32),
+                           f.class_members.size() * sizeof(DClassMember), f.cluster_entries.size() * sizeof(DBox32),
                            f.tri_smooth.size() * sizeof(DTriSmooth)};
     for (int k = 0; k < kTables; k++) {
         off[k] = at;
@@ -308,7 +308,7 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->view.materials = (const DMaterial*)(base + off[8]);
     s->view.class_offsets = (const int32_t*)(base + off[9]);
     s->view.class_members = (const DClassMember*)(base + off[10]);
-    s->view.prim_boxes = (const DBox32*)(base + off[11]);
+    s->view.cluster_entries = (const DBox32*)(base + off[11]);
     s->view.tri_smooth = f.tri_smooth.empty() ? nullptr : (const DTriSmooth*)(base + off[12]);
     s->view.n_classes = f.class_offsets.empty() ? 0 : (int32_t)f.class_offsets.size() - 1;
     s->view.pad1 = 0;

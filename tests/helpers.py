@@ -106,6 +106,8 @@ class HostSim:
         self.lib.sim_scene_gates.argtypes = [vp, _capi.c_double_p, C.c_uint64]
         self.lib.sim_scene_gates.restype = C.c_uint64
         self.lib.sim_scene_destroy.argtypes = [vp]
+        self.lib.sim_scene_cluster_entries.argtypes = [vp, C.POINTER(C.c_int32), C.c_uint64]
+        self.lib.sim_scene_cluster_entries.restype = C.c_uint64
         self.lib.sim_render.argtypes = [vp, C.POINTER(_capi.CameraDesc), C.POINTER(C.c_uint32), C.c_uint64, C.c_int,
                                         _capi.c_double_p, C.POINTER(C.c_uint8), _capi.c_u64_p]
         self.lib.sim_color_at.argtypes = [vp, _capi.c_double_p, C.c_uint64, _capi.c_double_p]
@@ -139,6 +141,12 @@ class SimScene:
         buf = np.zeros((64, 6))
         n = self.sim.lib.sim_scene_gates(self.h, buf.ctypes.data_as(_capi.c_double_p), 64)
         return buf[:n]
+
+    def cluster_entries(self):
+        """[(skip, prim), ...] of every LIST cluster's skip list (device_scene.h DBox32)."""
+        buf = np.zeros((4096, 2), dtype=np.int32)
+        n = self.sim.lib.sim_scene_cluster_entries(self.h, buf.ctypes.data_as(C.POINTER(C.c_int32)), 4096)
+        return [tuple(int(x) for x in row) for row in buf[:n]]
 
     def tables(self):
         """(bvh nodes, triangles, meshes, content hash of the mesh tables)."""

@@ -54,7 +54,7 @@ int sim_scene_create_ex(const rtc_scene_desc* desc, int device_build, void** out
     v.tris = s->flat.tris.data();
     v.tri_attr = s->flat.tri_attr.data();
     v.materials = s->flat.materials.data();
-    v.prim_boxes = s->flat.prim_boxes.data();
+    v.cluster_entries = s->flat.cluster_entries.data();
     v.tri_smooth = s->flat.tri_smooth.empty() ? nullptr : s->flat.tri_smooth.data();
     v.class_offsets = s->flat.class_offsets.data();
     v.class_members = s->flat.class_members.data();
@@ -80,6 +80,16 @@ uint64_t sim_scene_gates(void* scene, double* out, uint64_t cap) {
     return s->flat.gates.size();
 }
 // table sizes and a content hash of the mesh tables (FNV-1a over bvh, tris, tri_attr), to compare builds
+// the skip lists of the LIST clusters: per entry (skip, prim); returns the number of entries
+uint64_t sim_scene_cluster_entries(void* scene, int32_t* out, uint64_t cap) {
+    Sim* s = (Sim*)scene;
+    const uint64_t n = s->flat.cluster_entries.size();
+    for (uint64_t i = 0; i < n && i < cap; i++) {
+        out[2 * i] = s->flat.cluster_entries[i].skip;
+        out[2 * i + 1] = s->flat.cluster_entries[i].prim;
+    }
+    return n;
+}
 void sim_scene_tables(void* scene, uint64_t n[4]) {
     Sim* s = (Sim*)scene;
     n[0] = s->flat.bvh.size();

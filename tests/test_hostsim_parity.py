@@ -463,3 +463,20 @@ def test_obj_with_vertex_normals_parses_like_the_oracle(rtc, oracle, hostsim):
         worldgen.sa.Shapes(rtc.api()).obj_str("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//2 3//1\n")
     with pytest.raises(ValueError):
         worldgen.sa.Shapes(oracle).obj_str("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//2 3//1\n")
+
+
+def test_cluster_skip_list_is_well_formed(rtc, hostsim):
+    """The table scene's 18 cubes are one LIST cluster: every leaf is in its skip list exactly once, every header covers
+    entries inside the list, headers nest, and there ARE headers (the table and what stands on it, the pictures on the
+    walls) — a ray that misses a header's box skips its leaves."""
+    world, cam = rtc.build_scene("table", 64, 36)
+    e = hostsim.scene(world).cluster_entries()
+    leaves = sorted(p for s, p in e if s < 0)
+    assert leaves == list(range(18))
+    headers = [(i, s) for i, (s, p) in enumerate(e) if s >= 0]
+    assert len(headers) >= 2 and len(e) == 18 + len(headers)
+    for i, s in headers:
+        assert e[i][1] == -1 and s >= 3 and i + s < len(e) + 0  # covers at least three entries, all inside the list
+        for j, t in headers:
+            if i < j <= i + s:
+                assert j + t <= i + s  # nested, never straddling
