@@ -34,32 +34,97 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
     RayCounters rc;
     Tally tl;
     uint32_t primary = 0;
-    // Tile queue: one atomic per tile.  Measured and rejected: guided batches of 4/8/16 tiles per atomic (1.1x-3x slower on
-    // every config — neighbouring heavy tiles land on one warp; profiles/r01g_tile_batch_sweep.json) and requesting the
-    // NEXT tile before rendering the current one to hide the atomic's round trip (4-8 % slower on every config: the
-    // pending result holds a register across the whole tile; profiles/r02c_variants.json).
-    for (;;) {
-        unsigned tile = 0;
-        if (lane == 0) tile = atomicAdd(&q->next_tile, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= ntiles) break;
-        const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
-        const uint32_t px = tx * kTileW + (lane & (kTileW - 1));
-        const uint32_t lrow = rows.row_begin + ty * kTileH + (lane / kTileW);  // row inside this call's compact output
-        if (px < cam.hsize && lrow < rows.row_begin + rows.row_count) {
-            const uint32_t band = lrow / rows.band_rows;
-            const uint32_t py = (rows.band_first + band * rows.band_stride) * rows.band_rows + (lrow % rows.band_rows);
-            const Ray ray = ray_for_pixel(cam, px, py);
-            primary++;
-            V3 c;
-            if constexpr (kFeatures & FEAT_DEPTH) c = color_at_general<kFeatures & FEAT_ALL>(s, ray, rc, tl);
-            else c = color_at<kFeatures>(s, ray, rc, tl);
-            const size_t o = (size_t)(rows.frame_layout ? py : lrow) * cam.hsize + px;
-            if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
-            if (out64) {
-                out64[3 * o + 0] = c.x;
-                out64[3 * o + 1] = c.y;
-                out64[3 * o + 2] = c.z;
+#if defined(RTC_LANE_REFILL)
+    if constexpr (!(kFeatures & FEAT_DEPTH)) {
+        // LANE REFILL: a pixel is a PixelTask advanced one scene walk at a time (rt_core.cuh), and the warp's loop is over
+        // WALKS, not pixels — a lane whose pixel is finished (a miss after one walk, a matte surface after two) takes the next
+        // pixel of the warp's tile at once instead of idling until the slowest pixel of the tile (a mirror or glass hit: six
+        // walks) is done.  Idle lanes are found with one ballot and numbered with a population count; the tile counter is
+        // warp-uniform, so handing out pixels costs no atomics beyond the one per tile.
+        PixelTask t;
+        bool active = false;
+        uint32_t slot_o = 0;          // where this lane's pixel goes (index into out8 / out64)
+        uint32_t tile = 0, taken = 32;  // the warp's current tile and how many of its 32 pixels are handed out
+        bool exhausted = false;
+        for (;;) {
+            unsigned idle = __ballot_sync(0xffffffffu, !active);
+            while (idle != 0 && !exhausted) {
+                if (taken == 32) {
+                    unsigned next = 0;
+                    if (lane == 0) next = atomicAdd(&q->next_tile, 1u);
+                    tile = __shfl_sync(0xffffffffu, next, 0);
+                    taken = 0;
+                    if (tile >= ntiles) {
+                        exhausted = true;
+                        break;
+                    }
+                }
+                const uint32_t avail = 32u - taken;
+                const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+                if (!active && rank < avail) {
+                    const uint32_t in_tile = taken + rank;
+                    const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+                    const uint32_t px = tx * kTileW + (in_tile & (kTileW - 1));
+                    const uint32_t lrow = rows.row_begin + ty * kTileH + (in_tile / kTileW);
+                    if (px < cam.hsize && lrow < rows.row_begin + rows.row_count) {
+                        const uint32_t band = lrow / rows.band_rows;
+                        const uint32_t py = (rows.band_first + band * rows.band_stride) * rows.band_rows + (lrow % rows.band_rows);
+                        task_begin(t, ray_for_pixel(cam, px, py));
+                        primary++;
+                        slot_o = (rows.frame_layout ? py : lrow) * cam.hsize + px;
+                        active = true;
+                    }
+                }
+                const uint32_t n_idle = __popc(idle);
+                taken += n_idle < avail ? n_idle : avail;
+                idle = __ballot_sync(0xffffffffu, !active);
+            }
+            if (__ballot_sync(0xffffffffu, active) == 0) break;
+            if (active) {
+                scene_walk<kFeatures>(s, t.ray, t.w, tl);  // the only call site of the walker
+                if (task_step<kFeatures>(s, t, rc, tl)) {
+                    const V3 c = t.acc;
+                    const size_t o = slot_o;
+                    if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
+                    if (out64) {
+                        out64[3 * o + 0] = c.x;
+                        out64[3 * o + 1] = c.y;
+                        out64[3 * o + 2] = c.z;
+                    }
+                    active = false;
+                }
+            }
+        }
+    } else
+#endif
+    {
+        // Tile queue: one atomic per tile.  Measured and rejected: guided batches of 4/8/16 tiles per atomic (1.1x-3x slower on
+        // every config — neighbouring heavy tiles land on one warp; profiles/r01g_tile_batch_sweep.json) and requesting the
+        // NEXT tile before rendering the current one to hide the atomic's round trip (4-8 % slower on every config: the
+        // pending result holds a register across the whole tile; profiles/r02c_variants.json).
+        for (;;) {
+            unsigned tile = 0;
+            if (lane == 0) tile = atomicAdd(&q->next_tile, 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= ntiles) break;
+            const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+            const uint32_t px = tx * kTileW + (lane & (kTileW - 1));
+            const uint32_t lrow = rows.row_begin + ty * kTileH + (lane / kTileW);  // row inside this call's compact output
+            if (px < cam.hsize && lrow < rows.row_begin + rows.row_count) {
+                const uint32_t band = lrow / rows.band_rows;
+                const uint32_t py = (rows.band_first + band * rows.band_stride) * rows.band_rows + (lrow % rows.band_rows);
+                const Ray ray = ray_for_pixel(cam, px, py);
+                primary++;
+                V3 c;
+                if constexpr (kFeatures & FEAT_DEPTH) c = color_at_general<kFeatures & FEAT_ALL>(s, ray, rc, tl);
+                else c = color_at<kFeatures>(s, ray, rc, tl);
+                const size_t o = (size_t)(rows.frame_layout ? py : lrow) * cam.hsize + px;
+                if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
+                if (out64) {
+                    out64[3 * o + 0] = c.x;
+                    out64[3 * o + 1] = c.y;
+                    out64[3 * o + 2] = c.z;
+                }
             }
         }
     }
