@@ -179,6 +179,18 @@ int rtc_render(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_
 int rtc_render_device(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows,
                       void* d_rgba8_out, void* d_rgb_f64_out, void* cuda_stream, int sync_stats, rtc_stats* stats);
 
+/* Sharded renders across PROCESSES (one per GPU) without a collective on the frame's path.  rtc_render_device_notify is
+ * rtc_render_device (asynchronous, no stats) whose launch adds 1, with system scope, to the uint32 at d_counter once every
+ * pixel it stored is visible system-wide — d_counter may live in another GPU's memory mapped into this device
+ * (rtc_frame_share_open), e.g. next to the frame the kernels store into (RTC_ROWS_FRAME).  The frame's owner makes its
+ * stream wait for the counter to reach the number of contributions it expects (rtc_stream_wait_counter: a stream wait-value
+ * operation, no kernel occupies the GPU while waiting) and later tells the other ranks that a frame buffer may be written
+ * again by setting a counter in each rank's own memory (rtc_stream_set_counters, up to 16 per call). */
+int rtc_render_device_notify(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows,
+                             void* d_rgba8_out, void* d_rgb_f64_out, void* cuda_stream, void* d_counter);
+int rtc_stream_wait_counter(int device, void* cuda_stream, void* d_counter, uint32_t at_least);
+int rtc_stream_set_counters(int device, void* cuda_stream, void** d_counters, uint32_t n, uint32_t value);
+
 /* ONE frame sharded over the devices 0 .. ngpus-1 of this process — no torch, no NCCL, plain CUDA: the scene is flattened
  * once and uploaded to every device, the frame's 8-row bands are dealt cyclically to the devices (band b -> device b mod
  * ngpus), every device renders its bands with one launch, and the frame is completed in one of two places:

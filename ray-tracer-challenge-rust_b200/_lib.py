@@ -61,6 +61,9 @@ class RtcApi(BuilderApi):
         f("multi_destroy", None, vp)
         f("render_multi", C.c_int, vp, C.POINTER(CameraDesc), C.c_int, C.c_uint32, vp, C.POINTER(Stats))
         f("rows_count", C.c_uint32, C.POINTER(CameraDesc), C.POINTER(Rows))
+        f("render_device_notify", C.c_int, vp, C.POINTER(CameraDesc), C.POINTER(Rows), vp, vp, vp, vp)
+        f("stream_wait_counter", C.c_int, C.c_int, vp, vp, C.c_uint32)
+        f("stream_set_counters", C.c_int, C.c_int, vp, C.POINTER(vp), C.c_uint32, C.c_uint32)
         f("color_at", C.c_int, vp, c_double_p, C.c_uint64, c_double_p)
         f("intersect", C.c_int, vp, c_double_p, C.c_uint64, C.c_uint32, c_double_p, C.POINTER(C.c_int32),
           C.POINTER(C.c_uint32))

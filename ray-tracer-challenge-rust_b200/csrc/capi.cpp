@@ -43,6 +43,7 @@ int to_drows(const rtc_camera_desc& cam, const rtc_rows* rows, DRows* out) {
         out->row_begin = 0;
         out->row_count = cam.vsize;
         out->pad = 0;
+        out->notify = 0;
         return RTC_OK;
     }
     if (rows->layout > RTC_ROWS_FRAME) return set_err(RTC_ERR_INVALID, "unknown rtc_rows.layout");
@@ -64,6 +65,7 @@ int to_drows(const rtc_camera_desc& cam, const rtc_rows* rows, DRows* out) {
     out->row_begin = 0;
     out->row_count = (uint32_t)local;
     out->pad = 0;
+    out->notify = 0;
     return RTC_OK;
 }
 void fill_stats(const LaunchStats& ls, rtc_stats* st) {
@@ -261,6 +263,39 @@ int rtc_render_device(const rtc_scene* scene, const rtc_camera_desc* camera, con
     rc = render_device(scene->dev, to_dcamera(*camera), dr, d_rgba8_out, d_rgb_f64_out, cuda_stream, want ? &ls : nullptr, &e);
     if (rc != 0) return set_err(RTC_ERR_CUDA, e);
     if (want) fill_stats(ls, stats);
+    return RTC_OK;
+}
+
+int rtc_render_device_notify(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows, void* d_rgba8_out,
+                             void* d_rgb_f64_out, void* cuda_stream, void* d_counter) {
+    if (!scene || !camera) return set_err(RTC_ERR_INVALID, "null argument");
+    if (!affine_camera(*camera)) return set_err(RTC_ERR_UNSUPPORTED, "non-affine camera transform");
+    DRows dr;
+    int rc = to_drows(*camera, rows, &dr);
+    if (rc != RTC_OK) return rc;
+    dr.notify = (unsigned long long)(uintptr_t)d_counter;
+    std::string e;
+    if (dr.row_count == 0 || camera->hsize == 0) {  // nothing to launch: the counter still has to move
+        void* one[1] = {d_counter};
+        if (d_counter && stream_counters_add(device_scene_device(scene->dev), cuda_stream, one, 1, &e) != 0)
+            return set_err(RTC_ERR_CUDA, e);
+        return RTC_OK;
+    }
+    rc = render_device(scene->dev, to_dcamera(*camera), dr, d_rgba8_out, d_rgb_f64_out, cuda_stream, nullptr, &e);
+    if (rc != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+int rtc_stream_wait_counter(int device, void* cuda_stream, void* d_counter, uint32_t at_least) {
+    if (!d_counter) return set_err(RTC_ERR_INVALID, "null argument");
+    std::string e;
+    if (stream_counter_wait(device, cuda_stream, d_counter, at_least, &e) != 0) return set_err(RTC_ERR_CUDA, e);
+    return RTC_OK;
+}
+int rtc_stream_set_counters(int device, void* cuda_stream, void** d_counters, uint32_t n, uint32_t value) {
+    if (n && !d_counters) return set_err(RTC_ERR_INVALID, "null argument");
+    if (n > 16) return set_err(RTC_ERR_INVALID, "at most 16 counters per call");
+    std::string e;
+    if (stream_counters_set(device, cuda_stream, d_counters, n, value, &e) != 0) return set_err(RTC_ERR_CUDA, e);
     return RTC_OK;
 }
 

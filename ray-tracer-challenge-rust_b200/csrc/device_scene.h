@@ -144,6 +144,10 @@ struct DRows {
     uint32_t frame_layout;                                    // 1: outputs are addressed by FRAME row, not by local row
     uint32_t row_begin, row_count;                            // the local rows THIS launch renders (a chunk of the call)
     uint32_t pad;
+    // 0, or the address of a uint32 counter (device memory of ANY GPU mapped into this device): the launch's last CTA adds 1
+    // to it with system scope once every pixel store of the launch is visible system-wide — how a rank tells the frame's
+    // owner that its bands have landed (multi-process sharded renders: multi.py)
+    unsigned long long notify;
 };
 // depth of the per-thread traversal stack; flatten.hpp refuses a mesh whose BVH is deeper (the builder bounds depth)
 constexpr int kBvhStackDepth = 48;

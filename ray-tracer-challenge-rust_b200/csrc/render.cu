@@ -577,6 +577,70 @@ int measure_fp64_peak(int device, double* nofma_gflops, double* fma_gflops, std:
     return 0;
 }
 
+// ---- stream-ordered counters (render.cuh) ------------------------------------------------------------------------------
+namespace {
+struct CounterList {
+    unsigned int* p[16];
+};
+__global__ void counters_store_kernel(CounterList c, uint32_t n, uint32_t value, int add) {
+    const unsigned k = threadIdx.x;
+    if (k >= n) return;
+    __threadfence_system();
+    if (add) atomicAdd_system(c.p[k], 1u);
+    else atomicExch_system(c.p[k], value);
+}
+__global__ void counter_poll_kernel(const volatile unsigned int* c, uint32_t at_least) {
+    while (*c < at_least) __nanosleep(200);
+    __threadfence_system();
+}
+// cuStreamWaitValue32 through the runtime's driver entry point: librtc_b200.so links no libcuda (it must load on a box
+// without a driver, where only the host API is used)
+typedef int (*StreamWaitValue32Fn)(void* stream, unsigned long long addr, uint32_t value, unsigned int flags);
+StreamWaitValue32Fn stream_wait_value32() {
+    static StreamWaitValue32Fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        static const bool off = std::getenv("RTC_B200_NO_WAIT_VALUE") != nullptr;  // A/B switch: force the polling kernel
+        return off ? nullptr : (StreamWaitValue32Fn)p;
+    }();
+    return fn;
+}
+}  // namespace
+int stream_counter_wait(int device, void* stream, void* d_counter, uint32_t at_least, std::string* err) {
+    DeviceGuard guard_;
+    RTC_CUDA(cudaSetDevice(device));
+    if (StreamWaitValue32Fn fn = stream_wait_value32()) {
+        const int rc = fn(stream, (unsigned long long)(uintptr_t)d_counter, at_least, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+        if (rc == 0) return 0;
+        // (e.g. CUDA_ERROR_NOT_SUPPORTED for this address) fall through to the polling kernel
+    }
+    counter_poll_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const volatile unsigned int*)d_counter, at_least);
+    RTC_CUDA(cudaGetLastError());
+    return 0;
+}
+static int counters_store(int device, void* stream, void* const* d_counters, uint32_t n, uint32_t value, int add,
+                          std::string* err) {
+    if (n == 0) return 0;
+    DeviceGuard guard_;
+    RTC_CUDA(cudaSetDevice(device));
+    CounterList c{};
+    for (uint32_t k = 0; k < n && k < 16; k++) c.p[k] = (unsigned int*)d_counters[k];
+    counters_store_kernel<<<1, 16, 0, (cudaStream_t)stream>>>(c, n, value, add);
+    RTC_CUDA(cudaGetLastError());
+    return 0;
+}
+int stream_counters_set(int device, void* stream, void* const* d_counters, uint32_t n, uint32_t value, std::string* err) {
+    return counters_store(device, stream, d_counters, n, value, 0, err);
+}
+int stream_counters_add(int device, void* stream, void* const* d_counters, uint32_t n, std::string* err) {
+    return counters_store(device, stream, d_counters, n, 0, 1, err);
+}
+
 void* pinned_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {

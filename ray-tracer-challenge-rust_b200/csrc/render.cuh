@@ -60,6 +60,15 @@ void* multi_device_frame(const MultiRenderer* m);
 const void* multi_host_frame(const MultiRenderer* m);
 int multi_device_count(const MultiRenderer* m);
 
+// Stream-ordered counters for sharded renders across processes (one per GPU): a render launch can bump a uint32 counter in
+// any mapped device memory when its pixels are visible system-wide (DRows.notify); these wait for / set such counters.
+//   wait: the stream's later work runs once *d_counter >= at_least (cuStreamWaitValue32 when the driver offers it — no
+//         kernel occupies the GPU while waiting — else a one-thread polling kernel);
+//   set / add: one tiny kernel stores `value` to (adds 1 to) each of up to 16 counters with system scope.
+int stream_counter_wait(int device, void* stream, void* d_counter, uint32_t at_least, std::string* err);
+int stream_counters_set(int device, void* stream, void* const* d_counters, uint32_t n, uint32_t value, std::string* err);
+int stream_counters_add(int device, void* stream, void* const* d_counters, uint32_t n, std::string* err);
+
 // Feature mask of the render_kernel instantiation a scene with this FEAT_* mask is rendered by (render_launch.cuh); -1: none.
 int render_instance_mask(int feature_mask);
 

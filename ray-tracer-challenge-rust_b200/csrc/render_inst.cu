@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
     // the last CTA to finish publishes the launch's counters and leaves the queue zeroed for the next launch (DQueue)
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (rows.notify) __threadfence_system();  // this CTA's pixel stores (possibly into a peer GPU's frame) first
+        else __threadfence();
         if (atomicAdd(&q->done_ctas, 1u) == gridDim.x - 1) {
             __threadfence();
             q->result[0] = atomicExch(&q->primary, 0ull);
@@ -155,6 +156,10 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
             q->next_tile = 0;
             q->done_ctas = 0;
             __threadfence();
+            if (rows.notify) {  // every CTA's stores are ordered before its done_ctas increment, which this CTA has seen
+                __threadfence_system();
+                atomicAdd_system((unsigned int*)rows.notify, 1u);
+            }
         }
     }
 }

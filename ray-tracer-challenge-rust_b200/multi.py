@@ -5,10 +5,12 @@ dealt cyclically to the ranks (band b -> rank b mod G: meshes sit mid-frame, con
 scene (< 2 MB) is replicated and every rank renders its bands with ONE launch (rtc_render_device + rtc_rows).  Two ways
 to get the bands to rank 0:
 
-  "peer"   (default when it can be set up) — rank 0's frame buffer is mapped into every rank over NVLink (CUDA IPC) and
-           the render kernel stores each pixel STRAIGHT INTO IT at its frame position (RTC_ROWS_FRAME): the transfer
+  "peer"   (default when it can be set up) — rank 0's frame buffers are mapped into every rank over NVLink (CUDA IPC) and
+           the render kernel stores each pixel STRAIGHT INTO THEM at its frame position (RTC_ROWS_FRAME): the transfer
            rides along with the computation tile by tile, there is no collective on the data path and no reassembly;
-           one stream-ordered barrier tells rank 0 the frame is complete.
+           completion is a counter the kernels' last CTAs bump over NVLink and rank 0's stream waits on (no NCCL call
+           per frame); frames alternate between two buffers and a second counter keeps a rank from overwriting a frame
+           rank 0 has not consumed yet (ShardedRenderer, "peer exchange").
   "gather" — every rank renders into a compact device buffer, `dist.gather` moves the buffers to rank 0 over NCCL and
            one strided copy there interleaves the bands back into frame order.
 """
@@ -52,6 +54,30 @@ class BandPlan:
         return v.reshape(self.bands_per_rank * g * self.band_rows, w, c)[: self.vsize]
 
 
+def peer_schedule(rank, world_size, f):
+    """The stream operations of frame f on `rank` under the peer exchange, in stream order (ShardedRenderer.render runs
+    them; tests/test_multi_cpu.py simulates them): rank 0 owns two frame buffers and the `arrive` counter, every other rank
+    a `go` counter.
+        ("set_go", v)        rank 0 stores v into every rank's go counter: frames < v are consumed
+        ("wait_go", v)       the stream waits for this rank's go counter to reach v
+        ("render", b)        render this rank's bands into frame buffer b
+        ("render_notify", b) the same, and the launch's last CTA adds 1 to arrive[b]
+        ("wait_arrive", (b, v)) rank 0's stream waits for arrive[b] to reach v: the frame in buffer b is complete
+    arrive is per BUFFER: a rank may run a frame ahead of rank 0, and its early contribution to the next frame must not be
+    counted towards this one."""
+    ops = []
+    if rank == 0:
+        if f >= 1:
+            ops.append(("set_go", f))
+        ops.append(("render", f % 2))
+        ops.append(("wait_arrive", (f % 2, (f // 2 + 1) * (world_size - 1))))
+    else:
+        if f >= 2:  # frame f - 2 lived in this buffer: rank 0 must have started frame f - 1
+            ops.append(("wait_go", f - 1))
+        ops.append(("render_notify", f % 2))
+    return ops
+
+
 class ShardedRenderer:
     """Camera::render of one frame across `world_size` ranks; the RGBA8 frame lands on rank 0's device."""
 
@@ -65,20 +91,25 @@ class ShardedRenderer:
         world.scene(device)  # flatten + upload now, not inside the first frame
         self.mode = "single" if world_size == 1 else mode
         self.frame = self.local = self.gathered = None
+        self._shared = []  # (pointer, owner) of every library-shared allocation this rank holds
+        self._f = 0        # frames rendered so far (the same number on every rank: render() is collective)
         if self.mode in ("auto", "peer"):
+            import torch.distributed as dist
+            err = None
             try:
                 self._setup_peer(dev, w)
-                self.mode = "peer"
             except Exception as e:  # IPC not permitted in this container, no P2P, ...
-                if mode == "peer":
-                    raise
-                self.peer_error = f"{type(e).__name__}: {e}"
-                self.mode = "gather"
-            # every rank must agree on the path
-            import torch.distributed as dist
-            ok = torch.tensor([1 if self.mode == "peer" else 0], device=dev)
+                err = f"{type(e).__name__}: {e}"
+            # every rank must agree on the path (and every rank has run the same collectives inside _setup_peer)
+            ok = torch.tensor([0 if err else 1], device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
+            if int(ok.item()) == 1:
+                self.mode = "peer"
+            else:
+                self._close_shared()
+                if mode == "peer":
+                    raise RuntimeError("peer exchange could not be set up on every rank: " + (err or "another rank failed"))
+                self.peer_error = err
                 self.mode = "gather"
         if self.mode == "peer":
             self.rows = self.plan.rows(rank, frame_layout=True)
@@ -88,58 +119,171 @@ class ShardedRenderer:
             if world_size > 1 and rank == 0:
                 self.gathered = torch.empty((world_size, self.plan.padded_rows, w, 4), dtype=torch.uint8, device=dev)
 
-    def _setup_peer(self, dev, w):
-        """Rank 0 allocates the frame through the library (plain cudaMalloc + CUDA IPC handle); every other rank maps it
-        with ITS device current, which also enables peer access, so its render kernel can store through the pointer."""
+    # ---- peer exchange ---------------------------------------------------------------------------------------------------
+    # Rank 0 owns TWO frame buffers (frame f goes to buffer f % 2) and an `arrive` counter per buffer; every rank maps them over NVLink
+    # (CUDA IPC) and its render kernel stores each pixel straight into the frame, then adds 1 to `arrive` from its last CTA
+    # once the stores are visible system-wide (rtc_render_device_notify).  Rank 0's stream waits for arrive to reach
+    # (f // 2 + 1) * (G - 1) with a stream wait-value operation: no collective and no kernel on the completion path.  In the other
+    # direction every rank owns a `go` counter that rank 0 maps: at the start of its frame f rank 0 stores f into all of them
+    # (everything it enqueued to consume frame f - 1 precedes that store in its stream), and a rank waits for go >= f - 1
+    # before it overwrites the buffer frame f - 2 lived in — a rank can run one frame ahead of rank 0, never two.
+    def _share_create(self, nbytes):
         import ctypes as C
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        self.camera.api.check(self.camera.api.frame_share_create(self.device, nbytes, C.byref(ptr), handle))
+        self._shared.append((ptr.value, 1))
+        return ptr.value, handle.raw
+
+    def _share_open(self, handle):
+        import ctypes as C
+        ptr = C.c_void_p()
+        self.camera.api.check(self.camera.api.frame_share_open(self.device, handle, C.byref(ptr)))
+        self._shared.append((ptr.value, 0))
+        return ptr.value
+
+    def _setup_peer(self, dev, w):
+        """Collectives run in the same order on every rank whatever fails locally (a failure travels as None and is raised
+        after the last collective)."""
         import torch.distributed as dist
         torch = self.torch
-        api = self.camera.api
         nbytes = self.camera.vsize * w * 4
+        failure = None
+        # 1. rank 0: two frames + the arrive counter -> everyone
         box = [None]
-        ptr = C.c_void_p()
         if self.rank == 0:
-            handle = C.create_string_buffer(64)
-            api.check(api.frame_share_create(self.device, nbytes, C.byref(ptr), handle))
-            box[0] = handle.raw
+            try:
+                made = [self._share_create(nbytes), self._share_create(nbytes), self._share_create(256)]
+                box[0] = [h for _, h in made]
+                self._frames = [made[0][0], made[1][0]]
+                self._arrive = made[2][0]
+            except Exception as e:
+                failure = e
         dist.broadcast_object_list(box, src=0)
         if self.rank != 0:
-            api.check(api.frame_share_open(self.device, box[0], C.byref(ptr)))
-        self._frame_ptr = ptr.value
-        self._frame_owner = self.rank == 0
-        if self.rank == 0:  # a torch view of the library-owned buffer (for the host copy / PPM encoder)
+            if box[0] is None:
+                failure = RuntimeError("rank 0 could not create the shared frame")
+            else:
+                try:
+                    ptrs = [self._share_open(h) for h in box[0]]
+                    self._frames, self._arrive = ptrs[:2], ptrs[2]
+                except Exception as e:
+                    failure = e
+        # 2. every other rank: its go counter -> rank 0
+        mine = None
+        if self.rank != 0 and failure is None:
+            try:
+                self._go, mine = self._share_create(256)
+            except Exception as e:
+                failure = e
+        handles = [None] * self.world_size
+        dist.all_gather_object(handles, mine)
+        if self.rank == 0 and failure is None:
+            try:
+                if any(h is None for h in handles[1:]):
+                    raise RuntimeError("a rank could not create its go counter")
+                self._go_peers = [self._share_open(h) for h in handles[1:]]
+            except Exception as e:
+                failure = e
+        if failure is not None:
+            raise failure
+        for p, owner in self._shared:  # counters start at zero, frames black
+            if owner:
+                torch.cuda.synchronize(self.device)
+        if self.rank == 0:
             class _Iface:
-                __cuda_array_interface__ = {"shape": (self.camera.vsize, w, 4), "typestr": "|u1",
-                                            "data": (ptr.value, False), "version": 2}
-            self.frame = torch.as_tensor(_Iface(), device=dev)
-            self.frame.zero_()
-        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                def __init__(self, ptr, shape):
+                    self.__cuda_array_interface__ = {"shape": shape, "typestr": "|u1", "data": (ptr, False), "version": 2}
+            self._frame_views = [torch.as_tensor(_Iface(p, (self.camera.vsize, w, 4)), device=dev) for p in self._frames]
+            for v in self._frame_views:
+                v.zero_()
+            torch.as_tensor(_Iface(self._arrive, (256,)), device=dev).zero_()
+            self.frame = self._frame_views[0]
+        else:
+            class _Iface:
+                def __init__(self, ptr, shape):
+                    self.__cuda_array_interface__ = {"shape": shape, "typestr": "|u1", "data": (ptr, False), "version": 2}
+            torch.as_tensor(_Iface(self._go, (256,)), device=dev).zero_()
+        torch.cuda.synchronize(self.device)
 
-    def close(self):
-        if getattr(self, "_frame_ptr", None):
+    def _close_shared(self):
+        if self._shared:
             self.torch.cuda.synchronize(self.device)
             self.frame = None
-            self.camera.api.frame_share_close(self.device, self._frame_ptr, int(self._frame_owner))
-            self._frame_ptr = None
+            self._frame_views = None
+            for ptr, owner in reversed(self._shared):
+                self.camera.api.frame_share_close(self.device, ptr, owner)
+            self._shared = []
+
+    def close(self):
+        """Collective: every rank unmaps before any owner frees."""
+        if self._shared and self.world_size > 1:
+            import torch.distributed as dist
+            self.torch.cuda.synchronize(self.device)
+            dist.barrier()
+            mapped = [(p, o) for p, o in self._shared if not o]
+            owned = [(p, o) for p, o in self._shared if o]
+            self.frame = None
+            self._frame_views = None
+            for ptr, owner in mapped:
+                self.camera.api.frame_share_close(self.device, ptr, owner)
+            dist.barrier()
+            for ptr, owner in owned:
+                self.camera.api.frame_share_close(self.device, ptr, owner)
+            self._shared = []
 
     def out_ptr(self):
-        return self._frame_ptr if self.mode == "peer" else self.local.data_ptr()
-
-    def finish(self):
-        """After this rank's launch: make the frame complete on rank 0.  Returns it there (None elsewhere)."""
-        if self.mode == "single":
-            return self.local[: self.camera.vsize]
-        import torch.distributed as dist
-        if self.mode == "peer":
-            dist.all_reduce(self._flag)  # stream-ordered barrier: every rank's stores precede rank 0's completion
-            return self.frame if self.rank == 0 else None
-        dist.gather(self.local, list(self.gathered.unbind(0)) if self.rank == 0 else None, dst=0)
-        return self.plan.assemble(self.gathered) if self.rank == 0 else None
+        return self._frames[self._f % 2] if self.mode == "peer" else self.local.data_ptr()
 
     def render(self, stats=None, scene=None):
         """One frame.  Returns the [vsize, W, 4] uint8 device tensor on rank 0 (None elsewhere).  Asynchronous on
         torch's current stream unless `stats` is given.  `scene`: an explicit rtc_scene handle (default: the world's)."""
-        stream = self.torch.cuda.current_stream(self.device).cuda_stream
-        self.camera.render_device(scene if scene is not None else self.world, d_rgba8=self.out_ptr(), rows=self.rows,
-                                  stream=stream, stats=stats, device=self.device)
-        return self.finish()
+        import ctypes as C
+        torch = self.torch
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        target = scene if scene is not None else self.world
+        if self.mode != "peer":
+            self.camera.render_device(target, d_rgba8=self.out_ptr(), rows=self.rows, stream=stream, stats=stats,
+                                      device=self.device)
+            return self._finish_gather()
+        api, f = self.camera.api, self._f
+        sp = C.c_void_p(stream) if stream else None
+        for op, v in peer_schedule(self.rank, self.world_size, f):
+            if op == "set_go":
+                peers = (C.c_void_p * len(self._go_peers))(*self._go_peers)
+                api.check(api.stream_set_counters(self.device, sp, peers, len(self._go_peers), v))
+            elif op == "wait_go":
+                api.check(api.stream_wait_counter(self.device, sp, C.c_void_p(self._go), v))
+            elif op == "wait_arrive":
+                api.check(api.stream_wait_counter(self.device, sp, C.c_void_p(self._arrive + 128 * v[0]), v[1]))
+            elif op == "render" or stats is not None:
+                self.camera.render_device(target, d_rgba8=self._frames[v], rows=self.rows, stream=stream, stats=stats,
+                                          device=self.device)
+                if op == "render_notify":  # a counting frame is a synchronous launch without notify: count this rank in
+                    self._bump_arrive(sp, v)
+            else:
+                d = self.camera.desc()
+                sc = target.scene(self.device) if hasattr(target, "scene") else target
+                api.check(api.render_device_notify(sc, C.byref(d), C.byref(self.rows), C.c_void_p(self._frames[v]), None, sp,
+                                                   C.c_void_p(self._arrive + 128 * v)))
+        self._f = f + 1
+        if self.rank == 0:
+            self.frame = self._frame_views[f % 2]
+            return self.frame
+        return None
+
+    def _bump_arrive(self, sp, buf):
+        """arrive[buf] += 1 from the host side of a rank whose launch carried no notify (the counting frame)."""
+        import ctypes as C
+        d = self.camera.desc()
+        empty = Rows(self.rows.band_rows, 1 << 30, self.rows.band_stride, self.rows.layout)  # selects no band: nothing renders
+        sc = self.world.scene(self.device)
+        self.camera.api.check(self.camera.api.render_device_notify(sc, C.byref(d), C.byref(empty), None, None, sp,
+                                                                   C.c_void_p(self._arrive + 128 * buf)))
+
+    def _finish_gather(self):
+        if self.mode == "single":
+            return self.local[: self.camera.vsize]
+        import torch.distributed as dist
+        dist.gather(self.local, list(self.gathered.unbind(0)) if self.rank == 0 else None, dst=0)
+        self._f += 1
+        return self.plan.assemble(self.gathered) if self.rank == 0 else None

@@ -226,6 +226,23 @@ extern "C" {
         stats: *mut rtc_stats,
     ) -> c_int;
     /// one frame sharded over `ngpus` devices of this process (row bands, peer stores into device 0's frame)
+    pub fn rtc_render_device_notify(
+        scene: *const rtc_scene,
+        camera: *const rtc_camera_desc,
+        rows: *const rtc_rows,
+        d_rgba8_out: *mut c_void,
+        d_rgb_f64_out: *mut c_void,
+        cuda_stream: *mut c_void,
+        d_counter: *mut c_void,
+    ) -> c_int;
+    pub fn rtc_stream_wait_counter(device: c_int, cuda_stream: *mut c_void, d_counter: *mut c_void, at_least: u32) -> c_int;
+    pub fn rtc_stream_set_counters(
+        device: c_int,
+        cuda_stream: *mut c_void,
+        d_counters: *mut *mut c_void,
+        n: u32,
+        value: u32,
+    ) -> c_int;
     pub fn rtc_render_multi(
         desc: *const rtc_scene_desc,
         camera: *const rtc_camera_desc,

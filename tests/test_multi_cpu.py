@@ -75,3 +75,57 @@ def test_gloo_world_size_2_gather_reassembles_the_frame(tmp_path, vsize):
     plan = multi.BandPlan(vsize, 2, 8)
     assert np.array_equal(frame[:, 0, 2], (rows // plan.band_rows) % 2)  # band b came from rank b mod 2
     assert (frame[:, :, 3] == 255).all()
+
+
+@pytest.mark.parametrize("g", [2, 4, 8])
+@pytest.mark.parametrize("seed", range(6))
+def test_peer_exchange_schedule_never_tears_a_frame(g, seed):
+    """multi.peer_schedule under adversarial interleavings: every rank's stream runs its operations in order, the ranks at
+    arbitrary relative speed (a seeded scheduler picks which stream advances; a wait blocks only its own stream).  Rank 0
+    consumes every frame right after its wait_arrive (in its own stream, as bench.py's device->host copy does).  No schedule
+    may deadlock, hand rank 0 an incomplete frame, or let a rank write a buffer whose frame rank 0 has not consumed."""
+    rng = np.random.default_rng(100 * g + seed)
+    frames = 7
+    streams = []
+    for r in range(g):
+        ops = []
+        for f in range(frames):
+            for op, v in multi.peer_schedule(r, g, f):
+                ops.append((op, v, f))
+            if r == 0:
+                ops.append(("consume", f % 2, f))
+        streams.append(ops)
+    pc = [0] * g
+    arrive, go = [0, 0], [0] * g
+    written = [dict(), dict()]   # buffer -> {rank: frame it last wrote there}
+    consumed = -1
+    steps = 0
+    while any(pc[r] < len(streams[r]) for r in range(g)):
+        runnable = []
+        for r in range(g):
+            if pc[r] >= len(streams[r]):
+                continue
+            op, v, f = streams[r][pc[r]]
+            if op == "wait_go" and go[r] < v:
+                continue
+            if op == "wait_arrive" and arrive[v[0]] < v[1]:
+                continue
+            runnable.append(r)
+        assert runnable, "deadlock"
+        r = int(rng.choice(runnable))
+        op, v, f = streams[r][pc[r]]
+        if op == "set_go":
+            for k in range(1, g):
+                go[k] = v
+        elif op in ("render", "render_notify"):
+            # the buffer's previous tenant (frame f - 2) must have been consumed before ANY rank overwrites its bands
+            assert f < 2 or consumed >= f - 2, f"rank {r} overwrites frame {f - 2} before rank 0 consumed it"
+            written[v][r] = f
+            if op == "render_notify":
+                arrive[v] += 1
+        elif op == "consume":
+            assert all(written[v].get(k) == f for k in range(g)), f"frame {f} incomplete or torn when consumed: {written[v]}"
+            consumed = f
+        pc[r] += 1
+        steps += 1
+    assert consumed == frames - 1 and steps == sum(len(s) for s in streams)
