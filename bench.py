@@ -451,6 +451,15 @@ def run_b200(args):
 
     if pumpkin_line is not None:
         line["pumpkin_at_n"] = pumpkin_line
+    if world_size > 1:
+        # the sharded frame (the last e2e step's, in pinned host memory) against rank 0's own single-GPU render
+        whole = torch.empty((h, w, 4), dtype=torch.uint8, device=dev)
+        cam.render_device(world, d_rgba8=whole.data_ptr(), stream=stream, device=local_rank)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(whole.cpu(), host_frame))
+        line["sharded_frame_check"] = {"identical_to_single_gpu_render": same, "bytes": int(whole.numel())}
+        if not same:
+            raise SystemExit("the sharded frame differs from the single-GPU frame")
 
     if not args.no_cpu_baseline and world_size == 1:
         step_px = {"table": 8, "hexagon": 2, "teapot": 64, "cow_teddy": 96, "pumpkin": 192}.get(args.workload, 32)

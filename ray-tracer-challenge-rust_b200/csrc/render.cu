@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -370,6 +371,10 @@ static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
     uint64_t blocks = (tiles + warps_per_block - 1) / warps_per_block;
     const uint64_t cap = (uint64_t)s->sm_count * kBlocksPerSm;
     if (blocks > cap) blocks = cap;
+    // (Launching fewer CTAs for a small slice — a minimum number of tiles per warp, or exactly ceil(tiles / resident warps)
+    // tiles for every warp — was measured and changes nothing: one rank's eighth of the 1080p table frame takes 0.121 ms with
+    // any of them, against 0.574 / 8 = 0.072 ms; every slice costs about 0.05 ms on top of its share, the time the last tiles
+    // (32 pixels x up to six dependent walks) take to drain.  profiles/r02u_slice_sweep.md)
     if (timed) RTC_CUDA(cudaEventRecord(ctx->ev0, st));
     const RenderLaunchFn fn = pick_instance(s->feature_mask).fn;
     fn((unsigned)blocks, st, s->view, cam, rows, (uint32_t*)d8, (double*)d64, queue);
