@@ -18,6 +18,26 @@ using namespace core;
 
 namespace {
 
+// canvas.rs:24-26 + :61-63: the Canvas colour and its quantised RGBA8.  The frame is written once and never read here:
+// streaming stores, so that on its way to HBM it does not push the scene tables and the traversal stacks out of L2.
+__device__ __forceinline__ void store_pixel(uint32_t* __restrict__ out8, double* __restrict__ out64, size_t o, const V3& c) {
+#if defined(RTC_PLAIN_FRAME_STORES)  // A/B switch (tools/tune_variants.py)
+    if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
+    if (out64) {
+        out64[3 * o + 0] = c.x;
+        out64[3 * o + 1] = c.y;
+        out64[3 * o + 2] = c.z;
+    }
+#else
+    if (out8) __stcs(out8 + o, quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u);
+    if (out64) {
+        __stcs(out64 + 3 * o + 0, c.x);
+        __stcs(out64 + 3 * o + 1, c.y);
+        __stcs(out64 + 3 * o + 2, c.z);
+    }
+#endif
+}
+
 // kMinBlocks = CTAs per SM the register allocation must allow (6 -> 80 registers, 24 warps/SM: the measured optimum of
 // the launch-shape sweeps in profiles/: more warps hide FP64 latency and fetch bubbles, fewer registers spill).
 template <int kMinBlocks, int kFeatures>
@@ -85,12 +105,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
                 if (task_step<kFeatures>(s, t, rc, tl)) {
                     const V3 c = t.acc;
                     const size_t o = slot_o;
-                    if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
-                    if (out64) {
-                        out64[3 * o + 0] = c.x;
-                        out64[3 * o + 1] = c.y;
-                        out64[3 * o + 2] = c.z;
-                    }
+                    store_pixel(out8, out64, o, c);
                     active = false;
                 }
             }
@@ -119,12 +134,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
                 if constexpr (kFeatures & FEAT_DEPTH) c = color_at_general<kFeatures & FEAT_ALL>(s, ray, rc, tl);
                 else c = color_at<kFeatures>(s, ray, rc, tl);
                 const size_t o = (size_t)(rows.frame_layout ? py : lrow) * cam.hsize + px;
-                if (out8) out8[o] = quantise(c.x) | (quantise(c.y) << 8) | (quantise(c.z) << 16) | 0xff000000u;
-                if (out64) {
-                    out64[3 * o + 0] = c.x;
-                    out64[3 * o + 1] = c.y;
-                    out64[3 * o + 2] = c.z;
-                }
+                store_pixel(out8, out64, o, c);
             }
         }
     }
