@@ -129,7 +129,8 @@ struct DScene {
     int32_t pad1;
     int32_t program_count;
     int32_t recursion_limit;  // World's RECURSION_LIMIT (world.rs:11): 5 in the reference
-    int32_t pad0[2];
+    int32_t n_bvh;            // host-built BVH nodes (bvh[0 .. n_bvh); device-built ones follow)
+    int32_t pad0;
     uint32_t n_prims, n_xforms, n_gates, n_materials;  // table lengths (shared-memory staging)
     double light_pos[3];
     double light_int[3];

@@ -375,6 +375,33 @@ class Flattener {
     }
     void push_prim(const DPrim& p) { out_.prims.push_back(p); }
 
+    // Relabels the nodes out_.bvh[first ..) of one mesh in breadth-first order from `root`: the top levels of the tree — the
+    // nodes every ray visits — become the first entries of the mesh's range (contiguous in L1/L2; a kernel that stages the
+    // top of the tree in shared memory, RTC_STAGE_BVH_TOP, copies one range).  Returns the new root index (= first).
+    int32_t breadth_first(size_t first, int32_t root) {
+        const size_t n = out_.bvh.size() - first;
+        std::vector<int32_t> order;  // new position -> old index
+        order.reserve(n);
+        std::vector<int32_t> where(n, -1);  // old index - first -> new position
+        order.push_back(root);
+        for (size_t head = 0; head < order.size(); head++) {
+            const DBvhNode& nd = out_.bvh[order[head]];
+            where[order[head] - first] = (int32_t)head;
+            if (nd.count0 == 0) order.push_back(nd.child0);
+            if (nd.count1 == 0) order.push_back(nd.child1);
+        }
+        if (order.size() != n) return root;  // (unreachable nodes would be a builder bug: leave the layout alone)
+        std::vector<DBvhNode> moved(n);
+        for (size_t k = 0; k < n; k++) {
+            DBvhNode nd = out_.bvh[order[k]];
+            if (nd.count0 == 0) nd.child0 = (int32_t)first + where[nd.child0 - first];
+            if (nd.count1 == 0) nd.child1 = (int32_t)first + where[nd.child1 - first];
+            moved[k] = nd;
+        }
+        std::copy(moved.begin(), moved.end(), out_.bvh.begin() + first);
+        return (int32_t)first;
+    }
+
     // ---- the skip list of a LIST cluster (device_scene.h DBox32) -------------------------------------------------------
     // A small exact-sweep SAH tree over the leaves' padded boxes, written out in depth-first order; an inner node becomes a
     // HEADER entry only where that lowers the expected number of box tests (surface-area heuristic: a ray that enters a box
@@ -924,7 +951,9 @@ class Flattener {
         int depth = 0;
         double max_abs = 0.;
         clock.lap(out_.phase_ms, FlatScene::T_BVH_ITEMS);
+        const size_t nodes_before = out_.bvh.size();
         m.root = build_bvh(bt, out_.bvh, m.tri_base, order, &depth, &max_abs, out_.phase_ms + FlatScene::T_BVH_ITEMS);
+        if (m.root >= 0) m.root = breadth_first(nodes_before, m.root);
         clock = PhaseClock();  // build_bvh booked its own phases
         if (attr_thread.joinable()) attr_thread.join();
         m.extent = f32_above_(max_abs * (1.0 + 2.0 * kPadRel));

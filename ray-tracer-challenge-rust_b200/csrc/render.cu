@@ -315,6 +315,8 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->view.pad1 = 0;
     s->view.program_count = (int32_t)f.program.size();
     s->view.recursion_limit = f.recursion_limit;
+    s->view.n_bvh = (int32_t)f.bvh.size();
+    s->view.pad0 = 0;
     s->view.n_prims = (uint32_t)f.prims.size();
     s->view.n_xforms = (uint32_t)f.xforms.size();
     s->view.n_gates = (uint32_t)f.gates.size();

@@ -54,6 +54,14 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
     RayCounters rc;
     Tally tl;
     uint32_t primary = 0;
+#if defined(RTC_STAGE_BVH_TOP)
+    if constexpr (kFeatures & FEAT_MESHES) {  // the top of the first mesh's tree into shared memory (rt_core.cuh load_node)
+        const int32_t staged = s.n_bvh < RTC_STAGE_BVH_TOP ? s.n_bvh : RTC_STAGE_BVH_TOP;
+        for (int32_t k = threadIdx.x; k < staged * 4; k += blockDim.x) g_bvh_top[k] = __ldg((const float4*)s.bvh + k);
+        if (threadIdx.x == 0) g_bvh_top_count = staged;
+        __syncthreads();
+    }
+#endif
 #if defined(RTC_LANE_REFILL)
     if constexpr (!(kFeatures & FEAT_DEPTH)) {
         // LANE REFILL: a pixel is a PixelTask advanced one scene walk at a time (rt_core.cuh), and the warp's loop is over
