@@ -48,9 +48,7 @@ static_assert(sizeof(DPrim) == 48, "DPrim layout: read with 16-byte loads");
 // list without headers (0.62 ms): profiles/r02c_variants.json, r02p_variants.json.  Larger clusters get the BVH.
 struct alignas(16) DBox32 {
     float lo[3], hi[3];
-    int32_t skip;  // >= 0: header over the next `skip` entries; -1: leaf; -2: a leaf whose solid IS its box (a cube whose
-                   // transform neither rotates nor shears): a shadow ray that starts and ends strictly inside the box shrunk
-                   // by DMesh.inner_shrink cannot meet it between its origin and the light — the exact test is skipped
+    int32_t skip;  // >= 0: header over the next `skip` entries; -1: leaf
     int32_t prim;  // leaf: index into prims[]
 };
 static_assert(sizeof(DBox32) == 32, "DBox32 layout: read with two 16-byte loads");
@@ -71,7 +69,7 @@ struct DMesh {
     float extent;                              // max |coordinate| of the boxes (f32 slab error bound)
     float cx, cy, cz, rfast2;                  // CLUSTER: centre and squared reach of the fast path
     int32_t entry_base, entry_count;           // LIST cluster: its skip list is cluster_entries[entry_base .. + entry_count)
-    float inner_shrink;                        // LIST cluster: how far inside a skip == -2 entry's stored box its solid begins
+    int32_t pad;
 };
 static_assert(sizeof(DMesh) == 48, "DMesh layout");
 // f32 boxes rounded OUTWARD from the padded f64 boxes: 64 bytes hold both children, one fetch decides two subtrees.

@@ -45,11 +45,6 @@ struct FlattenOptions {
 #else
     bool clusters = true;            // gather bounded sibling leaves into BVH clusters (off: every leaf is a PRIM entry)
 #endif
-#if defined(RTC_NO_CLUSTER_INNER)  // A/B switch: no skip == -2 entries (shadow rays inside a box-shaped leaf run its exact test)
-    bool cluster_inner = false;
-#else
-    bool cluster_inner = true;
-#endif
 #if defined(RTC_NO_CLUSTER_HEADERS)  // A/B switch: LIST clusters without header entries (a flat list of leaf boxes)
     bool cluster_headers = false;
 #else
@@ -334,7 +329,6 @@ class Flattener {
         uint32_t shape;
         double lo[3], hi[3];
         double scale;  // cubes: largest column norm of the transform's 3x3; others: 0 (no EPSILON drift)
-        bool boxy = false;  // a cube whose transform neither rotates nor shears: the solid is exactly its world box
     };
     // world box of a bounded leaf; false: not bounded (or not finite) — stays a PRIM entry
     bool leaf_world_box(const rtc_shape_desc& s, ClusterItem& it) const {
@@ -363,15 +357,12 @@ class Flattener {
             }
         }
         it.scale = 0.;
-        it.boxy = false;
         if (s.kind == RTC_CUBE) {
             for (int c = 0; c < 3; c++) {
                 const double x = td.transform[c], y = td.transform[4 + c], z = td.transform[8 + c];
                 it.scale = std::fmax(it.scale, std::sqrt(x * x + y * y + z * z));
             }
             if (!(it.scale <= kClusterMaxScale)) return false;
-            it.boxy = td.transform[1] == 0. && td.transform[2] == 0. && td.transform[4] == 0. && td.transform[6] == 0. &&
-                      td.transform[8] == 0. && td.transform[9] == 0.;
         }
         return true;
     }
@@ -496,12 +487,12 @@ class Flattener {
         return r;
     }
     void skip_emit(const std::vector<SkipNode>& nodes, int n, int anc, SkipMemo& memo, bool headers, double pad,
-                   int32_t prim_base, const std::vector<char>& boxy) {
+                   int32_t prim_base) {
         const SkipNode& nd = nodes[n];
         const bool head = nd.item < 0 && headers && skip_cost(nodes, n, anc, memo).second;
         if (nd.item < 0 && !head) {
-            skip_emit(nodes, nd.left, anc, memo, headers, pad, prim_base, boxy);
-            skip_emit(nodes, nd.right, anc, memo, headers, pad, prim_base, boxy);
+            skip_emit(nodes, nd.left, anc, memo, headers, pad, prim_base);
+            skip_emit(nodes, nd.right, anc, memo, headers, pad, prim_base);
             return;
         }
         DBox32 b;
@@ -510,13 +501,13 @@ class Flattener {
             b.lo[a] = detail::f32_below(nd.lo[a] - pad);
             b.hi[a] = detail::f32_above(nd.hi[a] + pad);
         }
-        b.skip = (nd.item >= 0 && boxy[nd.item]) ? -2 : -1;
+        b.skip = -1;
         b.prim = nd.item >= 0 ? prim_base + nd.item : -1;
         const size_t at = out_.cluster_entries.size();
         out_.cluster_entries.push_back(b);
         if (nd.item >= 0) return;
-        skip_emit(nodes, nd.left, n, memo, headers, pad, prim_base, boxy);
-        skip_emit(nodes, nd.right, n, memo, headers, pad, prim_base, boxy);
+        skip_emit(nodes, nd.left, n, memo, headers, pad, prim_base);
+        skip_emit(nodes, nd.right, n, memo, headers, pad, prim_base);
         out_.cluster_entries[at].skip = (int32_t)(out_.cluster_entries.size() - at - 1);
     }
     void set_site(uint32_t leaf, const LeafSite& st) {
@@ -581,17 +572,8 @@ class Flattener {
             const int root = skip_build(nodes, items, all);
             SkipMemo memo;
             // the root is never a header, but its box is what the headers beneath it are measured against
-            // leaves whose solid is their box: a shadow ray wholly inside one (shrunk by everything the stored box was grown
-            // by — EPSILON drift, padding, the f32 rounding — plus a margin far above any f64 rounding) skips its exact test
-            std::vector<char> boxy(n, 0);
-            double grown = 0.;
-            for (uint32_t k = 0; k < n; k++) {
-                boxy[k] = opts_.cluster_inner && run[k].boxy;
-                if (boxy[k]) grown = std::fmax(grown, 1.0001e-5 * longest * run[k].scale);
-            }
-            m.inner_shrink = f32_above_(grown + pad + 1e-6 * std::fmax(max_abs, 1.0));
-            skip_emit(nodes, nodes[root].left, root, memo, opts_.cluster_headers, pad, m.tri_base, boxy);
-            skip_emit(nodes, nodes[root].right, root, memo, opts_.cluster_headers, pad, m.tri_base, boxy);
+            skip_emit(nodes, nodes[root].left, root, memo, opts_.cluster_headers, pad, m.tri_base);
+            skip_emit(nodes, nodes[root].right, root, memo, opts_.cluster_headers, pad, m.tri_base);
             m.entry_count = (int32_t)out_.cluster_entries.size() - m.entry_base;
             for (uint32_t k = 0; k < n; k++) {
                 const ClusterItem& ci = run[k];
@@ -922,8 +904,7 @@ class Flattener {
             m.tri_count = (int32_t)n;
             m.extent = 0.f;
             m.cx = m.cy = m.cz = m.rfast2 = 0.f;
-            m.entry_base = m.entry_count = 0;
-            m.inner_shrink = 0.f;
+            m.entry_base = m.entry_count = m.pad = 0;
             out_.pending.push_back(p);
             for (uint32_t k = 0; k < n; k++) set_site(p.leaf0 + k, LeafSite{begin + k, (int32_t)out_.program.size(), -1});
             out_.program.push_back(DProgramNode{NODE_MESH, (int32_t)out_.meshes.size(), 0, gate_node_});
@@ -977,8 +958,7 @@ class Flattener {
         if (attr_thread.joinable()) attr_thread.join();
         m.extent = f32_above_(max_abs * (1.0 + 2.0 * kPadRel));
         m.cx = m.cy = m.cz = m.rfast2 = 0.f;
-        m.entry_base = m.entry_count = 0;
-        m.inner_shrink = 0.f;
+        m.entry_base = m.entry_count = m.pad = 0;
         if (depth > out_.bvh_max_depth) out_.bvh_max_depth = depth;
         if (depth + 2 > kBvhStackDepth)
             fail(RTC_ERR_UNSUPPORTED, "mesh BVH deeper than the device traversal stack (more than ~16M triangles)");
