@@ -149,6 +149,10 @@ struct DRows {
     // to it with system scope once every pixel store of the launch is visible system-wide — how a rank tells the frame's
     // owner that its bands have landed (multi-process sharded renders: multi.py)
     unsigned long long notify;
+    // Tile ORDER of the queue (never which tiles are rendered): the tiles of the rectangle [hot_x0, hot_x1) x [hot_y0, hot_y1)
+    // — where the scene's bounded geometry projects to, the expensive pixels — are handed out first, the rest after them, so
+    // the launch drains on cheap background tiles instead of on the last mesh tiles (render_inst.cu tile_of).
+    uint32_t hot_x0, hot_y0, hot_x1, hot_y1;
 };
 // depth of the per-thread traversal stack; flatten.hpp refuses a mesh whose BVH is deeper (the builder bounds depth)
 constexpr int kBvhStackDepth = 48;

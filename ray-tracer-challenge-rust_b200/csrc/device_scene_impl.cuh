@@ -56,6 +56,8 @@ struct DeviceScene {
     size_t slab_size = 0;
     size_t upload_bytes = 0;        // host->device bytes the create call copied (tables, device-build inputs)
     DScene view{};
+    double hot_lo[3] = {0, 0, 0}, hot_hi[3] = {0, 0, 0};  // FlatScene::hot_*; hot_valid: finite and not empty
+    bool hot_valid = false;
     int feature_mask = 0;           // FEAT_* bits of what the flattened world contains (picks the kernel instantiation)
     cudaStream_t stream = nullptr;  // == ctx->stream
     std::mutex& mu() { return ctx->mu; }

@@ -42,6 +42,8 @@ struct FlatScene {
     std::vector<int32_t> class_offsets;        // n_classes + 1 entries (empty: no class of value-equal leaves)
     std::vector<DClassMember> class_members;
     double light_pos[3] = {0, 0, 0}, light_int[3] = {0, 0, 0};
+    // union of the world boxes of everything bounded (group gates, clusters, bounded leaves): where the expensive pixels are
+    double hot_lo[3] = {1e300, 1e300, 1e300}, hot_hi[3] = {-1e300, -1e300, -1e300};
     uint64_t leaf_count = 0;
     int32_t recursion_limit = 5;  // world.rs:11
     int32_t feature_mask = 0;  // bit k: leaves of ShapeKind k; 32 meshes; 64 gates; 128 a transparent material; 256 clusters; 512 a RECURSION_LIMIT other than 5;

@@ -97,6 +97,7 @@ class Flattener {
         clock.lap(out_.phase_ms, FlatScene::T_VALIDATE);
         emit_children(0, d_.shape_count);  // World.objects in order (world.rs:46-50)
         out_.leaf_count = next_leaf_;
+        for (const DGate& g : out_.gates) hot_add(g.lo, g.hi);
         // device-built meshes take the table entries after the host-built ones
         for (PendingMesh& p : out_.pending) {
             p.tri_base = (int32_t)(out_.tris.size() + out_.device_tris);
@@ -374,6 +375,15 @@ class Flattener {
         return n;
     }
     void push_prim(const DPrim& p) { out_.prims.push_back(p); }
+    void hot_add(const double* lo, const double* hi) {
+        for (int a = 0; a < 3; a++) {
+            if (!(std::isfinite(lo[a]) && std::isfinite(hi[a]))) return;
+        }
+        for (int a = 0; a < 3; a++) {
+            out_.hot_lo[a] = std::fmin(out_.hot_lo[a], lo[a]);
+            out_.hot_hi[a] = std::fmax(out_.hot_hi[a], hi[a]);
+        }
+    }
 
     // Relabels the nodes out_.bvh[first ..) of one mesh in breadth-first order from `root`: the top levels of the tree — the
     // nodes every ray visits — become the first entries of the mesh's range (contiguous in L1/L2; a kernel that stages the
@@ -525,6 +535,7 @@ class Flattener {
             }
             smax = std::fmax(smax, it.scale);
         }
+        hot_add(lo, hi);
         double centre[3], r2 = 0.;
         for (int a = 0; a < 3; a++) {
             centre[a] = 0.5 * (lo[a] + hi[a]);
@@ -764,6 +775,8 @@ class Flattener {
                 if (cluster && leaf_world_box(s, ci)) {
                     run.push_back(ci);  // hit selection is min over (t, DFS leaf): the order of the tests is free
                 } else {
+                    ClusterItem bounded;
+                    if (leaf_world_box(s, bounded)) hot_add(bounded.lo, bounded.hi);  // (a plane is not: it stays "the rest")
                     set_site((uint32_t)p.leaf, LeafSite{i, (int32_t)out_.program.size(), (int32_t)out_.prims.size()});
                     out_.program.push_back(DProgramNode{NODE_PRIM, (int32_t)out_.prims.size(), 0, gate_node_});
                     push_prim(p);

@@ -5,6 +5,8 @@
 // as canvas.rs:61-63 does and store one uchar4 (and optionally the f64 Canvas colour) per pixel.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -322,6 +324,13 @@ int device_scene_create(const FlatScene& f, int device, DeviceScene** out, std::
     s->view.n_gates = (uint32_t)f.gates.size();
     s->view.n_materials = (uint32_t)f.materials.size();
     s->feature_mask = f.feature_mask;
+    s->hot_valid = true;
+    for (int k = 0; k < 3; k++) {
+        s->hot_lo[k] = f.hot_lo[k];
+        s->hot_hi[k] = f.hot_hi[k];
+        if (!(f.hot_lo[k] <= f.hot_hi[k]) || !std::isfinite(f.hot_lo[k]) || !std::isfinite(f.hot_hi[k])) s->hot_valid = false;
+    }
+    if (!f.pending.empty()) s->hot_valid = false;  // a device-built mesh folds its gate box on the GPU: not known here
     for (int k = 0; k < 3; k++) {
         s->view.light_pos[k] = f.light_pos[k];
         s->view.light_int[k] = f.light_int[k];
@@ -359,6 +368,66 @@ static DQueue* queue_for(DeviceContext* ctx, cudaStream_t st, bool* shared) {
     return ctx->queues + (kQueueSlots - 1);
 }
 
+// Where the scene's bounded geometry lands in this launch's tile grid (DRows.hot_*): its world box through the camera
+// (camera.rs:48-65 inverted: pixel = (half - c / -z) / pixel_size - 0.5 for a camera-space point (c, z), z < 0).  Only the
+// ORDER of the tile queue depends on it, so anything doubtful — a corner beside or behind the camera plane, a device-built
+// mesh, an empty box — simply means "every tile is hot" (the plain row-major order).
+static void hot_rectangle(const DeviceScene* s, const DCamera& cam, DRows* rows) {
+    const uint32_t tiles_x = (cam.hsize + kTileW - 1) / kTileW, tiles_y = (rows->row_count + kTileH - 1) / kTileH;
+    rows->hot_x0 = rows->hot_y0 = 0;
+    rows->hot_x1 = tiles_x;
+    rows->hot_y1 = tiles_y;
+    static const bool off = std::getenv("RTC_B200_NO_HOT_TILES") != nullptr;  // A/B switch
+    if (!s->hot_valid || off || tiles_x == 0 || tiles_y == 0) return;
+    // camera-to-world is [A | t] (rows 0..2 of transform_inverse): world-to-camera is [A^-1 | -A^-1 t]
+    const double* m = cam.inv;
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    if (!(std::fabs(det) > 1e-300)) return;
+    const double r[9] = {(e * i - f * h) / det, (c * h - b * i) / det, (b * f - c * e) / det,
+                         (f * g - d * i) / det, (a * i - c * g) / det, (c * d - a * f) / det,
+                         (d * h - e * g) / det, (b * g - a * h) / det, (a * e - b * d) / det};
+    double px0 = 1e300, px1 = -1e300, py0 = 1e300, py1 = -1e300;
+    for (int k = 0; k < 8; k++) {
+        const double w[3] = {((k & 1) ? s->hot_hi[0] : s->hot_lo[0]) - m[3], ((k & 2) ? s->hot_hi[1] : s->hot_lo[1]) - m[7],
+                             ((k & 4) ? s->hot_hi[2] : s->hot_lo[2]) - m[11]};
+        const double cx = r[0] * w[0] + r[1] * w[1] + r[2] * w[2], cy = r[3] * w[0] + r[4] * w[1] + r[5] * w[2],
+                     cz = r[6] * w[0] + r[7] * w[1] + r[8] * w[2];
+        if (!(cz < -1e-6)) return;  // beside or behind the camera plane: the box's image is not a rectangle
+        const double x = (cam.half_width - cx / -cz) / cam.pixel_size - 0.5, y = (cam.half_height - cy / -cz) / cam.pixel_size - 0.5;
+        if (!(std::isfinite(x) && std::isfinite(y))) return;
+        px0 = std::fmin(px0, x); px1 = std::fmax(px1, x);
+        py0 = std::fmin(py0, y); py1 = std::fmax(py1, y);
+    }
+    px0 = std::floor(px0) - 1.0; py0 = std::floor(py0) - 1.0;
+    px1 = std::ceil(px1) + 2.0;  py1 = std::ceil(py1) + 2.0;
+    if (px1 <= 0.0 || py1 <= 0.0 || px0 >= (double)cam.hsize || py0 >= (double)cam.vsize) {  // nothing bounded on screen
+        rows->hot_x1 = rows->hot_y1 = 0;
+        return;
+    }
+    const double fx0 = std::fmax(px0, 0.0), fx1 = std::fmin(px1, (double)cam.hsize);
+    double fy0 = std::fmax(py0, 0.0), fy1 = std::fmin(py1, (double)cam.vsize);
+    // frame rows -> this launch's local rows: local band k holds frame band band_first + k * band_stride
+    const double br = (double)rows->band_rows, st = (double)rows->band_stride;
+    double ly0 = std::floor((std::floor(fy0 / br) - (double)rows->band_first) / st) * br;
+    double ly1 = (std::floor((std::floor(fy1 / br) - (double)rows->band_first) / st) + 1.0) * br;
+    if (rows->band_stride == 1 && rows->band_first == 0) {  // contiguous rows: exact
+        ly0 = fy0;
+        ly1 = fy1;
+    }
+    ly0 = std::fmax(ly0 - (double)rows->row_begin, 0.0);
+    ly1 = std::fmin(std::fmax(ly1 - (double)rows->row_begin, 0.0), (double)rows->row_count);
+    if (!(ly1 > ly0)) {
+        rows->hot_x1 = rows->hot_y1 = 0;
+        return;
+    }
+    rows->hot_x0 = (uint32_t)(fx0 / kTileW);
+    rows->hot_x1 = std::min<uint32_t>(tiles_x, (uint32_t)((fx1 + kTileW - 1) / kTileW));
+    rows->hot_y0 = (uint32_t)(ly0 / kTileH);
+    rows->hot_y1 = std::min<uint32_t>(tiles_y, (uint32_t)((ly1 + kTileH - 1) / kTileH));
+    if (rows->hot_x1 <= rows->hot_x0 || rows->hot_y1 <= rows->hot_y0) rows->hot_x1 = rows->hot_y1 = rows->hot_x0 = rows->hot_y0 = 0;
+}
+
 // Enqueues one render kernel on `st`.  timed: bracket it with the context's events (one timed launch in flight per device).
 static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d8, void* d64, cudaStream_t st, bool timed,
                   DQueue** used, std::string* err) {
@@ -379,7 +448,9 @@ static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
     // (32 pixels x up to six dependent walks) take to drain.  profiles/r02u_slice_sweep.md)
     if (timed) RTC_CUDA(cudaEventRecord(ctx->ev0, st));
     const RenderLaunchFn fn = pick_instance(s->feature_mask).fn;
-    fn((unsigned)blocks, st, s->view, cam, rows, (uint32_t*)d8, (double*)d64, queue);
+    DRows ordered = rows;
+    hot_rectangle(s, cam, &ordered);
+    fn((unsigned)blocks, st, s->view, cam, ordered, (uint32_t*)d8, (double*)d64, queue);
     RTC_CUDA(cudaGetLastError());
     if (timed) RTC_CUDA(cudaEventRecord(ctx->ev1, st));
     if (shared) RTC_CUDA(cudaEventRecord(ctx->shared_slot_free, st));

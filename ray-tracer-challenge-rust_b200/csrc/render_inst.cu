@@ -43,6 +43,36 @@ __device__ __forceinline__ void store_pixel(uint32_t* __restrict__ out8, double*
 #endif
 }
 
+// Queue position -> tile.  The tiles of the hot rectangle (DRows.hot_*: where the scene's bounded geometry projects to) come
+// first, row by row; then the rows above it, the tiles left and right of it, and the rows below it.  A bijection of
+// [0, tiles_x * tiles_y) for any rectangle inside the grid.
+__device__ __forceinline__ void tile_of(uint32_t q, uint32_t tiles_x, const DRows& rows, uint32_t& tx, uint32_t& ty) {
+    const uint32_t hw = rows.hot_x1 - rows.hot_x0, hh = rows.hot_y1 - rows.hot_y0, hot = hw * hh;
+    if (q < hot) {
+        tx = rows.hot_x0 + q % hw;
+        ty = rows.hot_y0 + q / hw;
+        return;
+    }
+    q -= hot;
+    const uint32_t above = rows.hot_y0 * tiles_x;
+    if (hot == 0 || q < above) {  // (no rectangle: plain row-major order)
+        tx = q % tiles_x;
+        ty = q / tiles_x;
+        return;
+    }
+    q -= above;
+    const uint32_t side = tiles_x - hw;  // tiles of a rectangle row that are outside the rectangle
+    if (q < side * hh) {
+        const uint32_t c = q % side;
+        tx = c < rows.hot_x0 ? c : c + hw;
+        ty = rows.hot_y0 + q / side;
+        return;
+    }
+    q -= side * hh;
+    tx = q % tiles_x;
+    ty = rows.hot_y1 + q / tiles_x;
+}
+
 // kMinBlocks = CTAs per SM the register allocation must allow (6 -> 80 registers, 24 warps/SM: the measured optimum of
 // the launch-shape sweeps in profiles/: more warps hide FP64 latency and fetch bubbles, fewer registers spill).
 template <int kMinBlocks, int kFeatures>
@@ -96,7 +126,8 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
                 const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
                 if (!active && rank < avail) {
                     const uint32_t in_tile = taken + rank;
-                    const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+                    uint32_t tx, ty;
+            tile_of(tile, tiles_x, rows, tx, ty);
                     const uint32_t px = tx * kTileW + (in_tile & (kTileW - 1));
                     const uint32_t lrow = rows.row_begin + ty * kTileH + (in_tile / kTileW);
                     if (px < cam.hsize && lrow < rows.row_begin + rows.row_count) {
@@ -135,7 +166,8 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
             if (lane == 0) tile = atomicAdd(&q->next_tile, 1u);
             tile = __shfl_sync(0xffffffffu, tile, 0);
             if (tile >= ntiles) break;
-            const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+            uint32_t tx, ty;
+            tile_of(tile, tiles_x, rows, tx, ty);
             const uint32_t px = tx * kTileW + (lane & (kTileW - 1));
             const uint32_t lrow = rows.row_begin + ty * kTileH + (lane / kTileW);  // row inside this call's compact output
             if (px < cam.hsize && lrow < rows.row_begin + rows.row_count) {

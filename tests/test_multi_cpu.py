@@ -129,3 +129,34 @@ def test_peer_exchange_schedule_never_tears_a_frame(g, seed):
         pc[r] += 1
         steps += 1
     assert consumed == frames - 1 and steps == sum(len(s) for s in streams)
+
+
+def test_hot_rectangle_tile_order_is_a_bijection():
+    """render_inst.cu tile_of (queue position -> tile; the hot rectangle's tiles first) restated: every tile exactly once for
+    any rectangle inside the grid, including none."""
+    def tile_of(q, tiles_x, hot):
+        x0, y0, x1, y1 = hot
+        hw, hh = x1 - x0, y1 - y0
+        n = hw * hh
+        if q < n:
+            return x0 + q % hw, y0 + q // hw
+        q -= n
+        above = y0 * tiles_x
+        if n == 0 or q < above:
+            return q % tiles_x, q // tiles_x
+        q -= above
+        side = tiles_x - hw
+        if q < side * hh:
+            c = q % side
+            return (c if c < x0 else c + hw), y0 + q // side
+        q -= side * hh
+        return q % tiles_x, y1 + q // tiles_x
+    rng = np.random.default_rng(3)
+    for _ in range(400):
+        tx, ty = int(rng.integers(1, 30)), int(rng.integers(1, 30))
+        x0 = int(rng.integers(0, tx + 1)); x1 = int(rng.integers(x0, tx + 1))
+        y0 = int(rng.integers(0, ty + 1)); y1 = int(rng.integers(y0, ty + 1))
+        if x1 == x0 or y1 == y0:
+            x0 = x1 = y0 = y1 = 0
+        seen = {tile_of(q, tx, (x0, y0, x1, y1)) for q in range(tx * ty)}
+        assert seen == {(a, b) for a in range(tx) for b in range(ty)}
