@@ -1,0 +1,6 @@
+set -x
+for w in hexagon teapot cow_teddy pumpkin; do python bench.py --workload $w --no-extras > gpurun_out/r02z_bench_n1_$w.json 2>> gpurun_out/r02z_bench.err; done
+python bench.py > gpurun_out/r02z_bench_n1_table.json 2>> gpurun_out/r02z_bench.err
+B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras"
+for w in teapot pumpkin; do $B --workload $w > gpurun_out/plain_$w.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 3 -c 2 -o gpurun_out/prof_r02z_$w $B --workload $w > gpurun_out/ncu_$w.log 2>&1; done
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
