@@ -367,9 +367,11 @@ rtc_camera* rtc_camera_new(uint64_t hsize, uint64_t vsize, double field_of_view)
 void rtc_camera_free(rtc_camera* c);
 int rtc_camera_set_transform(rtc_camera* c, const double* m16);
 void rtc_camera_desc_get(const rtc_camera* c, rtc_camera_desc* out);
-/* camera.rs:67-79: Camera::render(&World) -> Canvas, on GPU `device`.  The canvas holds the f64 colours and the quantised
- * RGBA8 frame in pinned host memory (pooled: a freed canvas's buffers serve the next canvas of that size).  `want_f64` = 0
- * skips the 24-byte-per-pixel colour copy (get_pixel then fails) and keeps the RGBA8 frame that to_ppm needs. */
+/* camera.rs:67-79: Camera::render(&World) -> Canvas, on GPU `device`, in pinned host memory (pooled: a freed canvas's
+ * buffers serve the next canvas of that size).  `want_f64` != 0: the canvas holds the f64 colours (canvas.rs:8), as the
+ * reference's does — 24 bytes per pixel cross PCIe — and its RGBA8 pixels are quantised from them on the host the first
+ * time they are asked for (rtc_canvas_pixels_rgba8, rtc_canvas_to_ppm: canvas.rs:61-63 happens at PPM time there too).
+ * `want_f64` = 0: only the RGBA8 frame the kernel quantised (4 bytes per pixel; get_pixel then fails). */
 int rtc_camera_render(const rtc_camera* c, rtc_world* w, int device, int want_f64, rtc_canvas** out, rtc_stats* stats);
 
 /* canvas.rs:12-58 */
@@ -380,7 +382,7 @@ uint64_t rtc_canvas_height(const rtc_canvas* c);
 int rtc_canvas_get_pixel(const rtc_canvas* c, uint64_t x, uint64_t y, double* rgb3);
 int rtc_canvas_set_pixel(rtc_canvas* c, uint64_t x, uint64_t y, const double* rgb3);
 const double* rtc_canvas_pixels_f64(const rtc_canvas* c); /* NULL if rendered with want_f64 = 0 */
-const uint8_t* rtc_canvas_pixels_rgba8(const rtc_canvas* c);
+const uint8_t* rtc_canvas_pixels_rgba8(const rtc_canvas* c); /* quantised on first use for a want_f64 canvas */
 /* canvas.rs:28-58: P3 text, 70-column wrap.  Returns a malloc'd buffer (free with rtc_free). */
 char* rtc_canvas_to_ppm(const rtc_canvas* c, uint64_t* len);
 /* Canvas::to_ppm ON THE DEVICE: encodes an RGBA8 frame that is still in HBM (e.g. the output of rtc_render_device, or

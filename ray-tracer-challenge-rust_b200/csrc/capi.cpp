@@ -109,8 +109,13 @@ struct rtc_marshalled {
 struct rtc_canvas {
     uint64_t width = 0, height = 0;
     double* rgb = nullptr;     // Canvas.pixels (canvas.rs:8), 3 f64 per pixel; may be absent for want_f64 = 0 renders
-    uint8_t* rgba8 = nullptr;  // the same pixels quantised as canvas.rs:61-63
-    bool rgb_pinned = false, rgba_pinned = false;
+    // the same pixels quantised as canvas.rs:61-63.  A canvas rendered WITH its f64 colours holds only those at first — as the
+    // reference's Canvas does, which quantises at PPM time — and this array is filled from them the first time it is asked
+    // for (canvas_rgba8): a frame's 4 B/px then never cross PCIe next to its 24 B/px
+    mutable uint8_t* rgba8 = nullptr;
+    bool rgb_pinned = false;
+    mutable bool rgba_pinned = false;
+    mutable std::mutex lazy;
 };
 
 // RTC_B200_TRACE=1: where the host time of a scene build went (stderr, one line per call)
@@ -786,16 +791,16 @@ PinnedPool& pinned_pool() {
 }
 }  // namespace
 
-static rtc_canvas* canvas_alloc(uint64_t width, uint64_t height, bool want_f64, bool pinned) {
+static rtc_canvas* canvas_alloc(uint64_t width, uint64_t height, bool want_f64, bool pinned, bool want_rgba8 = true) {
     rtc_canvas* cv = new rtc_canvas();
     cv->width = width;
     cv->height = height;
     const size_t px = (size_t)width * height;
-    if (pinned) {
+    if (want_rgba8 && pinned) {
         cv->rgba8 = (uint8_t*)pinned_pool().take(px * 4 ? px * 4 : 1);
         cv->rgba_pinned = cv->rgba8 != nullptr;
     }
-    if (!cv->rgba8) cv->rgba8 = (uint8_t*)std::malloc(px * 4 ? px * 4 : 1);
+    if (want_rgba8 && !cv->rgba8) cv->rgba8 = (uint8_t*)std::malloc(px * 4 ? px * 4 : 1);
     if (want_f64) {
         if (pinned) {
             cv->rgb = (double*)pinned_pool().take(px * 24 ? px * 24 : 1);
@@ -804,6 +809,28 @@ static rtc_canvas* canvas_alloc(uint64_t width, uint64_t height, bool want_f64, 
         if (!cv->rgb) cv->rgb = (double*)std::malloc(px * 24 ? px * 24 : 1);
     }
     return cv;
+}
+
+// The canvas's RGBA8 pixels, quantised from its f64 colours on first use (canvas.rs:61-63 per channel, rows in parallel).
+static const uint8_t* canvas_rgba8(const rtc_canvas* c) {
+    std::lock_guard<std::mutex> lk(c->lazy);
+    if (c->rgba8 || !c->rgb) return c->rgba8;
+    const size_t px = (size_t)c->width * c->height;
+    uint8_t* out = (uint8_t*)std::malloc(px * 4 ? px * 4 : 1);
+    const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, std::thread::hardware_concurrency()), px / 65536));
+    auto rows = [&](unsigned t) {
+        for (size_t i = px * t / nt; i < px * (t + 1) / nt; i++) {
+            for (int k = 0; k < 3; k++) out[4 * i + k] = quantise_channel(c->rgb[3 * i + k]);
+            out[4 * i + 3] = 255;
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(rows, t);
+    rows(0);
+    for (auto& t : th) t.join();
+    c->rgba8 = out;
+    c->rgba_pinned = false;
+    return out;
 }
 
 int rtc_camera_render(const rtc_camera* c, rtc_world* w, int device, int want_f64, rtc_canvas** out, rtc_stats* stats) {
@@ -815,7 +842,8 @@ int rtc_camera_render(const rtc_camera* c, rtc_world* w, int device, int want_f6
     if (rc != RTC_OK) return rc;
     rtc_camera_desc cd;
     rtc_camera_desc_get(c, &cd);
-    rtc_canvas* cv = canvas_alloc(c->c.hsize, c->c.vsize, want_f64 != 0, true);
+    // with the f64 colours wanted, only they are brought to the host (canvas_rgba8 quantises them on demand)
+    rtc_canvas* cv = canvas_alloc(c->c.hsize, c->c.vsize, want_f64 != 0, true, want_f64 == 0);
     rc = rtc_render(s, &cd, nullptr, cv->rgba8, cv->rgb, stats);
     if (rc != RTC_OK) {
         rtc_canvas_free(cv);
@@ -856,18 +884,21 @@ int rtc_canvas_set_pixel(rtc_canvas* c, uint64_t x, uint64_t y, const double* rg
     if (x >= c->width || y >= c->height) return set_err(RTC_ERR_PANIC, "index out of bounds (src/canvas.rs:25)");
     const size_t i = x + y * c->width;
     if (c->rgb) std::memcpy(c->rgb + 3 * i, rgb3, 24);
-    for (int k = 0; k < 3; k++) c->rgba8[4 * i + k] = quantise_channel(rgb3[k]);
-    c->rgba8[4 * i + 3] = 255;
+    std::lock_guard<std::mutex> lk(c->lazy);
+    if (c->rgba8) {  // (not materialised yet: it will be quantised from rgb, which now holds the new colour)
+        for (int k = 0; k < 3; k++) c->rgba8[4 * i + k] = quantise_channel(rgb3[k]);
+        c->rgba8[4 * i + 3] = 255;
+    }
     return RTC_OK;
 }
 const double* rtc_canvas_pixels_f64(const rtc_canvas* c) { return c ? c->rgb : nullptr; }
-const uint8_t* rtc_canvas_pixels_rgba8(const rtc_canvas* c) { return c ? c->rgba8 : nullptr; }
+const uint8_t* rtc_canvas_pixels_rgba8(const rtc_canvas* c) { return c ? canvas_rgba8(c) : nullptr; }
 char* rtc_canvas_to_ppm(const rtc_canvas* c, uint64_t* len) {
     if (!c || !len) {
         g_err = "null argument";
         return nullptr;
     }
-    std::string s = ppm_from_rgba8(c->rgba8, c->width, c->height);
+    std::string s = ppm_from_rgba8(canvas_rgba8(c), c->width, c->height);
     char* out = (char*)std::malloc(s.size() + 1);
     std::memcpy(out, s.data(), s.size());
     out[s.size()] = 0;
