@@ -73,7 +73,7 @@ __device__ __forceinline__ void tile_of(uint32_t q, uint32_t tiles_x, const DRow
     ty = rows.hot_y1 + q / tiles_x;
 }
 
-// kMinBlocks = CTAs per SM the register allocation must allow (6 -> 80 registers, 24 warps/SM: the measured optimum of
+// kMinBlocks = CTAs per SM the register allocation must allow (7 -> 72 registers, 28 warps/SM: the measured optimum of
 // the launch-shape sweeps in profiles/: more warps hide FP64 latency and fetch bubbles, fewer registers spill).
 template <int kMinBlocks, int kFeatures>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const __grid_constant__ DScene s_in,

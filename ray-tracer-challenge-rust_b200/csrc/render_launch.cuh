@@ -20,10 +20,11 @@ namespace rtc {
 #define RTC_BLOCK_THREADS 128
 #endif
 #ifndef RTC_BLOCKS_PER_SM
-#define RTC_BLOCKS_PER_SM 6
+#define RTC_BLOCKS_PER_SM 7
 #endif
 constexpr int kBlockThreads = RTC_BLOCK_THREADS;
-constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;  // 6 -> 80 registers, 24 warps/SM: the measured optimum (profiles/r01d)
+constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;  // 7 -> 72 registers, 28 warps/SM: the measured optimum of round 2's kernel
+                                                 // (profiles/r02zh_variants.json; 6 -> 80 registers was round 1's, profiles/r01d)
 constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
 
 // mask, in dispatch order (smallest first):  clustered cubes + refraction (table) | spheres + cylinders + groups (hexagon)
