@@ -25,7 +25,11 @@ namespace rtc {
 constexpr int kBlockThreads = RTC_BLOCK_THREADS;
 constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;  // 7 -> 72 registers, 28 warps/SM: the measured optimum of round 2's kernel
                                                  // (profiles/r02zh_variants.json; 6 -> 80 registers was round 1's, profiles/r01d)
-constexpr int kTileW = 8, kTileH = 4;  // one warp = one tile
+#ifndef RTC_TILE_W
+#define RTC_TILE_W 8
+#endif
+constexpr int kTileW = RTC_TILE_W, kTileH = 32 / RTC_TILE_W;  // one warp = one tile (8 x 4: profiles/r02zi_variants.json)
+static_assert(kTileW * kTileH == 32 && (kTileW & (kTileW - 1)) == 0, "a tile is one warp");
 
 // mask, in dispatch order (smallest first):  clustered cubes + refraction (table) | spheres + cylinders + groups (hexagon)
 // | mesh + groups (teapot) | + plane (cow & teddy) | + refraction (pumpkin) | every primitive kind, clusters (lists and
