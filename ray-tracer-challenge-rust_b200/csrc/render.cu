@@ -440,7 +440,7 @@ static int launch(DeviceScene* s, const DCamera& cam, const DRows& rows, void* d
     const uint64_t tiles = (uint64_t)((cam.hsize + kTileW - 1) / kTileW) * ((rows.row_count + kTileH - 1) / kTileH);
     const uint64_t warps_per_block = kBlockThreads / 32;
     uint64_t blocks = (tiles + warps_per_block - 1) / warps_per_block;
-    const uint64_t cap = (uint64_t)s->sm_count * kBlocksPerSm;
+    const uint64_t cap = (uint64_t)s->sm_count * blocks_per_sm_for(pick_instance(s->feature_mask).mask);
     if (blocks > cap) blocks = cap;
     // (Launching fewer CTAs for a small slice — a minimum number of tiles per warp, or exactly ceil(tiles / resident warps)
     // tiles for every warp — was measured and changes nothing: one rank's eighth of the 1080p table frame takes 0.121 ms with

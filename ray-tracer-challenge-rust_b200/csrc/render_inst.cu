@@ -73,8 +73,9 @@ __device__ __forceinline__ void tile_of(uint32_t q, uint32_t tiles_x, const DRow
     ty = rows.hot_y1 + q / tiles_x;
 }
 
-// kMinBlocks = CTAs per SM the register allocation must allow (7 -> 72 registers, 28 warps/SM: the measured optimum of
-// the launch-shape sweeps in profiles/: more warps hide FP64 latency and fetch bubbles, fewer registers spill).
+// kMinBlocks = CTAs per SM the register allocation must allow (6 -> 80 registers, 24 warps/SM: the measured optimum of
+// the launch-shape sweeps in profiles/: more warps hide FP64 latency and fetch bubbles, fewer registers spill; 7 for the
+// kernels render_launch.cuh names).
 template <int kMinBlocks, int kFeatures>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const __grid_constant__ DScene s_in,
                                                                const __grid_constant__ DCamera cam,
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) render_kernel(const
 #define RTC_CAT(a, b) RTC_CAT2(a, b)
 void RTC_CAT(launch_render_, RTC_INST_MASK)(unsigned grid, cudaStream_t stream, const DScene& s, const DCamera& cam,
                                             const DRows& rows, uint32_t* out8, double* out64, DQueue* q) {
-    render_kernel<kBlocksPerSm, RTC_INST_MASK><<<grid, kBlockThreads, 0, stream>>>(s, cam, rows, out8, out64, q);
+    render_kernel<blocks_per_sm_for(RTC_INST_MASK), RTC_INST_MASK><<<grid, kBlockThreads, 0, stream>>>(s, cam, rows, out8, out64, q);
 }
 
 }  // namespace rtc

@@ -20,11 +20,14 @@ namespace rtc {
 #define RTC_BLOCK_THREADS 128
 #endif
 #ifndef RTC_BLOCKS_PER_SM
-#define RTC_BLOCKS_PER_SM 7
+#define RTC_BLOCKS_PER_SM 6
 #endif
 constexpr int kBlockThreads = RTC_BLOCK_THREADS;
-constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;  // 7 -> 72 registers, 28 warps/SM: the measured optimum of round 2's kernel
-                                                 // (profiles/r02zh_variants.json; 6 -> 80 registers was round 1's, profiles/r01d)
+constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;  // 6 -> 80 registers, 24 warps/SM (profiles/r01d, r02c, r02zh)
+// ... except the mesh + plane kernels (cow & teddy, flat and smooth): 7 -> 72 registers, 28 warps/SM is 4.9 % faster there.
+// Everywhere else 7 is within 1 % and multiplies the local-memory DRAM traffic (table 11.6 -> 52.8 MB, pumpkin 1.0 -> 2.6 GB
+// per frame: profiles/r02zh_variants.json, the first r02z ncu captures).
+constexpr int blocks_per_sm_for(int mask) { return (mask == 98 || mask == 2146) ? kBlocksPerSm + 1 : kBlocksPerSm; }
 #ifndef RTC_TILE_W
 #define RTC_TILE_W 8
 #endif
