@@ -1,5 +1,6 @@
 """GPU parity: the CUDA path through the C ABI against the CPU oracle on the same worlds (-m gpu)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -467,3 +468,24 @@ def test_config_4_with_smooth_triangles(rtc, oracle):
     flat = np.empty((h, w, 4), dtype=np.uint8)
     fcam.render_into(fworld, rgba8=flat)
     assert (flat != rgba).any(axis=2).mean() > 0.02
+
+
+def test_two_process_peer_exchange_renders_the_single_gpu_frame(rtc):
+    """One process per GPU (multi.ShardedRenderer, peer exchange with completion counters): bench.py under torchrun at
+    N = 2 on a small frame; its own sharded_frame_check compares the sharded frame with rank 0's single-GPU render byte for
+    byte, after two dozen pipelined frames through both buffers.  Needs two GPUs (skipped on the one-GPU test box)."""
+    if rtc.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "bench.py"), "--gpus", "2", "--steps", "8", "--warmup", "3",
+           "--no-extras", "--workload", "cow_teddy", "--width", "640", "--height", "360"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().split("\n")[-1])
+    assert line["n_gpus"] == 2 and line["config"]["exchange"] == "peer"
+    assert line["sharded_frame_check"]["identical_to_single_gpu_render"] is True
