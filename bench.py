@@ -288,12 +288,31 @@ def run_b200(args):
     e2e_h2d = [0]
     world.set_build(args.e2e_build)
 
+    # N > 1: the Canvas lives in host memory shared by the ranks (multi.SharedCanvasRenderer): every rank's copy engine
+    # writes its own bands over its own PCIe link, completion is a counter per rank in the segment — so the drop-in call
+    # returns the SAME thing at every N (the f64 Canvas, 24 B/px).  If the segment cannot be set up (no /dev/shm, page
+    # locking refused) the loops fall back to the device-resident exchange + one RGBA8 copy from rank 0, and say so.
+    canvas_r = canvas8_r = None
+    canvas_error = None
+    if world_size > 1:
+        try:
+            canvas_r = multi.SharedCanvasRenderer(world, cam, rank, world_size, local_rank, args.band_rows, want_f64=True)
+            canvas8_r = multi.SharedCanvasRenderer(world, cam, rank, world_size, local_rank, args.band_rows,
+                                                   want_f64=False, want_rgba8=True)
+        except RuntimeError as e:  # raised on every rank alike (the constructor agrees on it collectively)
+            canvas_error = str(e)
+            if canvas_r is not None:
+                canvas_r.close()
+            canvas_r = canvas8_r = None
+
     def e2e_rgba8_step():
         scene = C.c_void_p()
         api.check(api.scene_create_ex(desc, local_rank, e2e_flags, C.byref(scene)))
         e2e_h2d[0] = int(api.scene_upload_bytes(scene))
         if world_size == 1:
             api.check(api.render(scene, C.byref(cdesc), None, C.c_void_p(host_frame.data_ptr()), None, None))
+        elif canvas8_r is not None:
+            canvas8_r.render(scene=scene)
         else:
             frame = renderer.render(scene=scene)
             if rank == 0:
@@ -308,6 +327,10 @@ def run_b200(args):
         if world_size == 1:
             canvas_box[0] = None  # rtc_canvas_free of the previous step's canvas (its pinned pages go back to the pool)
             canvas_box[0] = cam.render(world, want_f64=True, device=local_rank)
+        elif canvas_r is not None:
+            # one process per GPU: every rank marshals + uploads its replica, renders its bands and copies their f64
+            # colours into the shared canvas; rank 0 returns when every rank's bands have landed
+            canvas_r.render(scene=world.scene(local_rank))
         else:
             # one process per GPU: every rank marshals + uploads its replica, renders its bands into rank 0's frame
             frame = renderer.render(scene=world.scene(local_rank))
@@ -330,6 +353,10 @@ def run_b200(args):
     if world_size == 1:  # the drop-in call's own frame is the one the parity check below reads
         host_frame.copy_(torch.from_numpy(canvas_box[0].pixels_rgba8().reshape(h, w, 4)))
         e2e_d2h = 24 * w * h  # the f64 Canvas; its RGBA8 pixels are quantised on the host on demand (not in the timed call)
+    elif canvas_r is not None:
+        e2e_d2h = 24 * w * h  # summed over the ranks: each copies its own bands of the f64 Canvas
+        if rank == 0:
+            host_frame.copy_(torch.from_numpy(canvas8_r.views()[1]))
     else:
         e2e_d2h = 4 * w * h
     canvas_box[0] = None
@@ -371,6 +398,9 @@ def run_b200(args):
     if rank != 0:
         if world_size > 1:
             dist.barrier()  # rank 0 still reads the shared frame until its report is out
+            for c in (canvas_r, canvas8_r):
+                if c is not None:
+                    c.close()
             renderer.close()
             dist.destroy_process_group()
         return 0
@@ -428,13 +458,25 @@ def run_b200(args):
                          "World + flatten + mesh build + upload + render + the f64 Canvas (24 B/px) to pinned host memory "
                          "-> rtc_canvas_free; wall clock (as in the reference, the Canvas is quantised at PPM time)"
                          if world_size == 1 else
-                         "per step and rank: rtc_world_drop_scenes -> rtc_world_scene (marshal + flatten + mesh build + "
+                         "the drop-in call sharded over one process per GPU, per step and rank: rtc_world_drop_scenes -> "
+                         "rtc_world_scene (marshal + flatten + mesh build + upload) -> rtc_render(RTC_ROWS_FRAME) = render "
+                         "this rank's bands + copy their f64 colours (24 B/px) into the Canvas in host memory shared by the "
+                         "ranks, each over its own PCIe link -> per-rank completion counter; rank 0 returns when every "
+                         "rank's bands have landed; wall clock, max over ranks"
+                         if canvas_r is not None else
+                         "FALLBACK (no shared host canvas: " + str(canvas_error) + "): per step and rank: "
+                         "rtc_world_drop_scenes -> rtc_world_scene (marshal + flatten + mesh build + "
                          "upload) -> rtc_render_device (stores into rank 0's frame over NVLink) -> completion -> RGBA8 "
-                         "frame to pinned host memory on rank 0; wall clock, max over ranks")},
+                         "frame to pinned host memory on rank 0; wall clock, max over ranks"),
+                "exchange": "none (one GPU)" if world_size == 1 else
+                            "shared host canvas" if canvas_r is not None else "peer + one copy from rank 0"},
         "e2e_rgba8": {"value": e2e8_value, "unit": "Mrays/s", "frame_ms": e2e8_s / args.steps * 1e3,
                       "h2d_bytes_per_step": e2e_h2d[0], "d2h_bytes_per_step": int(4 * w * h), "build": build_note,
                       "what": "marshalled description kept; per step: rtc_scene_create_ex -> rtc_render into a pinned "
-                              "host RGBA8 frame (no f64 Canvas) -> rtc_scene_destroy; wall clock"},
+                              "host RGBA8 frame (no f64 Canvas) -> rtc_scene_destroy; wall clock"
+                              + ("" if world_size == 1 else
+                                 " — per rank, into the RGBA8 frame in host memory shared by the ranks" if canvas8_r is not None
+                                 else " — fallback: device-resident exchange + one copy from rank 0")},
         "gpu_launches": args.steps * 1,  # timed (device-resident) region: one render_kernel launch per frame
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -460,6 +502,15 @@ def run_b200(args):
         line["sharded_frame_check"] = {"identical_to_single_gpu_render": same, "bytes": int(whole.numel())}
         if not same:
             raise SystemExit("the sharded frame differs from the single-GPU frame")
+        if canvas_r is not None:
+            # the f64 Canvas the last e2e step left in shared host memory against rank 0's own single-GPU f64 render
+            whole64 = np.empty((h, w, 3))
+            cam.render_into(world, rgb_f64=whole64, device=local_rank)
+            same64 = bool(np.array_equal(whole64.view(np.uint64), canvas_r.views()[0].view(np.uint64)))
+            line["sharded_frame_check"]["f64_canvas_identical"] = same64
+            line["sharded_frame_check"]["f64_bytes"] = int(whole64.nbytes)
+            if not same64:
+                raise SystemExit("the sharded f64 canvas differs from the single-GPU canvas")
 
     if not args.no_cpu_baseline and world_size == 1:
         step_px = {"table": 8, "hexagon": 2, "teapot": 64, "cow_teddy": 96, "pumpkin": 192}.get(args.workload, 32)
@@ -499,6 +550,9 @@ def run_b200(args):
     emit(line)
     if world_size > 1:
         dist.barrier()
+        for c in (canvas_r, canvas8_r):
+            if c is not None:
+                c.close()
         renderer.close()
         dist.destroy_process_group()
     return 0

@@ -35,6 +35,7 @@ extern "C" {
 #define RTC_ERR_PANIC (-2)    /* the reference would have panicked (message says where: file:line) */
 #define RTC_ERR_CUDA (-3)     /* CUDA runtime failure or no device */
 #define RTC_ERR_UNSUPPORTED (-4)
+#define RTC_ERR_TIMEOUT (-6)  /* rtc_host_counter_wait: the counter did not get there in time */
 
 /* ShapeKind (src/shape.rs:14-39) */
 enum { RTC_SPHERE = 0, RTC_PLANE = 1, RTC_CUBE = 2, RTC_CYLINDER = 3, RTC_CONE = 4, RTC_GROUP = 5, RTC_TRIANGLE = 6,
@@ -170,7 +171,10 @@ uint64_t rtc_scene_upload_bytes(const rtc_scene* scene);
 /* Camera::render (src/camera.rs:67-79) with HOST output buffers (either may be NULL):
  *   rgba8_out  : rows*hsize*4 bytes, each channel quantised as canvas.rs:61-63 does at PPM time, alpha = 255
  *   rgb_f64_out: rows*hsize*3 doubles, the Canvas colours themselves (canvas.rs:24-26)
- * Includes the device->host copies.  `rows` NULL = whole frame. */
+ * Includes the device->host copies (rendered in a few launches so that the copies overlap the rendering).  `rows` NULL =
+ * whole frame.  With RTC_ROWS_COMPACT the buffers hold only this call's rows, packed; with RTC_ROWS_FRAME they are the WHOLE
+ * frame (vsize rows) and each rendered band is copied to its frame position, the other rows are left alone — what one rank
+ * of a sharded render passes when the frame lives in host memory shared by the ranks (rtc_host_share_*). */
 int rtc_render(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_rows* rows, uint8_t* rgba8_out,
                double* rgb_f64_out, rtc_stats* stats);
 
@@ -274,6 +278,24 @@ int rtc_enable_peer_access(int device, int peer);
 int rtc_frame_share_create(int device, uint64_t bytes, void** d_ptr, uint8_t handle64[64]);
 int rtc_frame_share_open(int device, const uint8_t handle64[64], void** d_ptr);
 int rtc_frame_share_close(int device, void* d_ptr, int owner);
+
+/* The Canvas of a sharded render in HOST memory shared by the PROCESSES (one per GPU): a POSIX shared-memory segment
+ * (`name` starts with '/', see shm_open(3)) that every rank maps and page-locks, so each rank's copy engine writes its own
+ * bands of the frame over its own PCIe link, all links in parallel (rtc_render with RTC_ROWS_FRAME and pointers into the
+ * segment) — instead of funnelling the frame through one GPU and one link.  create() makes the segment, zero-filled, and
+ * reserves its pages (fails cleanly when /dev/shm is too small); open() maps an existing one; close() unmaps and, given a
+ * name, unlinks it (the creator, after every rank has closed).  `device`: any CUDA device of the calling process; a negative
+ * device maps without page-locking (no CUDA call: copies into it still work, staged by the driver).
+ * Completion across processes is a counter in the segment itself: 8-byte aligned uint64 slots, store = release, load / wait =
+ * acquire; wait spins (then yields) until the slot is >= at_least or fails with RTC_ERR_TIMEOUT.  rtc_render returns after
+ * its copies have landed, so "rank r stores frame number f into its slot after rtc_render; the consumer waits for every
+ * slot to reach f" is a complete protocol (ray-tracer-challenge-rust_b200/multi.py SharedCanvasRenderer). */
+int rtc_host_share_create(int device, const char* name, uint64_t bytes, void** out);
+int rtc_host_share_open(int device, const char* name, uint64_t bytes, void** out);
+int rtc_host_share_close(void* p, uint64_t bytes, const char* unlink_name);
+void rtc_host_counter_store(void* counter, uint64_t value);
+uint64_t rtc_host_counter_load(const void* counter);
+int rtc_host_counter_wait(const void* counter, uint64_t at_least, double timeout_s);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * 2. HOST MIRROR of the reference API (C++ inside; the Rust host in the reference)

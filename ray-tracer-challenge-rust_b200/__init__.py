@@ -14,7 +14,7 @@ import numpy as np
 
 from . import scenes  # noqa: F401
 from ._capi import BuilderApi, CameraDesc, Rows, Stats, as_f64, dptr
-from ._lib import (LIB_PATH, RTC_BUILD_DEVICE_LBVH, RTC_BUILD_HOST_SAH, RTC_ERR_CUDA, RTC_ERR_INVALID, RTC_ERR_PANIC, RTC_ERR_UNSUPPORTED, RTC_OK, RtcError,
+from ._lib import (LIB_PATH, RTC_BUILD_DEVICE_LBVH, RTC_BUILD_HOST_SAH, RTC_ERR_CUDA, RTC_ERR_INVALID, RTC_ERR_PANIC, RTC_ERR_TIMEOUT, RTC_ERR_UNSUPPORTED, RTC_OK, RtcError,
                    api)
 from .scene_api import (BLACK, BLUE, GREEN, RED, WHITE, CameraHandle, Light, Material, Matrix, Pattern, Shape, Shapes,
                         Transformations, WorldHandle)

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RTC_B200_LIB") or os.path.join(HERE, "librtc_b200.so")
 
 RTC_BUILD_HOST_SAH, RTC_BUILD_DEVICE_LBVH = 0, 1
-RTC_OK, RTC_ERR_INVALID, RTC_ERR_PANIC, RTC_ERR_CUDA, RTC_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+RTC_OK, RTC_ERR_INVALID, RTC_ERR_PANIC, RTC_ERR_CUDA, RTC_ERR_UNSUPPORTED, RTC_ERR_TIMEOUT = 0, -1, -2, -3, -4, -6
 
 
 class RtcError(RuntimeError):
@@ -47,6 +47,12 @@ class RtcApi(BuilderApi):
         f("frame_share_create", C.c_int, C.c_int, C.c_uint64, C.POINTER(vp), C.c_char_p)
         f("frame_share_open", C.c_int, C.c_int, C.c_char_p, C.POINTER(vp))
         f("frame_share_close", C.c_int, C.c_int, vp, C.c_int)
+        f("host_share_create", C.c_int, C.c_int, C.c_char_p, C.c_uint64, C.POINTER(vp))
+        f("host_share_open", C.c_int, C.c_int, C.c_char_p, C.c_uint64, C.POINTER(vp))
+        f("host_share_close", C.c_int, vp, C.c_uint64, C.c_char_p)
+        f("host_counter_store", None, vp, C.c_uint64)
+        f("host_counter_load", C.c_uint64, vp)
+        f("host_counter_wait", C.c_int, vp, C.c_uint64, C.c_double)
         f("scene_create", C.c_int, vp, C.c_int, C.POINTER(vp))
         f("scene_create_ex", C.c_int, vp, C.c_int, C.c_uint32, C.POINTER(vp))
         f("scene_destroy", None, vp)

@@ -2,6 +2,14 @@
 // Camera::render (camera.rs:67-79) and World::color_at (world.rs:80-82), and the HOST MIRROR of the reference's scene
 // API.  There is no CPU rendering path in this library: every render / color_at call needs a CUDA device and fails with
 // RTC_ERR_CUDA otherwise.
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -196,6 +204,84 @@ int rtc_frame_share_close(int device, void* d_ptr, int owner) {
     if (frame_share_close(device, d_ptr, owner, &e) != 0) return set_err(RTC_ERR_CUDA, e);
     return RTC_OK;
 }
+/* Host memory shared by the processes of a sharded render: a POSIX shared-memory segment, mapped and page-locked in every
+ * process that opens it.  The creator reserves the pages up front (posix_fallocate), so a /dev/shm that is too small is an
+ * error here and not a SIGBUS in the middle of a frame. */
+static std::mutex g_share_mu;
+static std::map<void*, bool> g_share_locked;  // live mappings -> page-locked?
+static int host_share_map(int device, const char* name, uint64_t bytes, bool create, void** out) {
+    if (!name || name[0] != '/' || !out || bytes == 0) return set_err(RTC_ERR_INVALID, "host share: name must start with '/', bytes > 0");
+    *out = nullptr;
+    const int fd = shm_open(name, create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) return set_err(RTC_ERR_INVALID, std::string("shm_open ") + name + ": " + std::strerror(errno));
+    const auto fail = [&](const std::string& what, int code) {
+        close(fd);
+        if (create) shm_unlink(name);
+        return set_err(code, what);
+    };
+    if (create) {
+        const int rc = posix_fallocate(fd, 0, (off_t)bytes);
+        if (rc != 0) return fail(std::string("posix_fallocate ") + name + ": " + std::strerror(rc), RTC_ERR_INVALID);
+    } else {
+        struct stat st;
+        if (fstat(fd, &st) != 0 || (uint64_t)st.st_size < bytes) return fail(std::string(name) + " is smaller than the requested size", RTC_ERR_INVALID);
+    }
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (p == MAP_FAILED) return fail(std::string("mmap ") + name + ": " + std::strerror(errno), RTC_ERR_INVALID);
+    std::string e;
+    if (device >= 0 && host_register(device, p, bytes, &e) != 0) {
+        munmap(p, bytes);
+        return fail(e, RTC_ERR_CUDA);
+    }
+    close(fd);
+    {
+        std::lock_guard<std::mutex> lk(g_share_mu);
+        g_share_locked[p] = device >= 0;
+    }
+    *out = p;
+    return RTC_OK;
+}
+int rtc_host_share_create(int device, const char* name, uint64_t bytes, void** out) {
+    return host_share_map(device, name, bytes, true, out);
+}
+int rtc_host_share_open(int device, const char* name, uint64_t bytes, void** out) {
+    return host_share_map(device, name, bytes, false, out);
+}
+int rtc_host_share_close(void* p, uint64_t bytes, const char* unlink_name) {
+    int rc = RTC_OK;
+    if (p) {
+        bool locked = false;
+        {
+            std::lock_guard<std::mutex> lk(g_share_mu);
+            auto it = g_share_locked.find(p);
+            if (it == g_share_locked.end()) return set_err(RTC_ERR_INVALID, "not a mapping of rtc_host_share_create / _open");
+            locked = it->second;
+            g_share_locked.erase(it);
+        }
+        std::string e;
+        if (locked && host_unregister(p, &e) != 0) rc = set_err(RTC_ERR_CUDA, e);
+        munmap(p, bytes);
+    }
+    if (unlink_name) shm_unlink(unlink_name);
+    return rc;
+}
+void rtc_host_counter_store(void* counter, uint64_t value) { __atomic_store_n((uint64_t*)counter, value, __ATOMIC_RELEASE); }
+uint64_t rtc_host_counter_load(const void* counter) { return __atomic_load_n((const uint64_t*)counter, __ATOMIC_ACQUIRE); }
+int rtc_host_counter_wait(const void* counter, uint64_t at_least, double timeout_s) {
+    if (!counter) return set_err(RTC_ERR_INVALID, "null argument");
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint64_t spin = 0;; spin++) {
+        if (__atomic_load_n((const uint64_t*)counter, __ATOMIC_ACQUIRE) >= at_least) return RTC_OK;
+        if ((spin & 1023) == 1023) {
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s)
+                return set_err(RTC_ERR_TIMEOUT, "host counter did not reach " + std::to_string(at_least) + " (a rank of the sharded render is missing)");
+            if (spin > (1u << 20)) sched_yield();
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
 int rtc_device_count(void) {
     std::string e;
     int n = cuda_device_count(&e);
@@ -248,7 +334,6 @@ int rtc_render(const rtc_scene* scene, const rtc_camera_desc* camera, const rtc_
     if (rc != RTC_OK) return rc;
     LaunchStats ls;
     std::string e;
-    if (dr.frame_layout) return set_err(RTC_ERR_INVALID, "RTC_ROWS_FRAME needs device buffers (rtc_render_device)");
     rc = render_host(scene->dev, to_dcamera(*camera), dr, rgba8_out, rgb_f64_out, stats ? &ls : nullptr, &e);
     if (rc != 0) return set_err(RTC_ERR_CUDA, e);
     fill_stats(ls, stats);

@@ -155,7 +155,10 @@ struct DRows {
     uint32_t hot_x0, hot_y0, hot_x1, hot_y1;
 };
 // depth of the per-thread traversal stack; flatten.hpp refuses a mesh whose BVH is deeper (the builder bounds depth)
-constexpr int kBvhStackDepth = 48;
+#if !defined(RTC_BVH_STACK_DEPTH)  // A/B switch (tools/tune_variants.py, tools/dram_variants.py)
+#define RTC_BVH_STACK_DEPTH 48
+#endif
+constexpr int kBvhStackDepth = RTC_BVH_STACK_DEPTH;
 // the same for a kernel whose scenes hold clusters but no meshes (a cluster tree deeper than this is not built: its leaves
 // stay PRIM entries)
 constexpr int kClusterStackDepth = 16;

@@ -508,11 +508,44 @@ int render_device_end(DeviceScene* s, void* stream, void* token, LaunchStats* st
 }
 void* device_scene_stream(const DeviceScene* s) { return s->stream; }
 
-int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* rgba8, double* rgb_f64,
+// Local rows [r0, r1) of a compact device buffer -> the host buffer.  Compact host buffer: the same offsets.  Frame layout
+// (the host pointer addresses the WHOLE frame): local band j lands at frame band band_first + j * band_stride — one
+// strided copy for the whole bands of the range, one more for the frame's ragged last band; r0 is a multiple of band_rows.
+static int copy_rows_out(const DCamera& cam, const DRows& rows, bool to_frame, unsigned char* host, const unsigned char* dev,
+                         size_t bytes_per_pixel, uint32_t r0, uint32_t r1, cudaStream_t st, std::string* err) {
+    if (r1 <= r0 || cam.hsize == 0) return 0;
+    const size_t row_bytes = (size_t)cam.hsize * bytes_per_pixel;
+    if (!to_frame) {
+        RTC_CUDA(cudaMemcpyAsync(host + r0 * row_bytes, dev + r0 * row_bytes, (size_t)(r1 - r0) * row_bytes,
+                                 cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+    const size_t band_bytes = row_bytes * rows.band_rows;
+    const uint32_t b0 = r0 / rows.band_rows, full = (r1 - r0) / rows.band_rows;
+    const uint32_t rest = (r1 - r0) - full * rows.band_rows;
+    const auto frame_band = [&](uint32_t local_band) {
+        return host + ((size_t)rows.band_first + (size_t)local_band * rows.band_stride) * band_bytes;
+    };
+    if (full)
+        RTC_CUDA(cudaMemcpy2DAsync(frame_band(b0), band_bytes * rows.band_stride, dev + r0 * row_bytes, band_bytes, band_bytes,
+                                   full, cudaMemcpyDeviceToHost, st));
+    if (rest)
+        RTC_CUDA(cudaMemcpyAsync(frame_band(b0 + full), dev + ((size_t)r0 + (size_t)full * rows.band_rows) * row_bytes,
+                                 (size_t)rest * row_bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows_in, uint8_t* rgba8, double* rgb_f64,
                 LaunchStats* stats, std::string* err) {
     std::lock_guard<std::mutex> lk(s->mu());
     DeviceGuard guard_;
     RTC_CUDA(cudaSetDevice(s->device));
+    // RTC_ROWS_FRAME with host buffers: the kernel still renders into COMPACT device buffers; the copies place each band
+    // at its frame position in the host frame (e.g. a canvas in host memory shared by one process per GPU: every rank's
+    // copy engine writes its own bands over its own PCIe link).  The whole frame is its own compact form.
+    const bool to_frame = rows_in.frame_layout != 0 && !(rows_in.band_first == 0 && rows_in.band_stride == 1);
+    DRows rows = rows_in;
+    rows.frame_layout = 0;
     const size_t px = (size_t)rows.local_rows * cam.hsize;
     if (rgba8 && s->ctx->out8_size < px * 4) {
         if (s->ctx->out8) cudaFree(s->ctx->out8);
@@ -543,8 +576,12 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* 
         int rc = launch(s, cam, rows, rgba8 ? s->ctx->out8 : nullptr, rgb_f64 ? s->ctx->out64 : nullptr, s->stream,
                         stats != nullptr, &q, err);
         if (rc) return rc;
-        if (rgba8 && px) RTC_CUDA(cudaMemcpyAsync(rgba8, s->ctx->out8, px * 4, cudaMemcpyDeviceToHost, s->stream));
-        if (rgb_f64 && px) RTC_CUDA(cudaMemcpyAsync(rgb_f64, s->ctx->out64, px * 24, cudaMemcpyDeviceToHost, s->stream));
+        if (rgba8 && (rc = copy_rows_out(cam, rows, to_frame, rgba8, (const unsigned char*)s->ctx->out8, 4, 0, rows.local_rows,
+                                         s->stream, err)))
+            return rc;
+        if (rgb_f64 && (rc = copy_rows_out(cam, rows, to_frame, (unsigned char*)rgb_f64, (const unsigned char*)s->ctx->out64, 24,
+                                           0, rows.local_rows, s->stream, err)))
+            return rc;
     } else {
         DeviceContext* ctx = s->ctx;
         if (!ctx->copy_stream) {
@@ -554,7 +591,11 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* 
         }
         uint32_t cut[kHostChunks + 1];  // chunk k renders local rows [cut[k], cut[k + 1])
         int nchunks;
-        const auto tile_rows = [](uint32_t r) { return (r + kTileH - 1) / kTileH * kTileH; };
+        // chunks start on a tile row, and for a frame-layout copy on a band as well
+        uint32_t unit = kTileH;
+        if (to_frame)
+            for (unit = rows.band_rows; unit % kTileH; unit += rows.band_rows) {}
+        const auto tile_rows = [&](uint32_t r) { return std::min(rows.local_rows, (r + unit - 1) / unit * unit); };
         if (rgb_f64) {
             nchunks = 4;
             cut[0] = 0;
@@ -577,13 +618,12 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* 
             if (rc) return rc;
             RTC_CUDA(cudaEventRecord(ctx->chunk_done[k], s->stream));
             RTC_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done[k], 0));
-            const size_t p0 = (size_t)cut[k] * cam.hsize, pn = (size_t)part.row_count * cam.hsize;
-            if (rgba8 && pn)
-                RTC_CUDA(cudaMemcpyAsync(rgba8 + p0 * 4, (const unsigned char*)ctx->out8 + p0 * 4, pn * 4,
-                                         cudaMemcpyDeviceToHost, ctx->copy_stream));
-            if (rgb_f64 && pn)
-                RTC_CUDA(cudaMemcpyAsync(rgb_f64 + p0 * 3, (const double*)ctx->out64 + p0 * 3, pn * 24,
-                                         cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (rgba8 && (rc = copy_rows_out(cam, rows, to_frame, rgba8, (const unsigned char*)ctx->out8, 4, cut[k], cut[k + 1],
+                                             ctx->copy_stream, err)))
+                return rc;
+            if (rgb_f64 && (rc = copy_rows_out(cam, rows, to_frame, (unsigned char*)rgb_f64, (const unsigned char*)ctx->out64,
+                                               24, cut[k], cut[k + 1], ctx->copy_stream, err)))
+                return rc;
         }
         RTC_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
         RTC_CUDA(cudaStreamWaitEvent(s->stream, ctx->copy_done, 0));
@@ -717,6 +757,19 @@ int stream_counters_set(int device, void* stream, void* const* d_counters, uint3
 }
 int stream_counters_add(int device, void* stream, void* const* d_counters, uint32_t n, std::string* err) {
     return counters_store(device, stream, d_counters, n, 0, 1, err);
+}
+
+// Page-locks host memory the caller mapped itself (a POSIX shared-memory segment: capi.cpp rtc_host_share_*), for every
+// CUDA context of the process, so copies into it are asynchronous DMA at PCIe speed.
+int host_register(int device, void* p, size_t bytes, std::string* err) {
+    DeviceGuard guard_;
+    RTC_CUDA(cudaSetDevice(device));
+    RTC_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+int host_unregister(void* p, std::string* err) {
+    RTC_CUDA(cudaHostUnregister(p));
+    return 0;
 }
 
 void* pinned_alloc(size_t bytes) {

@@ -44,7 +44,8 @@ int render_device_begin(DeviceScene* s, const DCamera& cam, const DRows& rows, v
                         void** token, std::string* err);
 int render_device_end(DeviceScene* s, void* stream, void* token, LaunchStats* stats, std::string* err);
 void* device_scene_stream(const DeviceScene* s);
-// Same with host outputs (pinned or pageable), including the device->host copies.
+// Same with host outputs (pinned or pageable), including the device->host copies.  rows.frame_layout: the host pointers
+// address the whole frame and every rendered band is copied to its frame position.
 int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows, uint8_t* rgba8, double* rgb_f64,
                 LaunchStats* stats, std::string* err);
 // World::color_at for explicit rays (host in, host out).
@@ -97,6 +98,9 @@ int ppm_encode_device(int device, const void* d_rgba8, uint64_t width, uint64_t 
 // Pinned host memory for frame buffers (so device->host copies run at PCIe speed); falls back to nothing — returns null
 // on failure and the caller reports RTC_ERR_CUDA.
 void* pinned_alloc(size_t bytes);
+// cudaHostRegister(portable) / cudaHostUnregister of caller-mapped host memory (rtc_host_share_*).
+int host_register(int device, void* p, size_t bytes, std::string* err);
+int host_unregister(void* p, std::string* err);
 void pinned_free(void* p);
 
 }  // namespace rtc

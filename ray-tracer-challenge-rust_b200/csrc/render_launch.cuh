@@ -27,7 +27,13 @@ constexpr int kBlocksPerSm = RTC_BLOCKS_PER_SM;  // 6 -> 80 registers, 24 warps/
 // ... except the mesh + plane kernels (cow & teddy, flat and smooth): 7 -> 72 registers, 28 warps/SM is 4.9 % faster there.
 // Everywhere else 7 is within 1 % and multiplies the local-memory DRAM traffic (table 11.6 -> 52.8 MB, pumpkin 1.0 -> 2.6 GB
 // per frame: profiles/r02zh_variants.json, the first r02z ncu captures).
-constexpr int blocks_per_sm_for(int mask) { return (mask == 98 || mask == 2146) ? kBlocksPerSm + 1 : kBlocksPerSm; }
+// The mesh + refraction kernel (pumpkin) runs 5 -> 96 registers, 20 warps/SM: its frames hold ~300 bytes of live state per
+// thread across every scene walk, and with 6 CTAs per SM that working set no longer stays in L2 — 1.00 GB of DRAM writes per 8K
+// frame against 0.24 GB with 5 (the frame itself is 0.13 GB) for 0.6 % of frame time (10.04 -> 10.10 ms;
+// profiles/r02zk_dram_variants.json; the size of the traversal stack ALLOCATION, 48 / 32 / 24 entries, changes nothing).
+constexpr int blocks_per_sm_for(int mask) {
+    return (mask == 98 || mask == 2146) ? kBlocksPerSm + 1 : mask == 226 ? kBlocksPerSm - 1 : kBlocksPerSm;
+}
 #ifndef RTC_TILE_W
 #define RTC_TILE_W 8
 #endif

@@ -287,3 +287,172 @@ class ShardedRenderer:
         dist.gather(self.local, list(self.gathered.unbind(0)) if self.rank == 0 else None, dst=0)
         self._f += 1
         return self.plan.assemble(self.gathered) if self.rank == 0 else None
+
+
+def canvas_schedule(rank, world_size, f):
+    """The host-side operations of frame f (1-based) on `rank` for a canvas in host memory shared by the ranks
+    (SharedCanvasRenderer.render runs them; tests/test_multi_cpu.py simulates them under adversarial interleavings).  The
+    segment holds ONE canvas, a `consumed` counter rank 0 owns and a `done` counter per rank:
+        ("set_consumed", v)   rank 0: the caller asked for the next frame, so frames <= v are no longer being read
+        ("wait_consumed", v)  the rank waits until frames <= v are consumed before it overwrites their pixels
+        ("render",)           rtc_render with RTC_ROWS_FRAME into the canvas: returns when this rank's bands have landed
+        ("set_done", v)       this rank's bands of frame v are in the canvas
+        ("wait_done", v)      rank 0 waits for every other rank's done counter to reach v
+    A rank can finish frame f before rank 0 has even started it, but never touches the canvas of a frame rank 0's caller may
+    still be reading."""
+    ops = []
+    if rank == 0:
+        ops.append(("set_consumed", f - 1))
+    else:
+        ops.append(("wait_consumed", f - 1))
+    ops.append(("render",))
+    ops.append(("set_done", f))
+    if rank == 0 and world_size > 1:
+        ops.append(("wait_done", f))
+    return ops
+
+
+class SharedCanvasRenderer:
+    """Camera::render of one frame across `world_size` ranks (one process per GPU) with the Canvas in HOST memory shared
+    by the processes: every rank renders its bands and its own copy engine writes them into the canvas over its own PCIe
+    link (rtc_render + RTC_ROWS_FRAME into an rtc_host_share segment) — the frame never funnels through one GPU and one
+    link, and there is no collective per frame: completion is a counter per rank in the segment itself.
+
+    want_f64: the canvas holds the f64 colours (24 B/px — the reference's Canvas, canvas.rs:8); want_rgba8: the quantised
+    RGBA8 frame (4 B/px).  Rank 0's render() returns numpy views of them; they stay valid until its next render().
+    `name`: the segment's name when the launcher hands it out itself; by default rank 0 invents one and broadcasts it with
+    torch.distributed (set-up only).  page_lock=False maps without cudaHostRegister (CPU tests of the protocol)."""
+
+    HEADER = 4096  # counters: consumed at byte 0, done[r] at byte 64 * (r + 1)
+
+    def __init__(self, world, camera, rank=0, world_size=1, device=0, band_rows=8, want_f64=True, want_rgba8=False,
+                 name=None, timeout_s=120.0, page_lock=True):
+        import ctypes as C
+        if not (want_f64 or want_rgba8):
+            raise ValueError("a canvas needs its f64 colours, its RGBA8 pixels, or both")
+        if world_size > (self.HEADER // 64) - 1:
+            raise ValueError("too many ranks for the counter block")
+        self.world, self.camera, self.rank, self.world_size, self.device = world, camera, rank, world_size, device
+        self.api = camera.api
+        self.plan = BandPlan(camera.vsize, world_size, band_rows)
+        self.rows = self.plan.rows(rank, frame_layout=True)
+        self.timeout_s = float(timeout_s)
+        px = camera.hsize * camera.vsize
+        page = 4096
+        self._off64 = self.HEADER
+        self._off8 = self._off64 + ((px * 24 + page - 1) // page * page if want_f64 else 0)
+        self.nbytes = self._off8 + ((px * 4 + page - 1) // page * page if want_rgba8 else 0)
+        self.want_f64, self.want_rgba8 = bool(want_f64), bool(want_rgba8)
+        self._base = None
+        self._f = 0
+        dev_arg = device if page_lock else -1
+        failure = None
+        if name is None and world_size > 1:
+            import torch.distributed as dist
+            box = [None]
+            if rank == 0:
+                name = self._fresh_name()
+                try:
+                    self._map(dev_arg, name, create=True)
+                    box[0] = name
+                except Exception as e:  # /dev/shm too small, registration refused, ...
+                    failure = e
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                if box[0] is None:
+                    failure = RuntimeError("rank 0 could not create the shared canvas")
+                else:
+                    name = box[0]
+                    try:
+                        self._map(dev_arg, name, create=False)
+                    except Exception as e:
+                        failure = e
+            # every rank learns whether every rank has the canvas (same collectives on every rank whatever failed locally)
+            oks = [None] * world_size
+            dist.all_gather_object(oks, failure is None)
+            if not all(oks):
+                self._unmap(unlink=(rank == 0 and box[0] is not None))
+                raise RuntimeError("the shared canvas could not be set up on every rank: "
+                                   + (f"{type(failure).__name__}: {failure}" if failure else "another rank failed"))
+            self.name = name
+            self._owner = rank == 0
+        else:
+            self.name = name or self._fresh_name()
+            self._owner = rank == 0
+            self._map(dev_arg, self.name, create=self._owner)
+        self._C = C
+
+    @staticmethod
+    def _fresh_name():
+        import os
+        import secrets
+        return f"/rtc_canvas_{os.getpid()}_{secrets.token_hex(6)}"
+
+    def _map(self, dev_arg, name, create):
+        import ctypes as C
+        p = C.c_void_p()
+        fn = self.api.host_share_create if create else self.api.host_share_open
+        self.api.check(fn(dev_arg, name.encode(), self.nbytes, C.byref(p)))
+        self._base = p.value
+
+    def _unmap(self, unlink):
+        if self._base is not None:
+            self.api.host_share_close(self._base, self.nbytes, self.name.encode() if unlink and self.name else None)
+            self._base = None
+
+    def _counter(self, slot):
+        return self._C.c_void_p(self._base + 64 * slot)
+
+    def views(self):
+        """numpy views (f64 [vsize, W, 3] or None, rgba8 [vsize, W, 4] or None) of the shared canvas."""
+        import ctypes as C
+        import numpy as np
+        h, w = self.camera.vsize, self.camera.hsize
+        f64 = rgba = None
+        if self.want_f64:
+            f64 = np.ctypeslib.as_array((C.c_double * (h * w * 3)).from_address(self._base + self._off64)).reshape(h, w, 3)
+        if self.want_rgba8:
+            rgba = np.ctypeslib.as_array((C.c_uint8 * (h * w * 4)).from_address(self._base + self._off8)).reshape(h, w, 4)
+        return f64, rgba
+
+    def _render_rows(self, scene, stats):
+        C = self._C
+        target = scene if scene is not None else self.world
+        sc = target.scene(self.device) if hasattr(target, "scene") else target
+        d = self.camera.desc()
+        self.api.check(self.api.render(sc, C.byref(d), C.byref(self.rows),
+                                       C.c_void_p(self._base + self._off8) if self.want_rgba8 else None,
+                                       C.c_void_p(self._base + self._off64) if self.want_f64 else None,
+                                       C.byref(stats) if stats is not None else None))
+
+    def render(self, scene=None, stats=None, _render=None):
+        """One frame; collective in the sense that every rank must call it the same number of times.  Returns (f64, rgba8)
+        views on rank 0 once every rank's bands have landed, None elsewhere.  `stats`: this rank's counters (one launch)."""
+        api, f = self.api, self._f + 1
+        for op in canvas_schedule(self.rank, self.world_size, f):
+            if op[0] == "set_consumed":
+                api.host_counter_store(self._counter(0), op[1])
+            elif op[0] == "wait_consumed":
+                api.check(api.host_counter_wait(self._counter(0), op[1], self.timeout_s))
+            elif op[0] == "render":
+                (_render or self._render_rows)(scene, stats)
+            elif op[0] == "set_done":
+                api.host_counter_store(self._counter(1 + self.rank), op[1])
+            elif op[0] == "wait_done":
+                for r in range(1, self.world_size):
+                    api.check(api.host_counter_wait(self._counter(1 + r), op[1], self.timeout_s))
+        self._f = f
+        return self.views() if self.rank == 0 else None
+
+    def close(self):
+        """Collective when set up through torch.distributed: every rank unmaps before rank 0 unlinks the name."""
+        if self._base is None:
+            return
+        if self.world_size > 1:
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    dist.barrier()
+            except ImportError:
+                pass
+        self._unmap(unlink=self._owner)

@@ -21,6 +21,7 @@ pub const RTC_ERR_INVALID: c_int = -1;
 pub const RTC_ERR_PANIC: c_int = -2;
 pub const RTC_ERR_CUDA: c_int = -3;
 pub const RTC_ERR_UNSUPPORTED: c_int = -4;
+pub const RTC_ERR_TIMEOUT: c_int = -6;
 
 /// ShapeKind (src/shape.rs:14-39)
 pub const RTC_SPHERE: i32 = 0;
@@ -295,6 +296,13 @@ extern "C" {
     pub fn rtc_frame_share_create(device: c_int, bytes: u64, d_ptr: *mut *mut c_void, handle64: *mut u8) -> c_int;
     pub fn rtc_frame_share_open(device: c_int, handle64: *const u8, d_ptr: *mut *mut c_void) -> c_int;
     pub fn rtc_frame_share_close(device: c_int, d_ptr: *mut c_void, owner: c_int) -> c_int;
+    /// the Canvas of a sharded render in host memory shared by one process per GPU (POSIX shared memory, page-locked)
+    pub fn rtc_host_share_create(device: c_int, name: *const c_char, bytes: u64, out: *mut *mut c_void) -> c_int;
+    pub fn rtc_host_share_open(device: c_int, name: *const c_char, bytes: u64, out: *mut *mut c_void) -> c_int;
+    pub fn rtc_host_share_close(p: *mut c_void, bytes: u64, unlink_name: *const c_char) -> c_int;
+    pub fn rtc_host_counter_store(counter: *mut c_void, value: u64);
+    pub fn rtc_host_counter_load(counter: *const c_void) -> u64;
+    pub fn rtc_host_counter_wait(counter: *const c_void, at_least: u64, timeout_s: f64) -> c_int;
 
     /// Canvas::to_ppm (src/canvas.rs:28-58) for an RGBA8 frame in device memory
     pub fn rtc_ppm_max_bytes(width: u64, height: u64) -> u64;

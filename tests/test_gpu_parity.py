@@ -194,6 +194,52 @@ def test_frame_layout_rows_write_in_place(rtc):
     assert np.array_equal(frame.cpu().numpy(), full)
 
 
+@pytest.mark.parametrize("w,h,band_rows,stride", [(200, 117, 8, 3), (96, 1100, 8, 2), (64, 1043, 5, 3), (128, 600, 600, 1)])
+def test_frame_layout_rows_to_a_host_frame(rtc, w, h, band_rows, stride):
+    """rtc_render with RTC_ROWS_FRAME and HOST buffers: each call's bands are copied to their frame positions in one host
+    frame (the copies of one rank of a sharded render into the shared canvas) and every other row is left alone; both the
+    single-launch path and the chunked, overlapped one (>= 256 local rows), ragged last bands, RGBA8 and the f64 Canvas."""
+    world, cam = rtc.build_scene("table", w, h)
+    full8, full64 = np.empty((h, w, 4), dtype=np.uint8), np.empty((h, w, 3))
+    cam.render_into(world, rgba8=full8, rgb_f64=full64)
+    out8, out64 = np.full((h, w, 4), 0x5A, dtype=np.uint8), np.full((h, w, 3), -7.0)
+    for first in range(stride):
+        before8, before64 = out8.copy(), out64.copy()
+        rows = rtc.Rows(band_rows, first, stride, rtc.Rows.FRAME)
+        cam.render_into(world, rgba8=out8, rgb_f64=out64, rows=rows)
+        mine = ((np.arange(h) // band_rows) % stride) == first
+        assert np.array_equal(out8[mine], full8[mine]) and np.array_equal(out64[mine].view(np.uint64), full64[mine].view(np.uint64))
+        assert np.array_equal(out8[~mine], before8[~mine]) and np.array_equal(out64[~mine], before64[~mine])
+    assert np.array_equal(out8, full8) and np.array_equal(out64.view(np.uint64), full64.view(np.uint64))
+    # one buffer only, with stats (a single timed launch)
+    st = rtc.Stats()
+    out8[:] = 0
+    cam.render_into(world, rgba8=out8, rows=rtc.Rows(band_rows, 0, stride, rtc.Rows.FRAME), stats=st)
+    mine = ((np.arange(h) // band_rows) % stride) == 0
+    assert np.array_equal(out8[mine], full8[mine]) and not out8[~mine].any() and st.primary_rays == int(mine.sum()) * w
+
+
+def test_shared_canvas_single_rank(rtc):
+    """multi.SharedCanvasRenderer with one rank: the canvas lives in a page-locked POSIX shared-memory segment and holds the
+    frame rtc_render produces, f64 colours and RGBA8 pixels, frame after frame."""
+    import importlib
+    multi = importlib.import_module("ray-tracer-challenge-rust_b200.multi")
+    world, cam = rtc.build_scene("hexagon", 320, 160)
+    full8, full64 = np.empty((160, 320, 4), dtype=np.uint8), np.empty((160, 320, 3))
+    cam.render_into(world, rgba8=full8, rgb_f64=full64)
+    r = multi.SharedCanvasRenderer(world, cam, 0, 1, 0, want_f64=True, want_rgba8=True)
+    try:
+        for _ in range(3):
+            f64, rgba = r.render()
+            assert np.array_equal(rgba, full8) and np.array_equal(f64.view(np.uint64), full64.view(np.uint64))
+            f64[:] = 0
+            rgba[:] = 0
+        assert os.path.exists("/dev/shm" + r.name)
+    finally:
+        r.close()
+    assert not os.path.exists("/dev/shm" + r.name)
+
+
 def test_full_size_properties_8k(rtc):
     """BASELINE config 5 at its full 7680x4320: properties that need no oracle — rendering is idempotent, eight cyclic
     band shards (the 8-GPU decomposition) written in place reproduce the single-launch frame bit for bit, and the
@@ -489,3 +535,5 @@ def test_two_process_peer_exchange_renders_the_single_gpu_frame(rtc):
     line = json.loads(out.stdout.strip().split("\n")[-1])
     assert line["n_gpus"] == 2 and line["config"]["exchange"] == "peer"
     assert line["sharded_frame_check"]["identical_to_single_gpu_render"] is True
+    # the e2e loops ran through the canvas in shared host memory, and it held the single-GPU render's f64 colours
+    assert line["e2e"]["exchange"] == "shared host canvas" and line["sharded_frame_check"]["f64_canvas_identical"] is True

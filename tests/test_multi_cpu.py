@@ -160,3 +160,121 @@ def test_hot_rectangle_tile_order_is_a_bijection():
             x0 = x1 = y0 = y1 = 0
         seen = {tile_of(q, tx, (x0, y0, x1, y1)) for q in range(tx * ty)}
         assert seen == {(a, b) for a in range(tx) for b in range(ty)}
+
+
+@pytest.mark.parametrize("g", [1, 2, 4, 8])
+@pytest.mark.parametrize("seed", range(6))
+def test_shared_canvas_schedule_never_tears_a_frame(g, seed):
+    """multi.canvas_schedule under adversarial interleavings: every rank runs its host-side operations in order, the ranks
+    at arbitrary relative speed.  Rank 0's caller reads frame f from the return of render(f) until it calls render(f + 1)
+    (a `read` step here, right before that call's first operation).  No schedule may deadlock, hand rank 0 an incomplete
+    frame, or let any rank write into the one canvas while frame f may still be read."""
+    rng = np.random.default_rng(1000 * g + seed)
+    frames = 6
+    procs = []
+    for r in range(g):
+        ops = []
+        for f in range(1, frames + 1):
+            ops += [(op, f) for op in multi.canvas_schedule(r, g, f)]
+            if r == 0:
+                ops.append((("read",), f))
+        procs.append(ops)
+    pc = [0] * g
+    consumed, done = 0, [0] * g
+    wrote = [0] * g        # frame whose bands rank r last put into the canvas
+    reading = 0            # frame rank 0's caller may be reading (0: none)
+    while any(pc[r] < len(procs[r]) for r in range(g)):
+        runnable = []
+        for r in range(g):
+            if pc[r] >= len(procs[r]):
+                continue
+            op, f = procs[r][pc[r]]
+            if op[0] == "wait_consumed" and consumed < op[1]:
+                continue
+            if op[0] == "wait_done" and any(done[k] < op[1] for k in range(1, g)):
+                continue
+            runnable.append(r)
+        assert runnable, "deadlock"
+        r = int(rng.choice(runnable))
+        op, f = procs[r][pc[r]]
+        if op[0] == "set_consumed":
+            consumed, reading = op[1], 0
+        elif op[0] == "render":
+            assert reading == 0, f"rank {r} writes frame {f} while frame {reading} is being read"
+            assert wrote[r] == f - 1
+            wrote[r] = f
+        elif op[0] == "set_done":
+            done[r] = op[1]
+        elif op[0] == "read":
+            assert all(w == f for w in wrote), f"frame {f} incomplete when handed out: {wrote}"
+            reading = f
+        pc[r] += 1
+    assert all(w == frames for w in wrote)
+
+
+def _canvas_worker(rank, world_size, port, vsize, width, out_path):
+    import time
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    rtc = importlib.import_module("ray-tracer-challenge-rust_b200")
+    world, cam = rtc.build_scene("table", width, vsize)
+    r = multi.SharedCanvasRenderer(world, cam, rank, world_size, 0, band_rows=8, want_f64=True, want_rgba8=True,
+                                   page_lock=False, timeout_s=30.0)
+    other = multi.SharedCanvasRenderer(world, cam, rank, world_size, 0, name=r.name, page_lock=False) if rank else None
+    f64, rgba = r.views()
+    frame_no = [0]
+
+    def fake_render(scene, stats):  # stand-in for rtc_render + RTC_ROWS_FRAME: this rank's bands, stamped with the frame
+        for b in r.plan.bands_of(rank):
+            rows = slice(b * r.plan.band_rows, (b + 1) * r.plan.band_rows)
+            f64[rows] = frame_no[0] + rank / 16.0
+            rgba[rows] = (frame_no[0], rank, b % 256, 255)
+
+    ok = True
+    for f in range(1, 6):
+        frame_no[0] = f
+        out = r.render(_render=fake_render)
+        if rank == 0:
+            for _ in range(3):  # the caller reads for a while: nobody may write frame f + 1 under it
+                owner = (np.arange(vsize) // r.plan.band_rows) % world_size
+                ok &= bool((out[1][:, :, 0] == f).all() and (out[1][:, 0, 1] == owner).all())
+                ok &= bool(np.array_equal(out[0][:, 0, 0], f + owner / 16.0))
+                time.sleep(0.02)
+    if rank == 0:
+        np.save(out_path, np.array([ok]))
+    if other is not None:
+        other._unmap(unlink=False)
+    r.close()
+    dist.destroy_process_group()
+
+
+def test_gloo_world_size_2_shared_canvas(tmp_path):
+    """Two processes, one canvas in POSIX shared memory (not page-locked: no GPU here), the library's host counters as the
+    only per-frame synchronisation; the name travels by broadcast_object_list at set-up."""
+    port = 31500 + os.getpid() % 2000
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_canvas_worker, args=(2, port, 48, 16, out), nprocs=2, join=True)
+    assert bool(np.load(out)[0])
+
+
+def test_host_counter_wait_times_out_and_share_rejects_bad_names():
+    rtc = importlib.import_module("ray-tracer-challenge-rust_b200")
+    import ctypes as C
+    api = rtc.api()
+    p = C.c_void_p()
+    assert api.host_share_create(-1, b"no-slash", 4096, C.byref(p)) == rtc.RTC_ERR_INVALID
+    name = f"/rtc_test_{os.getpid()}".encode()
+    api.check(api.host_share_create(-1, name, 4096, C.byref(p)))
+    try:
+        q = C.c_void_p()
+        assert api.host_share_create(-1, name, 4096, C.byref(q)) == rtc.RTC_ERR_INVALID      # exists already
+        assert api.host_share_open(-1, name, 1 << 20, C.byref(q)) == rtc.RTC_ERR_INVALID     # smaller than asked for
+        api.check(api.host_share_open(-1, name, 4096, C.byref(q)))
+        api.host_counter_store(C.c_void_p(p.value + 64), 7)
+        assert api.host_counter_load(C.c_void_p(q.value + 64)) == 7                            # the same pages
+        assert api.host_counter_wait(C.c_void_p(q.value + 64), 7, 0.1) == rtc.RTC_OK
+        assert api.host_counter_wait(C.c_void_p(q.value + 64), 8, 0.05) == rtc.RTC_ERR_TIMEOUT
+        api.check(api.host_share_close(q, 4096, None))
+    finally:
+        api.check(api.host_share_close(p, 4096, name))
+    assert not os.path.exists("/dev/shm/" + name.decode().lstrip("/"))
