@@ -360,6 +360,38 @@ def run_b200(args):
     else:
         e2e_d2h = 4 * w * h
     canvas_box[0] = None
+
+    # N > 1, rank 0 alone while the other ranks wait: the same frame through ONE process driving the N devices — what the
+    # reference's (single-process) host gets from the C ABI without torch or a launcher: rtc_multi_create (marshalled World
+    # flattened once, uploaded to every device side by side) -> rtc_multi_render_host (every device renders its bands and
+    # copies their f64 colours to their frame positions in one pinned canvas over its own PCIe link) -> rtc_multi_destroy.
+    one_process = None
+    if world_size > 1 and not args.no_extras:
+        barrier()
+        if rank == 0:
+            try:
+                canvas64 = torch.empty((h, w, 3), dtype=torch.float64).pin_memory().numpy()
+
+                def one_process_step():
+                    m = rtc.MultiRenderer(world, world_size, build=args.e2e_build)
+                    m.render_into(cam, rgb_f64=canvas64)
+                    m.close()
+
+                for _ in range(3):
+                    one_process_step()
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    one_process_step()
+                dt = (time.perf_counter() - t0) / args.steps
+                one_process = {"frame_ms": dt * 1e3, "value": total_rays / dt / 1e6, "unit": "Mrays/s", "devices": world_size,
+                               "d2h_bytes_per_step": 24 * w * h,
+                               "what": "rank 0's process alone drives all N devices: rtc_multi_create -> "
+                                       "rtc_multi_render_host(f64 Canvas into pinned host memory) -> rtc_multi_destroy per "
+                                       "step; wall clock",
+                               "f64_canvas": canvas64}
+            except Exception as e:  # reported, never fatal: the contract's numbers do not depend on this leg
+                one_process = {"error": f"{type(e).__name__}: {e}"}
+        barrier()
     world.set_build("host")
     world.drop_scenes()
     api.marshalled_free(marshalled)
@@ -493,6 +525,8 @@ def run_b200(args):
 
     if pumpkin_line is not None:
         line["pumpkin_at_n"] = pumpkin_line
+    if one_process is not None:
+        line["e2e_one_process"] = one_process
     if world_size > 1:
         # the sharded frame (the last e2e step's, in pinned host memory) against rank 0's own single-GPU render
         whole = torch.empty((h, w, 4), dtype=torch.uint8, device=dev)
@@ -502,15 +536,20 @@ def run_b200(args):
         line["sharded_frame_check"] = {"identical_to_single_gpu_render": same, "bytes": int(whole.numel())}
         if not same:
             raise SystemExit("the sharded frame differs from the single-GPU frame")
-        if canvas_r is not None:
-            # the f64 Canvas the last e2e step left in shared host memory against rank 0's own single-GPU f64 render
+        one_canvas = one_process.pop("f64_canvas", None) if one_process is not None else None
+        if canvas_r is not None or one_canvas is not None:
             whole64 = np.empty((h, w, 3))
             cam.render_into(world, rgb_f64=whole64, device=local_rank)
+        if canvas_r is not None:
+            # the f64 Canvas the last e2e step left in shared host memory against rank 0's own single-GPU f64 render
             same64 = bool(np.array_equal(whole64.view(np.uint64), canvas_r.views()[0].view(np.uint64)))
             line["sharded_frame_check"]["f64_canvas_identical"] = same64
             line["sharded_frame_check"]["f64_bytes"] = int(whole64.nbytes)
             if not same64:
                 raise SystemExit("the sharded f64 canvas differs from the single-GPU canvas")
+        if one_canvas is not None:
+            one_process["identical_to_single_gpu_render"] = bool(
+                np.array_equal(whole64.view(np.uint64), one_canvas.view(np.uint64)))
 
     if not args.no_cpu_baseline and world_size == 1:
         step_px = {"table": 8, "hexagon": 2, "teapot": 64, "cow_teddy": 96, "pumpkin": 192}.get(args.workload, 32)

@@ -212,6 +212,13 @@ typedef struct rtc_multi rtc_multi;
 #define RTC_MULTI_DEVICE_FRAME 1u
 int rtc_multi_create(const rtc_scene_desc* desc, int ngpus, uint32_t build_flags, rtc_multi** out);
 int rtc_multi_render(rtc_multi* m, const rtc_camera_desc* camera, uint32_t where, uint8_t* rgba8_out, rtc_stats* stats);
+/* rtc_render sharded over the devices of `m`, into CALLER host buffers (either may be NULL): rgba8_out (vsize*hsize*4 bytes)
+ * and / or rgb_f64_out (vsize*hsize*3 doubles, the Canvas colours) — every device renders its bands and its copy engine
+ * writes them to their frame positions in these buffers over its own PCIe link, the copies overlapping the rendering
+ * (page-locked buffers — rtc_pinned_alloc — let the copies run at PCIe speed; pageable ones work, staged by the driver).
+ * The sharded form of `rtc_scene_create_ex; rtc_render(scene, camera, NULL, rgba8, rgb_f64, stats)`. */
+int rtc_multi_render_host(rtc_multi* m, const rtc_camera_desc* camera, uint8_t* rgba8_out, double* rgb_f64_out,
+                          rtc_stats* stats);
 const uint8_t* rtc_multi_host_frame(const rtc_multi* m);
 void* rtc_multi_device_frame(const rtc_multi* m);
 void rtc_multi_destroy(rtc_multi* m);
@@ -393,7 +400,13 @@ void rtc_camera_desc_get(const rtc_camera* c, rtc_camera_desc* out);
  * buffers serve the next canvas of that size).  `want_f64` != 0: the canvas holds the f64 colours (canvas.rs:8), as the
  * reference's does — 24 bytes per pixel cross PCIe — and its RGBA8 pixels are quantised from them on the host the first
  * time they are asked for (rtc_canvas_pixels_rgba8, rtc_canvas_to_ppm: canvas.rs:61-63 happens at PPM time there too).
- * `want_f64` = 0: only the RGBA8 frame the kernel quantised (4 bytes per pixel; get_pixel then fails). */
+ * `want_f64` = 0: only the RGBA8 frame the kernel quantised (4 bytes per pixel; get_pixel then fails).
+ * device = RTC_DEVICE_ALL: the frame is sharded over EVERY CUDA device of this process — what the Rust host, one process,
+ * gets on a multi-GPU box without changing a line: the World is marshalled and flattened once and uploaded to each device
+ * (in parallel), the frame's 8-row bands are dealt cyclically, every device renders its bands and its own copy engine writes
+ * them to their frame positions in the one pinned canvas over its own PCIe link.  Same pixels as any single device; stats
+ * are summed over the devices, device_ms is the slowest device's kernel.  With one device it is device 0. */
+#define RTC_DEVICE_ALL (-1)
 int rtc_camera_render(const rtc_camera* c, rtc_world* w, int device, int want_f64, rtc_canvas** out, rtc_stats* stats);
 
 /* canvas.rs:12-58 */

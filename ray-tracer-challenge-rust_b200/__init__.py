@@ -208,7 +208,8 @@ class Camera(CameraHandle):
         return d
 
     def render(self, world, want_f64=True, stats=None, device=0):
-        """Camera::render(&World) -> Canvas.  `stats` (a Stats) receives ray counts and the kernel's device time."""
+        """Camera::render(&World) -> Canvas.  `stats` (a Stats) receives ray counts and the kernel's device time.
+        device=ALL_DEVICES (-1, RTC_DEVICE_ALL): the frame is sharded over every CUDA device of this process."""
         out = C.c_void_p()
         st = stats if stats is not None else None
         self.api.check(self.api.camera_render(self.h, world.h, device, int(bool(want_f64)), C.byref(out),
@@ -242,6 +243,9 @@ class Camera(CameraHandle):
         return self.api.rows_count(C.byref(d), C.byref(rows) if rows is not None else None)
 
 
+ALL_DEVICES = -1  # RTC_DEVICE_ALL
+
+
 class MultiRenderer:
     """rtc_multi_*: one frame sharded over GPUs 0..ngpus-1 of THIS process (no torch, no NCCL).  where="host": every device
     copies its own row bands into one pinned host frame over its own PCIe link; where="device": kernels store straight into
@@ -270,6 +274,14 @@ class MultiRenderer:
         p = C.cast(self.api.multi_host_frame(self.h), C.POINTER(C.c_uint8))
         a = np.ctypeslib.as_array(p, shape=(camera.vsize, camera.hsize, 4))
         return a.copy() if copy else a
+
+    def render_into(self, camera, rgba8=None, rgb_f64=None, stats=None):
+        """rtc_multi_render_host: the sharded frame straight into caller-owned HOST arrays — rgba8 (vsize, hsize, 4) uint8
+        and / or rgb_f64 (vsize, hsize, 3) float64; every device copies its own bands to their frame positions."""
+        d = camera.desc()
+        p8 = rgba8.ctypes.data_as(C.c_void_p) if rgba8 is not None else None
+        p64 = rgb_f64.ctypes.data_as(C.c_void_p) if rgb_f64 is not None else None
+        self.api.check(self.api.multi_render_host(self.h, C.byref(d), p8, p64, C.byref(stats) if stats is not None else None))
 
     def close(self):
         if getattr(self, "h", None):

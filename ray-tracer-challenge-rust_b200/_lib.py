@@ -62,6 +62,7 @@ class RtcApi(BuilderApi):
         f("render_device", C.c_int, vp, C.POINTER(CameraDesc), C.POINTER(Rows), vp, vp, vp, C.c_int, C.POINTER(Stats))
         f("multi_create", C.c_int, vp, C.c_int, C.c_uint32, C.POINTER(vp))
         f("multi_render", C.c_int, vp, C.POINTER(CameraDesc), C.c_uint32, vp, C.POINTER(Stats))
+        f("multi_render_host", C.c_int, vp, C.POINTER(CameraDesc), vp, vp, C.POINTER(Stats))
         f("multi_host_frame", vp, vp)
         f("multi_device_frame", vp, vp)
         f("multi_destroy", None, vp)

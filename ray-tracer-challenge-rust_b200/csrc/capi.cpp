@@ -290,6 +290,17 @@ int rtc_device_count(void) {
 }
 
 /* ---------------------------------------------------------------------------------------------- 1. CORE BOUNDARY */
+static rtc_scene* scene_handle(const FlatScene& flat, DeviceScene* dev) {
+    rtc_scene* s = new rtc_scene();
+    s->dev = dev;
+    s->info[0] = flat.leaf_count;
+    s->info[1] = flat.gates.size();
+    s->info[2] = flat.meshes.size();
+    s->info[3] = flat.tris.size() + flat.device_tris;
+    s->info[4] = flat.bvh.size() + flat.device_nodes;
+    s->info[5] = device_scene_bytes(dev);
+    return s;
+}
 int rtc_scene_create(const rtc_scene_desc* desc, int device, rtc_scene** out) {
     return rtc_scene_create_ex(desc, device, RTC_BUILD_HOST_SAH, out);
 }
@@ -301,15 +312,7 @@ int rtc_scene_create_ex(const rtc_scene_desc* desc, int device, uint32_t flags, 
         DeviceScene* dev = nullptr;
         const int rc = device_scene_create(flat, device, &dev, e, nullptr);
         if (rc != 0) return rc;
-        rtc_scene* s = new rtc_scene();
-        s->dev = dev;
-        s->info[0] = flat.leaf_count;
-        s->info[1] = flat.gates.size();
-        s->info[2] = flat.meshes.size();
-        s->info[3] = flat.tris.size() + flat.device_tris;
-        s->info[4] = flat.bvh.size() + flat.device_nodes;
-        s->info[5] = device_scene_bytes(dev);
-        *out = s;
+        *out = scene_handle(flat, dev);
         return 0;
     });
 }
@@ -421,6 +424,17 @@ int rtc_multi_render(rtc_multi* m, const rtc_camera_desc* camera, uint32_t where
     if (multi_render(m->m, to_dcamera(*camera), where == RTC_MULTI_DEVICE_FRAME, stats ? &ls : nullptr, &frame_ms, &e) != 0)
         return set_err(RTC_ERR_CUDA, e);
     if (rgba8_out) std::memcpy(rgba8_out, multi_host_frame(m->m), (size_t)camera->hsize * camera->vsize * 4);
+    fill_stats(ls, stats);
+    return RTC_OK;
+}
+int rtc_multi_render_host(rtc_multi* m, const rtc_camera_desc* camera, uint8_t* rgba8_out, double* rgb_f64_out,
+                          rtc_stats* stats) {
+    if (!m || !camera) return set_err(RTC_ERR_INVALID, "null argument");
+    if (!affine_camera(*camera)) return set_err(RTC_ERR_UNSUPPORTED, "non-affine camera transform");
+    LaunchStats ls;
+    std::string e;
+    if (multi_render_host(m->m, to_dcamera(*camera), rgba8_out, rgb_f64_out, stats ? &ls : nullptr, &e) != 0)
+        return set_err(RTC_ERR_CUDA, e);
     fill_stats(ls, stats);
     return RTC_OK;
 }
@@ -918,10 +932,88 @@ static const uint8_t* canvas_rgba8(const rtc_canvas* c) {
     return out;
 }
 
+// The world's scene on EVERY device 0 .. ngpus-1: marshalled and flattened once, uploaded to the devices that do not hold it
+// yet in parallel (one host thread per device).
+static int world_scenes_all_locked(rtc_world* w, int ngpus, std::vector<rtc_scene*>* out) {
+    std::vector<int> missing;
+    for (int g = 0; g < ngpus; g++)
+        if (!w->scenes.count(g)) missing.push_back(g);
+    if (!missing.empty()) {
+        Marshalled m;
+        marshal_world(w->w, m);
+        m.desc.recursion_limit = w->recursion_limit;
+        std::vector<rtc_scene*> made(missing.size(), nullptr);
+        const auto drop_made = [&] {
+            for (rtc_scene*& s : made) {
+                rtc_scene_destroy(s);
+                s = nullptr;
+            }
+        };
+        const int rc = flatten_and_upload(&m.desc, w->build_flags, "rtc_camera_render(all devices)",
+                                          [&](const FlatScene& flat, std::string* e) {
+            std::vector<int> rcs(missing.size(), 0);
+            std::vector<std::string> errs(missing.size());
+            const auto upload_one = [&](size_t k) {
+                DeviceScene* dev = nullptr;
+                rcs[k] = device_scene_create(flat, missing[k], &dev, &errs[k], nullptr);
+                if (rcs[k] == 0) made[k] = scene_handle(flat, dev);
+            };
+            std::vector<std::thread> th;
+            for (size_t k = 1; k < missing.size(); k++) th.emplace_back(upload_one, k);
+            upload_one(0);
+            for (auto& t : th) t.join();
+            for (size_t k = 0; k < missing.size(); k++)
+                if (rcs[k] != 0) {  // (a tree too deep for the traversal stack on one device is too deep on all of them)
+                    drop_made();
+                    *e = errs[k];
+                    return rcs[k];
+                }
+            return 0;
+        });
+        if (rc != RTC_OK) return rc;
+        for (size_t k = 0; k < missing.size(); k++) w->scenes.emplace(missing[k], made[k]);
+    }
+    out->clear();
+    for (int g = 0; g < ngpus; g++) out->push_back(w->scenes.at(g));
+    return RTC_OK;
+}
+
+// Camera::render sharded over every CUDA device of this process (RTC_DEVICE_ALL): the frame's 8-row bands are dealt
+// cyclically to the devices, every device renders its bands and its own copy engine writes them to their frame positions in
+// the ONE pinned canvas over its own PCIe link (render_host with the frame layout, one host thread per device).
+static int camera_render_all_locked(const rtc_camera* c, rtc_world* w, int ngpus, int want_f64, rtc_canvas** out,
+                                    rtc_stats* stats) {
+    std::vector<rtc_scene*> scenes;
+    int rc = world_scenes_all_locked(w, ngpus, &scenes);
+    if (rc != RTC_OK) return rc;
+    rtc_camera_desc cd;
+    rtc_camera_desc_get(c, &cd);
+    if (!affine_camera(cd)) return set_err(RTC_ERR_UNSUPPORTED, "non-affine camera transform");
+    rtc_canvas* cv = canvas_alloc(c->c.hsize, c->c.vsize, want_f64 != 0, true, want_f64 == 0);
+    std::vector<DeviceScene*> devs;
+    for (rtc_scene* s : scenes) devs.push_back(s->dev);
+    LaunchStats ls;
+    std::string e;
+    if (render_host_sharded(devs.data(), ngpus, to_dcamera(cd), cv->rgba8, cv->rgb, stats ? &ls : nullptr, &e) != 0) {
+        rtc_canvas_free(cv);
+        return set_err(RTC_ERR_CUDA, e);
+    }
+    fill_stats(ls, stats);
+    *out = cv;
+    return RTC_OK;
+}
+
 int rtc_camera_render(const rtc_camera* c, rtc_world* w, int device, int want_f64, rtc_canvas** out, rtc_stats* stats) {
     if (!c || !w || !out) return set_err(RTC_ERR_INVALID, "null argument");
     *out = nullptr;
     std::lock_guard<std::mutex> lk(w->mu);  // the scene cannot be dropped under the render
+    if (device == RTC_DEVICE_ALL) {
+        std::string ce;
+        const int have = cuda_device_count(&ce);
+        if (have < 1) return set_err(RTC_ERR_CUDA, ce.empty() ? "no CUDA device" : ce);
+        if (have > 1) return camera_render_all_locked(c, w, have, want_f64, out, stats);
+        device = 0;
+    }
     rtc_scene* s = nullptr;
     int rc = world_scene_locked(w, device, &s);
     if (rc != RTC_OK) return rc;

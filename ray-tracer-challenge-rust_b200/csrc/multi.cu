@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device_scene_impl.cuh"
@@ -71,12 +72,22 @@ int multi_create(const FlatScene& flat, int ngpus, MultiRenderer** out, std::str
     m->local.assign(ngpus, nullptr);
     m->local_bytes.assign(ngpus, 0);
     m->done.assign(ngpus, nullptr);
+    {  // the uploads run side by side, one host thread per device (each is a pinned staging copy + one H2D copy + a sync)
+        std::vector<int> rcs(ngpus, 0);
+        std::vector<std::string> errs(ngpus);
+        const auto upload_one = [&](int g) { rcs[g] = device_scene_create(flat, g, &m->scene[g], &errs[g], nullptr); };
+        std::vector<std::thread> th;
+        for (int g = 1; g < ngpus; g++) th.emplace_back(upload_one, g);
+        upload_one(0);
+        for (auto& t : th) t.join();
+        for (int g = 0; g < ngpus; g++)
+            if (rcs[g] != 0) {
+                if (err) *err = errs[g];
+                multi_destroy(m);
+                return rcs[g];
+            }
+    }
     for (int g = 0; g < ngpus; g++) {
-        const int rc = device_scene_create(flat, g, &m->scene[g], err, nullptr);
-        if (rc != 0) {
-            multi_destroy(m);
-            return rc;
-        }
         cudaError_t e = cudaSetDevice(g);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->done[g], cudaEventDisableTiming);
         if (e != cudaSuccess) {
@@ -196,6 +207,57 @@ int multi_render(MultiRenderer* m, const DCamera& cam, bool to_device_frame, Lau
         }
     }
     return 0;
+}
+
+// Camera::render sharded over `n` device scenes of this process into CALLER host buffers (either may be null): the frame's
+// kBandRows-row bands are dealt cyclically, every device renders its bands (in a few launches, so that the copies overlap the
+// rendering: render_host) and its own copy engine writes them to their frame positions over its own PCIe link — one host
+// thread per device, since render_host returns when its copies have landed.  stats: counters summed, device_ms the slowest
+// device's kernel.
+int render_host_sharded(DeviceScene* const* scenes, int n, const DCamera& cam, uint8_t* rgba8, double* rgb_f64,
+                        LaunchStats* stats, std::string* err) {
+    const uint32_t nbands = (cam.vsize + kBandRows - 1) / kBandRows;
+    std::vector<int> rcs(n, 0);
+    std::vector<std::string> errs(n);
+    std::vector<LaunchStats> ls(n);
+    const auto render_one = [&](int g) {
+        DRows r{};
+        r.band_rows = kBandRows;
+        r.band_first = (uint32_t)g;
+        r.band_stride = (uint32_t)n;
+        uint32_t local = 0;
+        for (uint32_t b = (uint32_t)g; b < nbands; b += (uint32_t)n) local += std::min(kBandRows, cam.vsize - b * kBandRows);
+        r.local_rows = local;
+        r.frame_layout = 1;
+        r.row_begin = 0;
+        r.row_count = local;
+        rcs[g] = render_host(scenes[g], cam, r, rgba8, rgb_f64, stats ? &ls[g] : nullptr, &errs[g]);
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < n; g++) th.emplace_back(render_one, g);
+    render_one(0);
+    for (auto& t : th) t.join();
+    for (int g = 0; g < n; g++)
+        if (rcs[g] != 0) {
+            if (err) *err = "device " + std::to_string(g) + ": " + errs[g];
+            return rcs[g];
+        }
+    if (stats) {
+        *stats = LaunchStats{};
+        for (const LaunchStats& l : ls) {
+            stats->primary += l.primary;
+            stats->shadow += l.shadow;
+            stats->reflect += l.reflect;
+            stats->refract += l.refract;
+            stats->launches += l.launches;
+            stats->device_ms = std::max(stats->device_ms, l.device_ms);
+        }
+    }
+    return 0;
+}
+int multi_render_host(MultiRenderer* m, const DCamera& cam, uint8_t* rgba8, double* rgb_f64, LaunchStats* stats,
+                      std::string* err) {
+    return render_host_sharded(m->scene.data(), m->n, cam, rgba8, rgb_f64, stats, err);
 }
 
 void* multi_device_frame(const MultiRenderer* m) { return m->d_frame; }

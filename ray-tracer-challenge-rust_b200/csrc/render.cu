@@ -774,7 +774,7 @@ int host_unregister(void* p, std::string* err) {
 
 void* pinned_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {  // every device's copy engine may write it
         cudaGetLastError();
         return nullptr;
     }

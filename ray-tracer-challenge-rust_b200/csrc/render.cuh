@@ -57,6 +57,12 @@ int multi_create(const FlatScene& flat, int ngpus, MultiRenderer** out, std::str
 void multi_destroy(MultiRenderer* m);
 int multi_render(MultiRenderer* m, const DCamera& cam, bool to_device_frame, LaunchStats* stats, double* frame_ms,
                  std::string* err);
+// The same frame into caller host buffers (RGBA8 and / or the f64 colours), every device copying its own bands to their
+// frame positions; and the underlying call over any set of device scenes of this process.
+int multi_render_host(MultiRenderer* m, const DCamera& cam, uint8_t* rgba8, double* rgb_f64, LaunchStats* stats,
+                      std::string* err);
+int render_host_sharded(DeviceScene* const* scenes, int n, const DCamera& cam, uint8_t* rgba8, double* rgb_f64,
+                        LaunchStats* stats, std::string* err);
 void* multi_device_frame(const MultiRenderer* m);
 const void* multi_host_frame(const MultiRenderer* m);
 int multi_device_count(const MultiRenderer* m);

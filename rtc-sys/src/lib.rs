@@ -22,6 +22,8 @@ pub const RTC_ERR_PANIC: c_int = -2;
 pub const RTC_ERR_CUDA: c_int = -3;
 pub const RTC_ERR_UNSUPPORTED: c_int = -4;
 pub const RTC_ERR_TIMEOUT: c_int = -6;
+/// rtc_camera_render: shard the frame over every CUDA device of the process
+pub const RTC_DEVICE_ALL: c_int = -1;
 
 /// ShapeKind (src/shape.rs:14-39)
 pub const RTC_SPHERE: i32 = 0;
@@ -258,6 +260,14 @@ extern "C" {
         camera: *const rtc_camera_desc,
         where_: u32,
         rgba8_out: *mut u8,
+        stats: *mut rtc_stats,
+    ) -> c_int;
+    /// rtc_render sharded over the devices of `m`, into caller host buffers (RGBA8 and / or the f64 Canvas colours)
+    pub fn rtc_multi_render_host(
+        m: *mut rtc_multi,
+        camera: *const rtc_camera_desc,
+        rgba8_out: *mut u8,
+        rgb_f64_out: *mut f64,
         stats: *mut rtc_stats,
     ) -> c_int;
     pub fn rtc_multi_host_frame(m: *const rtc_multi) -> *const u8;

@@ -473,6 +473,38 @@ def test_multi_device_render_in_one_process(rtc, name, w, h):
 
 # ---- smooth triangles.  Parity UNPINNED against the reference, which does not implement them
 # (intersection.rs:381-386, obj_file.rs:295-335 are commented-out scenarios): the oracle follows the book's definition.
+@pytest.mark.parametrize("name,w,h,build", [("table", 640, 363, "host"), ("cow_teddy", 320, 300, "device")])
+def test_drop_in_call_over_all_devices(rtc, name, w, h, build):
+    """rtc_camera_render(device = RTC_DEVICE_ALL) and rtc_multi_render_host: Camera::render sharded over every device of
+    this process, each device copying its bands into the one canvas — the f64 colours and the RGBA8 pixels are those of a
+    single-device render, bit for bit, and the ray counts add up (on a one-GPU box this is device 0)."""
+    world, cam = rtc.build_scene(name, w, h)
+    world.set_build(build)
+    st1, sta = rtc.Stats(), rtc.Stats()
+    one = cam.render(world, want_f64=True, stats=st1, device=0)
+    f_one, p_one = one.pixels_f64().copy(), one.pixels_rgba8().copy()
+    for _ in range(2):  # the second call finds every device's scene cached
+        allc = cam.render(world, want_f64=True, stats=sta, device=rtc.ALL_DEVICES)
+        assert np.array_equal(allc.pixels_f64().view(np.uint64), f_one.view(np.uint64))
+        assert np.array_equal(allc.pixels_rgba8(), p_one)
+        assert (sta.primary_rays, sta.shadow_rays, sta.reflect_rays, sta.refract_rays) == \
+               (st1.primary_rays, st1.shadow_rays, st1.reflect_rays, st1.refract_rays)
+        assert sta.kernel_launches == rtc.device_count()
+    world.drop_scenes()
+    only8 = cam.render(world, want_f64=False, device=rtc.ALL_DEVICES)
+    assert np.array_equal(only8.pixels_rgba8(), p_one)
+    for ngpus in sorted({1, rtc.device_count()}):
+        m = rtc.MultiRenderer(world, ngpus, build=build)
+        out8, out64 = np.zeros((h, w, 4), dtype=np.uint8), np.zeros((h, w, 3))
+        m.render_into(cam, rgba8=out8, rgb_f64=out64)
+        assert np.array_equal(out8, p_one) and np.array_equal(out64.view(np.uint64), f_one.view(np.uint64))
+        out64[:] = 0
+        stm = rtc.Stats()
+        m.render_into(cam, rgb_f64=out64, stats=stm)
+        assert np.array_equal(out64.view(np.uint64), f_one.view(np.uint64)) and stm.total_rays == st1.total_rays
+        m.close()
+
+
 @pytest.mark.parametrize("seed", range(4))
 @pytest.mark.parametrize("build", ["host", "device"])
 def test_smooth_triangle_worlds_match_oracle(rtc, oracle, seed, build):
