@@ -365,25 +365,41 @@ def run_b200(args):
     # reference's (single-process) host gets from the C ABI without torch or a launcher: rtc_multi_create (marshalled World
     # flattened once, uploaded to every device side by side) -> rtc_multi_render_host (every device renders its bands and
     # copies their f64 colours to their frame positions in one pinned canvas over its own PCIe link) -> rtc_multi_destroy.
+    # (The other ranks wait on a host counter of the shared canvas, not in an NCCL barrier: a barrier's kernel would spin on
+    # their GPUs and time-slice with rank 0's work there.)
     one_process = None
-    if world_size > 1 and not args.no_extras:
+    if world_size > 1 and not args.no_extras and canvas_r is not None:
         barrier()
-        if rank == 0:
+        if rank != 0:
+            canvas_r.wait_signal(1, timeout_s=600.0)
+        else:
             try:
                 canvas64 = torch.empty((h, w, 3), dtype=torch.float64).pin_memory().numpy()
 
+                phase = [0.0, 0.0, 0.0]
+
                 def one_process_step():
+                    t_a = time.perf_counter()
                     m = rtc.MultiRenderer(world, world_size, build=args.e2e_build)
+                    t_b = time.perf_counter()
                     m.render_into(cam, rgb_f64=canvas64)
+                    t_c = time.perf_counter()
                     m.close()
+                    t_d = time.perf_counter()
+                    for k, v in enumerate((t_b - t_a, t_c - t_b, t_d - t_c)):
+                        phase[k] += v
 
                 for _ in range(3):
                     one_process_step()
+                phase[:] = [0.0, 0.0, 0.0]
                 t0 = time.perf_counter()
                 for _ in range(args.steps):
                     one_process_step()
                 dt = (time.perf_counter() - t0) / args.steps
                 one_process = {"frame_ms": dt * 1e3, "value": total_rays / dt / 1e6, "unit": "Mrays/s", "devices": world_size,
+                               "phases_ms": {"marshal + rtc_multi_create": phase[0] / args.steps * 1e3,
+                                             "rtc_multi_render_host": phase[1] / args.steps * 1e3,
+                                             "rtc_multi_destroy": phase[2] / args.steps * 1e3},
                                "d2h_bytes_per_step": 24 * w * h,
                                "what": "rank 0's process alone drives all N devices: rtc_multi_create -> "
                                        "rtc_multi_render_host(f64 Canvas into pinned host memory) -> rtc_multi_destroy per "
@@ -391,6 +407,7 @@ def run_b200(args):
                                "f64_canvas": canvas64}
             except Exception as e:  # reported, never fatal: the contract's numbers do not depend on this leg
                 one_process = {"error": f"{type(e).__name__}: {e}"}
+            canvas_r.signal(1)
         barrier()
     world.set_build("host")
     world.drop_scenes()

@@ -330,7 +330,7 @@ class SharedCanvasRenderer:
         import ctypes as C
         if not (want_f64 or want_rgba8):
             raise ValueError("a canvas needs its f64 colours, its RGBA8 pixels, or both")
-        if world_size > (self.HEADER // 64) - 1:
+        if world_size > (self.HEADER // 64) - 2:
             raise ValueError("too many ranks for the counter block")
         self.world, self.camera, self.rank, self.world_size, self.device = world, camera, rank, world_size, device
         self.api = camera.api
@@ -443,6 +443,18 @@ class SharedCanvasRenderer:
                     api.check(api.host_counter_wait(self._counter(1 + r), op[1], self.timeout_s))
         self._f = f
         return self.views() if self.rank == 0 else None
+
+    AUX_SLOT = 63  # a spare counter of the header for the caller's own host-side hand-shakes (signal / wait_signal)
+
+    def signal(self, value):
+        """Stores `value` into the segment's spare counter (release)."""
+        self.api.host_counter_store(self._counter(self.AUX_SLOT), int(value))
+
+    def wait_signal(self, value, timeout_s=None):
+        """Waits on the CPU — no GPU work, unlike an NCCL barrier, whose kernel spins on the device — until the spare
+        counter reaches `value`."""
+        self.api.check(self.api.host_counter_wait(self._counter(self.AUX_SLOT), int(value),
+                                                  self.timeout_s if timeout_s is None else float(timeout_s)))
 
     def close(self):
         """Collective when set up through torch.distributed: every rank unmaps before rank 0 unlinks the name."""
