@@ -23,7 +23,7 @@ struct DQueue {
 // Slots 0 .. kQueueSlots-2 belong to ONE caller stream each (launches of a stream are ordered, so its slot is never in use
 // by two kernels); the last slot is shared by any further streams, with an event between consecutive launches.
 constexpr int kQueueSlots = 16;
-constexpr int kHostChunks = 4;  // launches a host-output render is cut into at most (render_host)
+constexpr int kHostChunks = 8;  // launches a host-output render is cut into at most (render_host)
 
 // Per-device state created on first use and kept for the life of the process: creating streams, events and querying
 // device properties costs milliseconds, a frame costs less.

@@ -566,8 +566,8 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows_in, uint8_
     //   RGBA8 only (4 B/px): two launches, 3/4 then 1/4 — more, smaller chunks were measured slower at every frame size
     //   (each launch pays its own ramp-up and tail: 8K pumpkin 11.5 ms with 2 chunks, 11.7-12.2 ms with 4-16;
     //   profiles/r01n_host_chunk_sweep.json);
-    //   with the f64 Canvas colours (24 B/px more: the copy, not the kernel, is the long pole — 50 MB at 1080p) four
-    //   launches of 1/8, 1/8, 1/4, 1/2 of the rows: the copy engine starts after an eighth of the frame and never waits.
+    //   with the f64 Canvas colours (24 B/px more: the copy, not the kernel, is the long pole — 50 MB at 1080p) four or
+    //   eight launches (see the weights below): the copy engine starts after a fraction of the frame and hardly waits.
     // Ray counters are per launch; with `stats` requested the frame is rendered in one launch so that the reported kernel
     // time is one kernel's.
     const bool split = !stats && (rgba8 || rgb_f64) && rows.local_rows >= 256;
@@ -597,12 +597,38 @@ int render_host(DeviceScene* s, const DCamera& cam, const DRows& rows_in, uint8_
             for (unit = rows.band_rows; unit % kTileH; unit += rows.band_rows) {}
         const auto tile_rows = [&](uint32_t r) { return std::min(rows.local_rows, (r + unit - 1) / unit * unit); };
         if (rgb_f64) {
-            nchunks = 4;
+            // Relative sizes of the chunks.  The copy (24 B/px at ~55 GB/s) is slower than the rendering, so the call costs
+            // about  first chunk's render + the whole copy + the time the copy engine starves: a small first chunk, then
+            // chunks small enough that the next one is rendered before the last one has crossed, and a small last chunk
+            // (its copy is the only one nothing overlaps).  Eight chunks {1,2,2,2,2,2,2,1} for calls of >= 2 Mpx: the
+            // drop-in call on the 1080p table frame 1.20 -> 1.10 ms, 8K pumpkin 20.3 -> 16.8 ms, teapot and cow & teddy
+            // unchanged (their device mesh build and marshalling dominate); smaller calls — a rank's share of a sharded
+            // frame — keep four {1,1,2,4}: every launch pays its own ~0.05 ms drain.  profiles/r02zo_chunk_sweep.json;
+            // RTC_B200_F64_CHUNKS="w0,w1,..." (up to kHostChunks positive integers) overrides both (tools/chunk_sweep.py).
+            static const std::vector<uint32_t> env_weights = [] {
+                std::vector<uint32_t> w;
+                if (const char* env = std::getenv("RTC_B200_F64_CHUNKS")) {
+                    for (const char* p = env; *p && (int)w.size() < kHostChunks;) {
+                        char* end = nullptr;
+                        const long v = std::strtol(p, &end, 10);
+                        if (end == p) break;
+                        if (v > 0) w.push_back((uint32_t)v);
+                        p = (*end == ',') ? end + 1 : end;
+                        if (*end != ',' ) break;
+                    }
+                }
+                return w;
+            }();
+            static const std::vector<uint32_t> small_call = {1, 1, 2, 4}, large_call = {1, 2, 2, 2, 2, 2, 2, 1};
+            const std::vector<uint32_t>& weights = !env_weights.empty() ? env_weights : px >= 2000000 ? large_call : small_call;
+            nchunks = (int)weights.size();
+            uint64_t total = 0, run = 0;
+            for (uint32_t v : weights) total += v;
             cut[0] = 0;
-            cut[1] = tile_rows(rows.local_rows / 8);
-            cut[2] = tile_rows(rows.local_rows / 4);
-            cut[3] = tile_rows(rows.local_rows / 2);
-            cut[4] = rows.local_rows;
+            for (int k = 0; k < nchunks; k++) {
+                run += weights[k];
+                cut[k + 1] = k + 1 == nchunks ? rows.local_rows : tile_rows((uint32_t)((uint64_t)rows.local_rows * run / total));
+            }
         } else {
             nchunks = 2;
             cut[0] = 0;

@@ -271,9 +271,10 @@ def test_full_size_properties_8k(rtc):
 
 @pytest.mark.parametrize("w,h", [(1280, 720), (2560, 1442), (4096, 2160)])
 def test_host_output_chunks_match_single_launch(rtc, w, h):
-    """rtc_render's chunked path (csrc/render.cu render_host: 2 launches — 3/4 and 1/4 of the rows — for an RGBA8 frame, 4
-    launches — 1/8, 1/8, 1/4, 1/2 — when the f64 Canvas colours are wanted too; each chunk's copy overlaps the next
-    chunk's kernel; ragged last tile row included) returns the one-launch frame."""
+    """rtc_render's chunked path (csrc/render.cu render_host: 2 launches — 3/4 and 1/4 of the rows — for an RGBA8 frame;
+    when the f64 Canvas colours are wanted too, 4 launches — 1/8, 1/8, 1/4, 1/2 — below 2 Mpx (the first size here) and 8
+    launches — weights 1,2,2,2,2,2,2,1 — from there on; each chunk's copy overlaps the next chunk's kernel; ragged last
+    tile row included) returns the one-launch frame."""
     world, cam = rtc.build_scene("cow_teddy", w, h)
     one = np.empty((h, w, 4), dtype=np.uint8)
     two = np.zeros_like(one)
