@@ -370,12 +370,12 @@ class SharedCanvasRenderer:
             # every rank learns whether every rank has the canvas (same collectives on every rank whatever failed locally)
             oks = [None] * world_size
             dist.all_gather_object(oks, failure is None)
+            self.name = name
+            self._owner = rank == 0 and box[0] is not None
             if not all(oks):
-                self._unmap(unlink=(rank == 0 and box[0] is not None))
+                self._unmap(unlink=self._owner)
                 raise RuntimeError("the shared canvas could not be set up on every rank: "
                                    + (f"{type(failure).__name__}: {failure}" if failure else "another rank failed"))
-            self.name = name
-            self._owner = rank == 0
         else:
             self.name = name or self._fresh_name()
             self._owner = rank == 0
@@ -468,3 +468,10 @@ class SharedCanvasRenderer:
             except ImportError:
                 pass
         self._unmap(unlink=self._owner)
+
+    def __del__(self):  # a renderer dropped without close(): unmap, and the creator removes the name (no collective here)
+        try:
+            if getattr(self, "_base", None) is not None:
+                self._unmap(unlink=getattr(self, "_owner", False))
+        except Exception:
+            pass
