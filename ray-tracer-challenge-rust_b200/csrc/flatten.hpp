@@ -427,51 +427,68 @@ class Flattener {
         const double x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
         return 2.0 * (x * y + y * z + z * x);
     }
-    static int skip_build(std::vector<SkipNode>& nodes, const std::vector<detail::Item>& items, std::vector<int> idx) {
+    // (Every split position of every axis is tried with its exact cost: boxes of the two sides from prefix / suffix unions —
+    // min and max are exact, so these are the boxes a fresh fold over each side would give — and the first strictly cheaper
+    // candidate in (axis, cut) order wins.  At most kClusterListMax items: fixed arrays, an insertion sort (stable, like the
+    // std::stable_sort this replaced: the order is the same), no allocation.  The table scene's 17-cube cluster took
+    // 0.14 ms of every scene creation when each cut re-folded both sides and copied index vectors.)
+    static int skip_build(std::vector<SkipNode>& nodes, const std::vector<detail::Item>& items, const int* idx, int n) {
         SkipNode nd;
         for (int a = 0; a < 3; a++) {
             nd.lo[a] = 1e300;
             nd.hi[a] = -1e300;
         }
-        for (int i : idx)
+        for (int k = 0; k < n; k++)
             for (int a = 0; a < 3; a++) {
-                nd.lo[a] = std::fmin(nd.lo[a], items[i].lo[a]);
-                nd.hi[a] = std::fmax(nd.hi[a], items[i].hi[a]);
+                nd.lo[a] = std::fmin(nd.lo[a], items[idx[k]].lo[a]);
+                nd.hi[a] = std::fmax(nd.hi[a], items[idx[k]].hi[a]);
             }
-        nd.leaves = (int)idx.size();
-        if (idx.size() == 1) {
+        nd.leaves = n;
+        if (n == 1) {
             nd.item = idx[0];
             nodes.push_back(nd);
             return (int)nodes.size() - 1;
         }
+        constexpr int kMax = kClusterListMax;
         double best = 1e300;
-        std::vector<int> best_l, best_r;
+        int best_order[kMax], best_cut = 0;
         for (int axis = 0; axis < 3; axis++) {
-            std::vector<int> o = idx;
-            std::stable_sort(o.begin(), o.end(), [&](int x, int y) { return items[x].c[axis] < items[y].c[axis]; });
-            for (size_t cut = 1; cut < o.size(); cut++) {
-                double lo[2][3], hi[2][3];
-                for (int h = 0; h < 2; h++)
-                    for (int a = 0; a < 3; a++) {
-                        lo[h][a] = 1e300;
-                        hi[h][a] = -1e300;
-                    }
-                for (size_t k = 0; k < o.size(); k++) {
-                    const int h = k < cut ? 0 : 1;
-                    for (int a = 0; a < 3; a++) {
-                        lo[h][a] = std::fmin(lo[h][a], items[o[k]].lo[a]);
-                        hi[h][a] = std::fmax(hi[h][a], items[o[k]].hi[a]);
-                    }
+            int o[kMax];
+            for (int k = 0; k < n; k++) {  // stable insertion sort by the centre's coordinate
+                const int v = idx[k];
+                int j = k;
+                while (j > 0 && items[v].c[axis] < items[o[j - 1]].c[axis]) {
+                    o[j] = o[j - 1];
+                    j--;
                 }
-                const double cost = box_area(lo[0], hi[0]) * (double)cut + box_area(lo[1], hi[1]) * (double)(o.size() - cut);
+                o[j] = v;
+            }
+            double slo[kMax + 1][3], shi[kMax + 1][3];  // suffix unions: items o[k .. n)
+            for (int a = 0; a < 3; a++) {
+                slo[n][a] = 1e300;
+                shi[n][a] = -1e300;
+            }
+            for (int k = n - 1; k >= 0; k--)
+                for (int a = 0; a < 3; a++) {
+                    slo[k][a] = std::fmin(slo[k + 1][a], items[o[k]].lo[a]);
+                    shi[k][a] = std::fmax(shi[k + 1][a], items[o[k]].hi[a]);
+                }
+            double plo[3] = {1e300, 1e300, 1e300}, phi[3] = {-1e300, -1e300, -1e300};  // prefix union: items o[0 .. cut)
+            for (int cut = 1; cut < n; cut++) {
+                for (int a = 0; a < 3; a++) {
+                    plo[a] = std::fmin(plo[a], items[o[cut - 1]].lo[a]);
+                    phi[a] = std::fmax(phi[a], items[o[cut - 1]].hi[a]);
+                }
+                const double cost = box_area(plo, phi) * (double)cut + box_area(slo[cut], shi[cut]) * (double)(n - cut);
                 if (cost < best) {
                     best = cost;
-                    best_l.assign(o.begin(), o.begin() + cut);
-                    best_r.assign(o.begin() + cut, o.end());
+                    best_cut = cut;
+                    std::memcpy(best_order, o, sizeof(int) * (size_t)n);
                 }
             }
         }
-        const int l = skip_build(nodes, items, best_l), r = skip_build(nodes, items, best_r);
+        const int l = skip_build(nodes, items, best_order, best_cut);
+        const int r = skip_build(nodes, items, best_order + best_cut, n - best_cut);
         nd.left = l;
         nd.right = r;
         nodes.push_back(nd);
@@ -479,13 +496,18 @@ class Flattener {
     }
     // Expected box tests of subtree n when the nearest tested box above it is node `anc` (-1: none — the walk starts here);
     // memoised per (n, anc).  .second: make n a header in that context.
-    using SkipMemo = std::map<std::pair<int, int>, std::pair<double, bool>>;
+    struct SkipMemo {  // a table over (node, ancestor + 1): at most 63 x 64 entries
+        int nn;
+        std::vector<std::pair<double, bool>> value;
+        std::vector<char> known;
+        explicit SkipMemo(int nodes) : nn(nodes), value((size_t)nodes * (nodes + 1)), known((size_t)nodes * (nodes + 1), 0) {}
+        size_t at(int n, int anc) const { return (size_t)n * (nn + 1) + (size_t)(anc + 1); }
+    };
     static std::pair<double, bool> skip_cost(const std::vector<SkipNode>& nodes, int n, int anc, SkipMemo& memo) {
         const SkipNode& nd = nodes[n];
         if (nd.item >= 0) return {1.0, false};
-        const auto key = std::make_pair(n, anc);
-        const auto it = memo.find(key);
-        if (it != memo.end()) return it->second;
+        const size_t key = memo.at(n, anc);
+        if (memo.known[key]) return memo.value[key];
         const double plain = skip_cost(nodes, nd.left, anc, memo).first + skip_cost(nodes, nd.right, anc, memo).first;
         const double area = box_area(nd.lo, nd.hi);
         const double within = anc >= 0 ? box_area(nodes[anc].lo, nodes[anc].hi) : 0.0;
@@ -493,7 +515,8 @@ class Flattener {
         const double head = 1.0 + p * (skip_cost(nodes, nd.left, n, memo).first + skip_cost(nodes, nd.right, n, memo).first);
         const bool use = anc >= 0 && nd.leaves >= 3 && head < plain;  // anc < 0: the root is never a header
         const std::pair<double, bool> r{use ? head : plain, use};
-        memo.emplace(key, r);
+        memo.value[key] = r;
+        memo.known[key] = 1;
         return r;
     }
     void skip_emit(const std::vector<SkipNode>& nodes, int n, int anc, SkipMemo& memo, bool headers, double pad,
@@ -578,10 +601,11 @@ class Flattener {
             m.root = -1;
             m.entry_base = (int32_t)out_.cluster_entries.size();
             std::vector<SkipNode> nodes;
-            std::vector<int> all(n);
+            nodes.reserve(2 * n);
+            int all[kClusterListMax];
             for (uint32_t k = 0; k < n; k++) all[k] = (int)k;
-            const int root = skip_build(nodes, items, all);
-            SkipMemo memo;
+            const int root = skip_build(nodes, items, all, (int)n);
+            SkipMemo memo((int)nodes.size());
             // the root is never a header, but its box is what the headers beneath it are measured against
             skip_emit(nodes, nodes[root].left, root, memo, opts_.cluster_headers, pad, m.tri_base);
             skip_emit(nodes, nodes[root].right, root, memo, opts_.cluster_headers, pad, m.tri_base);
