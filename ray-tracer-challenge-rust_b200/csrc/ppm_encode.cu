@@ -3,11 +3,11 @@
 //
 // The format's only sequential dependence is the 70-column line wrap, and it restarts at every image row
 // (canvas.rs:34), so rows are independent:
-//   1. ppm_row_bytes_kernel — one thread per row walks the row's 3*W channel values with the reference's wrap rule,
-//      counts the row's bytes and notes where every text line starts;
+//   1. ppm_row_bytes_kernel — one WARP per row, 32 channel values at a time: the wrap rule in prefix form (a warp scan + a
+//      ballot per line break) counts the row's bytes and notes where every text line starts;
 //   2. ppm_row_offsets_kernel — exclusive prefix sum of the row sizes (one block; H is at most a few thousand);
-//   3. ppm_line_write_kernel — one CTA per row, one thread per text LINE (pass 1 recorded where each line starts):
-//      digits, single spaces and the line's newline, written in place.
+//   3. ppm_line_write_kernel — one CTA per row, one WARP per text LINE (pass 1 recorded where each line starts), one lane
+//      per token: digits, single spaces and the line's newline, written in place, neighbouring lanes to neighbouring bytes.
 // Byte/integer work, bound by HBM writes of ~12 bytes per pixel; no floating point at all.
 #include <cuda_runtime.h>
 
@@ -22,48 +22,61 @@ namespace rtc {
 
 namespace {
 
-// canvas.rs:44-55 for one token of n digits: returns the bytes it adds (separator + digits) and updates the line length
-__device__ __forceinline__ unsigned ppm_token(unsigned& len, unsigned n, bool& newline) {
-    unsigned add = n;
-    newline = false;
-    if (len + n + 1 > 70) {
-        newline = true;
-        add += 1;
-        len = 0;
+// The wrap rule (canvas.rs:44-55) in prefix form.  A token of n digits costs a = n + 1 characters (its digits and the space
+// before it); with P_t the running sum of a over the row's tokens, a line that starts at token s holds the tokens t with
+// P_t - P_{s-1} <= 71 (its length is that sum minus the first token's missing space, and the rule allows 70), the byte at
+// which it starts inside the row is P_{s-1} (every earlier token's digits and one separator each — space or newline), and
+// the row's size with its final newline is P of its last token.
+__device__ __forceinline__ unsigned ppm_token_chars(const uchar4* __restrict__ row, unsigned tok, unsigned& value) {
+    const uchar4 p = row[tok / 3u];
+    const unsigned c = tok % 3u;
+    value = c == 0 ? p.x : (c == 1 ? p.y : p.z);
+    return 2u + (value >= 10u) + (value >= 100u);
+}
+__device__ __forceinline__ unsigned warp_inclusive_scan(unsigned v, unsigned lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= (unsigned)off) v += o;
     }
-    if (len > 0) {
-        add += 1;  // the separating space (a newline resets len to 0, so the two never combine)
-        len += 1;
-    }
-    len += n;
-    return add;
+    return v;
 }
 
-// pass 1: the wrap rule is a sequential walk of the row's tokens — do it once, per row, and write down where every LINE of
-// the row starts (token index and byte offset inside the row) so that pass 3 can give every line its own thread
+// pass 1: one WARP per image row, 32 tokens at a time — a warp scan gives every token its P, a ballot finds the first token
+// that no longer fits the current line (at most three per 32 tokens: a line holds at least 17), and the lane that owns it
+// writes down where its line starts (token index, byte offset inside the row) so that pass 3 can give every line a warp
 __global__ void ppm_row_bytes_kernel(const uchar4* __restrict__ px, unsigned width, unsigned height, unsigned max_lines,
                                      unsigned long long* __restrict__ row_bytes, unsigned* __restrict__ row_lines,
                                      uint2* __restrict__ lines) {
-    const unsigned y = blockIdx.x * blockDim.x + threadIdx.x;
-    if (y >= height) return;
+    const unsigned y = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (y >= height) return;  // whole warps leave together
     const uchar4* row = px + (size_t)y * width;
     uint2* mine = lines + (size_t)y * max_lines;
-    unsigned len = 0, bytes = 0, nlines = 0, tok = 0;
-    mine[nlines++] = make_uint2(0u, 0u);
-    for (unsigned x = 0; x < width; x++) {
-        const uchar4 p = row[x];
-        const unsigned v[3] = {p.x, p.y, p.z};
-#pragma unroll
-        for (int c = 0; c < 3; c++, tok++) {
-            const unsigned n = 1u + (v[c] >= 10u) + (v[c] >= 100u);
-            bool nl;
-            const unsigned add = ppm_token(len, n, nl);
-            if (nl) mine[nlines++] = make_uint2(tok, bytes + 1);  // the line starts after the newline character
-            bytes += add;
+    const unsigned ntok = 3u * width;
+    unsigned run = 0;   // P of the last token of the chunks before this one
+    unsigned base = 0;  // P just before the current line's first token
+    unsigned nlines = 1;
+    if (lane == 0) mine[0] = make_uint2(0u, 0u);
+    for (unsigned t0 = 0; t0 < ntok; t0 += 32) {
+        const unsigned t = t0 + lane;
+        unsigned v, a = t < ntok ? ppm_token_chars(row, t, v) : 0u;
+        const unsigned P = run + warp_inclusive_scan(a, lane);
+        run = __shfl_sync(0xffffffffu, P, 31);
+        unsigned from = 0;  // lanes >= from are not placed yet
+        for (;;) {
+            const unsigned over = __ballot_sync(0xffffffffu, t < ntok && lane >= from && P - base > 71u);
+            if (!over) break;
+            const unsigned j = (unsigned)__ffs((int)over) - 1u;
+            base = __shfl_sync(0xffffffffu, P - a, (int)j);  // P of the token before j
+            if (lane == j) mine[nlines] = make_uint2(t, base);
+            nlines++;
+            from = j + 1;  // token j opens the line and always fits
         }
     }
-    row_bytes[y] = (unsigned long long)bytes + 1;  // the newline that ends the row (canvas.rs:56)
-    row_lines[y] = nlines;
+    if (lane == 0) {
+        row_bytes[y] = run;  // includes the newline that ends the row (canvas.rs:56)
+        row_lines[y] = nlines;
+    }
 }
 
 // one block: row_off[y] = header + sum of row_bytes[0..y); total at row_off[height]
@@ -94,30 +107,36 @@ __global__ void ppm_row_offsets_kernel(const unsigned long long* __restrict__ ro
     }
 }
 
-// pass 3: one CTA per row, one thread per text line (<= 70 characters): digits, single spaces, the line's newline
+// pass 3: one CTA per row, one WARP per text line (<= 70 characters, <= 35 tokens), one lane per token: a warp scan places
+// every token inside the line, so the lanes' byte stores of one instruction fall side by side in the same few sectors
 __global__ void ppm_line_write_kernel(const uchar4* __restrict__ px, unsigned width, unsigned max_lines,
                                       const unsigned long long* __restrict__ row_off,
                                       const unsigned* __restrict__ row_lines, const uint2* __restrict__ lines,
                                       char* __restrict__ out) {
-    const unsigned y = blockIdx.x;
+    const unsigned y = blockIdx.x, lane = threadIdx.x & 31u;
     const uchar4* row = px + (size_t)y * width;
     const uint2* mine = lines + (size_t)y * max_lines;
     const unsigned nlines = row_lines[y], ntok = 3u * width;
     char* base = out + row_off[y];
-    for (unsigned k = threadIdx.x; k < nlines; k += blockDim.x) {
+    for (unsigned k = threadIdx.x >> 5; k < nlines; k += blockDim.x >> 5) {
         const uint2 ln = mine[k];
         const unsigned end = (k + 1 < nlines) ? mine[k + 1].x : ntok;
         char* o = base + ln.y;
-        for (unsigned tok = ln.x; tok < end; tok++) {
-            const uchar4 p = row[tok / 3u];
-            const unsigned c = tok % 3u;
-            const unsigned v = c == 0 ? p.x : (c == 1 ? p.y : p.z);
-            if (tok != ln.x) *o++ = ' ';
-            if (v >= 100u) *o++ = (char)('0' + v / 100u);
-            if (v >= 10u) *o++ = (char)('0' + (v / 10u) % 10u);
-            *o++ = (char)('0' + v % 10u);
+        unsigned run = 0;  // characters of the line's tokens in the chunks before this one
+        for (unsigned t0 = ln.x; t0 < end; t0 += 32) {
+            const unsigned t = t0 + lane;
+            unsigned v = 0, a = t < end ? ppm_token_chars(row, t, v) : 0u;
+            const unsigned p = warp_inclusive_scan(a, lane);
+            if (t < end) {
+                char* q = o + run + p - a;  // the token's first digit; its separating space sits just before it
+                if (t != ln.x) q[-1] = ' ';
+                if (v >= 100u) *q++ = (char)('0' + v / 100u);
+                if (v >= 10u) *q++ = (char)('0' + (v / 10u) % 10u);
+                *q++ = (char)('0' + v % 10u);
+                if (t + 1 == end) *q = '\n';  // ends the line — for the row's last line the row terminator (canvas.rs:56)
+            }
+            run += __shfl_sync(0xffffffffu, p, 31);
         }
-        *o = '\n';  // ends the line — for the row's last line this is the row terminator (canvas.rs:56)
     }
 }
 
@@ -161,11 +180,11 @@ int ppm_encode_device(int device, const void* d_rgba8, uint64_t width, uint64_t 
     int rc = 0;
     if (e == cudaSuccess) {
         const unsigned h = (unsigned)height, w = (unsigned)width;
-        // 32-thread blocks: rows are long sequential walks, spread them over as many SMs as there are
-        ppm_row_bytes_kernel<<<(h + 31) / 32, 32, 0, st>>>((const uchar4*)d_rgba8, w, h, max_lines, d_bytes, d_nlines,
-                                                           d_lines);
+        // four rows (warps) per block
+        ppm_row_bytes_kernel<<<(h + 3) / 4, 128, 0, st>>>((const uchar4*)d_rgba8, w, h, max_lines, d_bytes, d_nlines,
+                                                          d_lines);
         ppm_row_offsets_kernel<<<1, 1024, 0, st>>>(d_bytes, h, (unsigned long long)hl, d_off);
-        ppm_line_write_kernel<<<h, 128, 0, st>>>((const uchar4*)d_rgba8, w, max_lines, d_off, d_nlines, d_lines, d_text);
+        ppm_line_write_kernel<<<h, 256, 0, st>>>((const uchar4*)d_rgba8, w, max_lines, d_off, d_nlines, d_lines, d_text);
         e = cudaGetLastError();
     }
     unsigned long long total = 0;
