@@ -187,3 +187,63 @@ def test_obj_numbers_are_correctly_rounded(rtc):
             assert got.tobytes() == want.tobytes(), (lines[i], got, want)
     finally:
         api.marshalled_free(m)
+
+
+def test_wrap_rule_in_prefix_form_equals_the_sequential_rule(rtc):
+    """csrc/ppm_encode.cu runs Canvas::to_ppm's 70-column wrap (canvas.rs:44-55) in PREFIX form, 32 tokens per step: a token
+    of n digits costs a = n + 1 characters; with P the running sum of a over a row's tokens, a line that starts at token s
+    holds the tokens t with P_t - P_{s-1} <= 71, starts at byte P_{s-1} of the row, and the row (with its final newline) is
+    P_last bytes.  Restated here step for step (chunks of 32, the first token over the limit opens a line) and compared
+    with the sequential host encoder on every digit count and wrap position; the kernels themselves are compared byte for
+    byte on the GPU (tests/test_gpu_parity.py::test_device_ppm_encoder_is_byte_identical)."""
+    def prefix_form(rgba):
+        h, w, _ = rgba.shape
+        out = bytearray(f"P3\n{w} {h}\n255\n".encode())
+        for y in range(h):
+            vals = rgba[y, :, :3].reshape(-1).astype(np.int64)
+            ntok = len(vals)
+            a_all = 2 + (vals >= 10) + (vals >= 100)
+            run, base, lines = 0, 0, [(0, 0)]
+            for t0 in range(0, ntok, 32):  # pass 1: a warp per row
+                a = np.zeros(32, dtype=np.int64)
+                m = min(32, ntok - t0)
+                a[:m] = a_all[t0:t0 + m]
+                P = run + np.cumsum(a)
+                run, start = int(P[31]), 0
+                while True:
+                    over = [l for l in range(start, m) if P[l] - base > 71]
+                    if not over:
+                        break
+                    j = over[0]
+                    base = int(P[j] - a[j])
+                    lines.append((t0 + j, base))
+                    start = j + 1
+            row = bytearray(run)
+            for k, (s, off) in enumerate(lines):  # pass 3: a warp per line, a lane per token
+                end = lines[k + 1][0] if k + 1 < len(lines) else ntok
+                assert end - s <= 35
+                before = 0
+                for t in range(s, end):
+                    q = off + before
+                    if t != s:
+                        row[q - 1] = 32
+                    digits = str(int(vals[t])).encode()
+                    row[q:q + len(digits)] = digits
+                    if t + 1 == end:
+                        row[q + len(digits)] = 10
+                    before += int(a_all[t])
+            out += row
+        return bytes(out)
+
+    rng = np.random.default_rng(5)
+    for h, w in ((3, 5), (2, 17), (4, 23), (2, 24), (3, 36), (2, 100), (1, 1), (2, 12), (1, 641)):
+        for mode in range(4):
+            if mode == 0:
+                img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+            elif mode == 1:
+                img = rng.integers(0, 10, (h, w, 4), dtype=np.uint8)
+            elif mode == 2:
+                img = np.full((h, w, 4), 255, dtype=np.uint8)
+            else:
+                img = rng.choice(np.array([0, 9, 10, 99, 100, 255], dtype=np.uint8), (h, w, 4))
+            assert prefix_form(img) == rtc.ppm_from_rgba8(img, w, h), (h, w, mode)
