@@ -33,6 +33,11 @@ SMI_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.acti
              "clocks_event_reasons.sw_power_cap")
 
 
+# config.l2, word for word the same in both arms
+L2_NOTE = ("B200 arm: 256 MiB device memset (> the 126 MB L2) between steps, outside the per-step CUDA-event brackets; "
+           "reference arm: CPU, no device cache to flush")
+
+
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -114,7 +119,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
         "frame_ms_extrapolated": secs / args.steps * 1e3 * (w * h / max(npx, 1)),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload} {w}x{h}", "scene": args.workload, "hsize": w, "vsize": h},
+        "config": {"workload": f"{args.workload} {w}x{h}", "scene": args.workload, "hsize": w, "vsize": h, "l2": L2_NOTE},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -488,15 +493,17 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload} {w}x{h}", "scene": args.workload, "hsize": w, "vsize": h,
-                   "rays_per_frame": {"primary": rays[0], "shadow": rays[1], "reflect": rays[2], "refract": rays[3]},
-                   "sharding": (f"cyclic {renderer.plan.band_rows}-row bands over {world_size} ranks; "
-                                + ("kernels store straight into rank 0's frame over NVLink peer mapping, one barrier"
-                                   if renderer.mode == "peer" else "NCCL gather to rank 0 + one interleaving copy"))
-                   if world_size > 1 else "single GPU, one launch per frame",
-                   "exchange": renderer.mode,
-                   "l2": "256 MiB device memset between steps, outside the per-step CUDA-event brackets",
-                   "flattened": info},
+        # the same dictionary in both arms (the driver compares them); everything that describes THIS arm's run is in
+        # config_detail
+        "config": {"workload": f"{args.workload} {w}x{h}", "scene": args.workload, "hsize": w, "vsize": h, "l2": L2_NOTE},
+        "config_detail": {
+            "rays_per_frame": {"primary": rays[0], "shadow": rays[1], "reflect": rays[2], "refract": rays[3]},
+            "sharding": (f"cyclic {renderer.plan.band_rows}-row bands over {world_size} ranks; "
+                         + ("kernels store straight into rank 0's frame over NVLink peer mapping, completion counters"
+                            if renderer.mode == "peer" else "NCCL gather to rank 0 + one interleaving copy"))
+            if world_size > 1 else "single GPU, one launch per frame",
+            "exchange": renderer.mode,
+            "flattened": info},
         "frame_ms": ms_per_step, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "sustained": {"frames": n_sustain, "frame_ms": sustained_ms, "mrays_s": total_rays / sustained_ms / 1e3,
                       "what": "back-to-back frames for about a second, no L2 flush, one device timing around all"},

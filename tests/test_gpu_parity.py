@@ -566,7 +566,7 @@ def test_two_process_peer_exchange_renders_the_single_gpu_frame(rtc):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().split("\n")[-1])
-    assert line["n_gpus"] == 2 and line["config"]["exchange"] == "peer"
+    assert line["n_gpus"] == 2 and line["config_detail"]["exchange"] == "peer"
     assert line["sharded_frame_check"]["identical_to_single_gpu_render"] is True
     # the e2e loops ran through the canvas in shared host memory, and it held the single-GPU render's f64 colours
     assert line["e2e"]["exchange"] == "shared host canvas" and line["sharded_frame_check"]["f64_canvas_identical"] is True
